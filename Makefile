@@ -1,0 +1,48 @@
+# Build of the B200-native IMSAME hot path.
+#   make            host library, GPU library (sm_100a), CLI binaries
+#   make oracle     test-only CPU restatement (oracle/_build/liboracle.so)
+#   make ref        the unmodified reference compiled from /root/reference/src into oracle/_ref/
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CC        ?= gcc
+CFLAGS    ?= -O3 -fPIC -Wall -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE -fopenmp
+NVFLAGS   ?= -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+             -Xcompiler -fPIC,-Wall,-fopenmp -Xptxas -v
+OUT       := imsame_b200/_lib
+HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/host/synth.c \
+             imsame_b200/host/render.c
+GPU_SRC   := imsame_b200/csrc/capi.cu
+GPU_HDR   := $(wildcard imsame_b200/csrc/*.cuh) include/imsame_gpu.h
+
+all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so bin/IMSAME bin/revComp
+
+$(OUT)/libimsame_host.so: $(HOST_SRC) imsame_b200/host/imsame_host.h include/imsame_gpu.h
+	@mkdir -p $(OUT)
+	$(CC) $(CFLAGS) -shared $(HOST_SRC) -lm -o $@
+
+$(OUT)/libimsame_gpu.so: $(GPU_SRC) $(GPU_HDR) imsame_b200/host/thresholds.c
+	@mkdir -p $(OUT)
+	$(CC) $(CFLAGS) -c imsame_b200/host/thresholds.c -o $(OUT)/thresholds.o
+	$(NVCC) $(NVFLAGS) -shared $(GPU_SRC) $(OUT)/thresholds.o -o $@ 2> $(OUT)/ptxas.log || (cat $(OUT)/ptxas.log; false)
+	@grep -E "error|warning|spill" $(OUT)/ptxas.log | grep -v "0 bytes spill" || true
+
+bin/IMSAME: imsame_b200/host/imsame_main.c $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
+	@mkdir -p bin
+	$(CC) $(CFLAGS) -fPIE imsame_b200/host/imsame_main.c -L$(OUT) -limsame_host -limsame_gpu \
+	    -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lm -o $@
+
+bin/revComp: imsame_b200/host/revcomp_main.c
+	@mkdir -p bin
+	$(CC) $(CFLAGS) -fPIE imsame_b200/host/revcomp_main.c -o $@
+
+oracle: oracle/_build/liboracle.so
+oracle/_build/liboracle.so: oracle/imsame_oracle.c oracle/imsame_oracle.h
+	@mkdir -p oracle/_build
+	$(CC) -O2 -fPIC -Wall -shared oracle/imsame_oracle.c -lm -o $@
+
+ref:
+	sh oracle/build_ref.sh
+
+clean:
+	rm -rf $(OUT) bin oracle/_build
+
+.PHONY: all oracle ref clean

@@ -1,0 +1,157 @@
+/*
+ * imsame_gpu.h -- C ABI of the B200-native IMSAME alignment hot path.
+ *
+ * The reference (Bitlab-UMA/IMSAME) has no plugin or FFI interface: its hot
+ * path is the pthread entry point
+ *     void *computeAlignmentsByThread(void *HashTableArgs)     (src/alignmentFunctions.h:51,
+ *                                                               src/alignmentFunctions.c:43-208)
+ * fed by `HashTableArgs` (src/alignmentFunctions.h:10-30) and fanned out from
+ * main (src/IMSAME.c:409-467) over a seed index built at src/IMSAME.c:232-281.
+ * This library replaces exactly that: index build + query scan + ungapped
+ * extension + NW/identity filter + first-accepted hit per read.  Everything is
+ * plain pointers and sizes; no torch / C++ types cross the boundary.
+ *
+ * Error convention: functions return 0 or a negative IMSAME_E* code and never
+ * call exit(); the CLI turns codes into the reference's `terror` text
+ * (src/commonFunctions.c:10-13).  There is no CPU fallback: every entry point
+ * that computes fails with IMSAME_ENODEV when no sm_100 device is usable.
+ */
+#ifndef IMSAME_GPU_H
+#define IMSAME_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMSAME_MAX_READ_SIZE 3000 /* src/structs.h:19 */
+#define IMSAME_FIXED_K 12         /* src/structs.h:15 */
+
+enum {
+    IMSAME_OK = 0,
+    IMSAME_ENODEV = -1,    /* no CUDA device / wrong architecture */
+    IMSAME_ECUDA = -2,     /* CUDA runtime error (see imsame_gpu_last_cuda_error) */
+    IMSAME_EARG = -3,      /* bad argument */
+    IMSAME_ENOMEM = -4,    /* host or device allocation failed */
+    IMSAME_EREADSIZE = -5, /* "Read size reached for gapped alignment." (src/alignmentFunctions.c:155) */
+    IMSAME_ESTATE = -6,    /* call order violated (e.g. run before set_query) */
+    IMSAME_ELIMIT = -7     /* input exceeds an implementation limit (documented in DESIGN.md) */
+};
+
+/* Replaces SeqInfo (src/structs.h:40-45), filled like src/IMSAME.c:199-226,323-347:
+ * `sequences` holds upper-case A/C/G/T only, reads concatenated without
+ * separators; start_pos[r] = offset of read r (n_seqs entries are read).
+ * The reference keeps one more fact implicitly in its k-mer table: database
+ * words are reset by dropped non-ACGT characters (src/IMSAME.c:229-231).
+ * break_pos[] lists, ascending, the index of the first kept base after such a
+ * character (NULL / 0 when the FASTA had none).  Ignored for the query. */
+typedef struct imsame_seqinfo {
+    const unsigned char *sequences;
+    const uint64_t *start_pos;
+    uint64_t total_len;
+    uint64_t n_seqs;
+    const uint64_t *break_pos;
+    uint64_t n_breaks;
+} imsame_seqinfo;
+
+/* The value-carrying part of HashTableArgs (src/alignmentFunctions.h:10-30). */
+typedef struct imsame_params {
+    long double min_e_value;  /* hta->min_e_value  */
+    long double min_coverage; /* hta->min_coverage */
+    long double min_identity; /* hta->min_identity */
+    int igap, egap;           /* negated, exactly as stored in hta (src/IMSAME.c:565,568) */
+    uint64_t n_threads;       /* -n_threads: only defines chunk starts (src/IMSAME.c:414,433) */
+    /* database sharding (multi-GPU): coordinates of this shard in the whole database */
+    uint64_t db_total_len_global; /* 0 = this shard is the whole database */
+    uint64_t db_pos_base;         /* global index of the shard's first base */
+    uint64_t db_seq_base;         /* global index of the shard's first read */
+} imsame_params;
+
+/* Result per query read = what src/alignmentFunctions.c:163-173 would print. */
+typedef struct imsame_best {
+    uint64_t db_seq;      /* curr_db_seq (global) */
+    uint64_t qpos_end;    /* curr_pos of the accepting k-mer */
+    uint64_t db_pos;      /* aux->pos of the accepting hit (global) */
+    uint32_t length;      /* ba.length */
+    uint32_t identities;  /* ba.identities */
+    uint32_t accepted;    /* 1 if the read produced a record */
+    uint32_t reserved;
+} imsame_best;
+
+typedef struct imsame_stats {
+    uint64_t n_query_kmers; /* entries of the query word table (K1) */
+    uint64_t n_db_kmers;    /* database words scanned (K2) */
+    uint64_t n_hits;        /* seed hits extended (K2) */
+    uint64_t n_evalue_pass; /* hits below the e-value threshold (K2) */
+    uint64_t n_pairs;       /* distinct (read, db_seq) candidates (K2b) */
+    uint64_t n_pairs_dp;    /* candidates actually run through NW (K3) */
+    uint64_t n_cells;       /* NW cells evaluated (K3): sum (xlen-1)(ylen-1) */
+    uint64_t n_accepted;    /* reads with a record */
+    float ms_pack_query, ms_k1, ms_pack_db, ms_k2, ms_k2b, ms_k3, ms_select;
+    float ms_h2d, ms_d2h, ms_total;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t k2_launches, k3_launches, total_launches;
+    uint32_t reserved;
+} imsame_stats;
+
+typedef struct imsame_ctx imsame_ctx;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int imsame_gpu_create(imsame_ctx **ctx, int device);
+void imsame_gpu_destroy(imsame_ctx *ctx);
+const char *imsame_gpu_strerror(int code);
+const char *imsame_gpu_last_cuda_error(const imsame_ctx *ctx);
+/* run all work of this context on an existing cudaStream_t (NULL = own stream) */
+int imsame_gpu_set_stream(imsame_ctx *ctx, void *cuda_stream);
+
+/* ---- one call = src/IMSAME.c:232-281 + :409-467 ------------------------ */
+/* Host buffers in, host records out (nq entries, caller-owned). */
+int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
+                     const imsame_params *params, imsame_best *out, imsame_stats *stats);
+
+/* ---- staged form (device-resident inputs; used for sharded databases) --- */
+/* upload + 2-bit pack + build the query word table (K1) */
+int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *query, const imsame_params *params);
+/* upload + 2-bit pack one database shard; stays resident until replaced */
+int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db);
+/* scan + extension + NW + filter over the resident shard. Results stay on the
+ * device as one packed key per read (smaller = earlier in the reference's scan
+ * order; IMSAME_KEY_NONE = no record) and one payload word.  d_keys/d_payload:
+ * device buffers of nq uint64 each supplied by the caller (e.g. NCCL buffers),
+ * or NULL to use the context's own. */
+int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *params, uint64_t *d_keys,
+                   uint64_t *d_payload, imsame_stats *stats);
+/* after a min-reduction of the keys across shards: zero the payload of every
+ * read this shard does not own, so that a max-reduction yields the owner's */
+int imsame_gpu_mask_payload(imsame_ctx *ctx, const uint64_t *d_keys_reduced,
+                            const uint64_t *d_keys_local, uint64_t *d_payload);
+/* decode (reduced) device keys/payload into host records */
+int imsame_gpu_fetch(imsame_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_payload,
+                     imsame_best *out);
+
+#define IMSAME_KEY_NONE 0x7FFFFFFFFFFFFFFFull
+
+/* ---- NW on explicit pairs (src/alignmentFunctions.c:389-560 in isolation) */
+/* X[i] / Y[i]: ASCII reads; out5[i*5..] = score, bx, by, length, identities */
+int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *const *X,
+                        const uint32_t *xlen, const unsigned char *const *Y, const uint32_t *ylen,
+                        int igap, int egap, int32_t *out5, float *ms_kernel);
+
+/* ---- winners-only traceback (src/alignmentFunctions.c:493-560) ---------- */
+/* For each accepted read of `best`, recompute NW with back-pointers on the
+ * device and return the path as run-length ops; see imsame_host.h for the
+ * renderer that turns them into the reference's text. ops_off has nq+1 entries. */
+int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
+                         const imsame_params *params, const imsame_best *best, uint64_t *ops_off,
+                         uint32_t **ops /* malloc'ed by the library, free with imsame_gpu_free */,
+                         uint32_t *bc_xy /* 2 per read: best cell x, y */);
+void imsame_gpu_free(void *p);
+
+/* pinned host memory helpers for callers that want full-speed copies */
+void *imsame_gpu_host_alloc(uint64_t bytes);
+void imsame_gpu_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
