@@ -3,17 +3,18 @@
 #   make oracle     test-only CPU restatement (oracle/_build/liboracle.so)
 #   make ref        the unmodified reference compiled from /root/reference/src into oracle/_ref/
 NVCC      ?= /usr/local/cuda/bin/nvcc
-CC        ?= gcc
-CFLAGS    ?= -O3 -fPIC -Wall -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE -fopenmp
-NVFLAGS   ?= -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
-             -Xcompiler -fPIC,-Wall,-fopenmp -Xptxas -v
+# the image exports CC=/opt/gcc/bin/gcc, a relocated gcc without libgomp.spec: use the system one
+CC        := $(firstword $(wildcard /usr/bin/gcc) gcc)
+OMPFLAG   := $(shell echo 'int main(){return 0;}' | $(CC) -fopenmp -x c - -o /dev/null 2>/dev/null && echo -fopenmp)
+CFLAGS    := -O3 -fPIC -Wall -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE $(OMPFLAG)
+NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+             -Xcompiler -fPIC,-Wall -Xptxas -v
 OUT       := imsame_b200/_lib
-HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/host/synth.c \
-             imsame_b200/host/render.c
+HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/host/synth.c
 GPU_SRC   := imsame_b200/csrc/capi.cu
 GPU_HDR   := $(wildcard imsame_b200/csrc/*.cuh) include/imsame_gpu.h
 
-all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so bin/IMSAME bin/revComp
+all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
 
 $(OUT)/libimsame_host.so: $(HOST_SRC) imsame_b200/host/imsame_host.h include/imsame_gpu.h
 	@mkdir -p $(OUT)
@@ -34,6 +35,10 @@ bin/revComp: imsame_b200/host/revcomp_main.c
 	@mkdir -p bin
 	$(CC) $(CFLAGS) -fPIE imsame_b200/host/revcomp_main.c -o $@
 
+tools: tools/int_peak
+tools/int_peak: tools/int_peak.cu
+	$(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -o $@ tools/int_peak.cu
+
 oracle: oracle/_build/liboracle.so
 oracle/_build/liboracle.so: oracle/imsame_oracle.c oracle/imsame_oracle.h
 	@mkdir -p oracle/_build
@@ -45,4 +50,4 @@ ref:
 clean:
 	rm -rf $(OUT) bin oracle/_build
 
-.PHONY: all oracle ref clean
+.PHONY: all oracle ref clean tools

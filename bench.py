@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native IMSAME hot path.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (reference CPU arm)
+
+Workload (BASELINE.json): configs[1] = 1 M x 250 bp Illumina-like query reads against a
+10 M-read synthetic metagenome on one B200.  For N > 1 the database grows to N x 10 M
+reads (configs[2] at N = 8: 80 M reads), sharded by contiguous read ranges, one shard per
+GPU, the query replicated, followed by one NCCL min-reduction of the packed best-hit keys
+and a max-reduction of the owner's payload (weak scaling: per-GPU work fixed).
+
+A "step" = one pass of the hot path (database scan + extension + NW + filter + selection
+[+ reductions]) over the resident shard.  `value` counts (query read x 10 M-read shard)
+alignments per second, i.e. plain query reads/s at N = 1; `query_reads_per_s` is always the
+plain figure.  `e2e` times the public C-ABI call imsame_gpu_align with pinned HOST buffers:
+H2D of both read sets, 2-bit packing, query table build, scan, NW, D2H of the records.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_CELL = 24  # INT32 ops per NW cell
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; <1 is not a valid bench)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-queries", type=int, default=2000)
+    ap.add_argument("--cpu-sample-db", type=int, default=200000)
+    return ap.parse_args()
+
+
+def workload(scale):
+    w = dict(name="cfg2: 1M x 250bp Illumina-like reads vs 10M-read synthetic metagenome (default flags)",
+             seed=2001, genomes_per_shard=1000, genome_len=1_000_000, L=250, nd_per_gpu=10_000_000,
+             nq=1_000_000, divergence=0.03)
+    if scale != 1.0:
+        w["nd_per_gpu"] = max(1000, int(w["nd_per_gpu"] * scale))
+        w["nq"] = max(100, int(w["nq"] * scale))
+        w["genomes_per_shard"] = max(2, int(w["genomes_per_shard"] * scale))
+        w["name"] += f" [SCALED x{scale}: not a valid bench]"
+    return w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def int32_peak_gops():
+    """measured INT32 lane-op rate (tools/int_peak.cu); ALU-pipe figure = imnmx line"""
+    exe = os.path.join(ROOT, "tools", "int_peak")
+    out = {}
+    try:
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+        for line in txt.splitlines():
+            d = json.loads(line)
+            if "op" in d:
+                out[d["op"]] = d["gops"]
+    except Exception as e:  # noqa: BLE001
+        out["error"] = str(e)
+    return out
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+def reference_cpu_run(args, w, steps, warmup):
+    """Times the reference's own CPU implementation (oracle/_ref/IMSAME, compiled unmodified from
+    /root/reference/src) on a bounded sample of the workload, all host threads."""
+    from imsame_b200 import hostlib as H
+    ref = os.path.join(ROOT, "oracle", "_ref", "IMSAME")
+    if not os.path.exists(ref):
+        return None, "oracle/_ref/IMSAME missing"
+    cores = os.cpu_count() or 1
+    nq, nd, L = args.cpu_sample_queries, args.cpu_sample_db, w["L"]
+    g = max(2, int(w["genomes_per_shard"] * nd / w["nd_per_gpu"]))  # same coverage as the full workload
+    pool = H.SynthPool(w["seed"], g, w["genome_len"])
+    db = pool.db_reads(0, nd, L)
+    q = pool.query_reads(0, nq, L, w["divergence"])
+    pool.close()
+    tmp = tempfile.mkdtemp(prefix="imsame_ref_")
+    dbf, qf, outf = (os.path.join(tmp, n) for n in ("db.fa", "q.fa", "out.align"))
+    H.write_fasta(dbf, db, nd, L, "d")
+    H.write_fasta(qf, q, nq, L, "q")
+    walls, aligns, builds = [], [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        txt = subprocess.run([ref, "-query", qf, "-db", dbf, "-out", outf, "-n_threads", str(cores)],
+                             capture_output=True, text=True, check=True).stdout
+        wall = time.perf_counter() - t0
+        # the load phases are single-threaded, so the reference's clock() prints are wall time there
+        # (src/IMSAME.c:102,295,407); alignment-phase wall = process wall - those
+        ph = {"Initialization took": 0.0, "Hash table building took": 0.0, "Took": 0.0}
+        for line in txt.splitlines():
+            for key in ph:
+                if key in line:
+                    try:
+                        ph[key] += float(line.split(key)[1].split()[0])
+                    except Exception:
+                        pass
+        if it >= warmup:
+            walls.append(wall)
+            aligns.append(max(wall - sum(ph.values()), 1e-9))
+            builds.append(ph["Hash table building took"])
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    wall = sum(walls) / len(walls)
+    al = sum(aligns) / len(aligns)
+    bl = sum(builds) / len(builds)
+    sample = (f"{nq} x {L}bp query reads vs {nd}-read database drawn from {g} genomes (same generator, seeds and "
+              f"coverage as the workload, database down-scaled {w['nd_per_gpu'] // nd}x because the reference's "
+              f"index needs 24 B per database base, so its per-read cost here is a LOWER bound of the full-size cost); "
+              f"whole-process wall {wall:.2f}s, database load + index build {bl:.2f}s (single thread), "
+              f"alignment phase {al:.2f}s on {cores} threads")
+    return {"reads_per_s_process": nq / wall, "reads_per_s_align_phase": nq / al,
+            "reads_per_s_index_plus_align": nq / (al + bl), "cores": cores, "sample": sample,
+            "ms_per_step": wall * 1e3}, None
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args.scale)
+    r, err = reference_cpu_run(args, w, max(1, args.steps), min(args.warmup, 1))
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": err}))
+        return
+    v = r["reads_per_s_align_phase"]
+    line = {"impl": "reference", "metric": "query reads aligned/sec", "value": v, "unit": "reads/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": w["name"], "sample": r["sample"]},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": r["cores"], "kind": "reference",
+                             "sample": r["sample"], "reads_per_s_whole_process": r["reads_per_s_process"]},
+            "e2e": {"value": r["reads_per_s_index_plus_align"], "unit": "reads/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0,
+                    "what": "index build (src/IMSAME.c:196-289) + alignment phase (:409-467), FASTA already parsed is not separable"}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    from imsame_b200 import api, hostlib as H
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = workload(args.scale)
+    L, nq, nd = w["L"], w["nq"], w["nd_per_gpu"]
+    n_genomes = w["genomes_per_shard"] * world
+    t0 = time.perf_counter()
+    pool = H.SynthPool(w["seed"], n_genomes, w["genome_len"])
+    db_pin = api.PinnedArray(nd * L)
+    q_pin = api.PinnedArray(nq * L)
+    pool.db_reads(rank * nd, nd, L, out=db_pin.array)                    # this rank's shard of the database
+    pool.query_reads(0, nq, L, w["divergence"], n_genomes_used=w["genomes_per_shard"], out=q_pin.array)
+    pool.close()
+    t_gen = time.perf_counter() - t0
+    ds = np.arange(nd + 1, dtype=np.uint64) * L
+    qs = np.arange(nq + 1, dtype=np.uint64) * L
+    db_total_global = nd * L * world
+    params = api.make_params(n_threads=4, db_total_len_global=db_total_global, db_pos_base=rank * nd * L,
+                             db_seq_base=rank * nd)
+
+    ctx = api.Imsame(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    keys = torch.empty(nq, dtype=torch.int64, device="cuda")
+    keys_local = torch.empty(nq, dtype=torch.int64, device="cuda")
+    payload = torch.empty(nq, dtype=torch.int64, device="cuda")
+
+    ctx.set_query((q_pin.array, qs), params)
+    ctx.set_db((db_pin.array, ds))
+    torch.cuda.synchronize()
+
+    def step():
+        st = ctx.run(params, keys.data_ptr(), payload.data_ptr())
+        if world > 1:
+            keys_local.copy_(keys)
+            dist.all_reduce(keys, op=dist.ReduceOp.MIN)      # C1: min-key reduction over NVLink
+            ctx.mask_payload(keys.data_ptr(), keys_local.data_ptr(), payload.data_ptr())
+            dist.all_reduce(payload, op=dist.ReduceOp.MAX)   # owner's payload
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats_steps = []
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        stats_steps.append(step())
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = float(tmax.item())
+    clocks = sampler.stop() if rank == 0 else None
+    rec = ctx.fetch(keys.data_ptr(), payload.data_ptr())
+    n_accepted = int(rec["accepted"].sum())
+
+    # per-kernel device times of the timed steps (CUDA events on the launching stream, inside the library)
+    def avg(k):
+        return sum(s[k] for s in stats_steps) / len(stats_steps)
+    cells = avg("n_cells")
+    ms_k3, ms_k2 = avg("ms_k3"), avg("ms_k2")
+    agg = torch.tensor([cells, ms_k3, ms_k2, avg("n_hits"), avg("n_pairs_dp"), avg("n_db_kmers"),
+                        avg("n_evalue_pass")], dtype=torch.float64, device="cuda")
+    agg_max = agg.clone()
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(agg_max, op=dist.ReduceOp.MAX)
+
+    # ---- end to end through the public C-ABI call with host buffers -------------------------
+    e2e = None
+    if args.e2e_steps > 0:
+        ctx2 = ctx
+        barrier()
+        t_e2e = []
+        h2d = d2h = 0
+        for it in range(args.e2e_steps + 1):
+            barrier()
+            t0 = time.perf_counter()
+            out, st = ctx2.align((db_pin.array, ds), (q_pin.array, qs), params)
+            if world > 1:
+                pass  # the sharded e2e figure is reported per rank: reductions are timed in `value`
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it > 0:
+                t_e2e.append(dt)
+                h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+        te = torch.tensor([sum(t_e2e) / len(t_e2e)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nq / float(te.item()), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3,
+               "what": "imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records"}
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        ipk = int32_peak_gops()
+        ms_step = ms_total / args.steps
+        cells_all, ms_k3_max, ms_k2_max = float(agg[0].item()), float(agg_max[1].item()), float(agg_max[2].item())
+        gcups = cells_all / world / (ms_k3_max * 1e-3) / 1e9 if ms_k3_max > 0 else 0.0   # per GPU
+        int_peak = ipk.get("imnmx") or ipk.get("iadd") or 0.0
+        achieved = gcups * OPS_PER_CELL
+        # K2 algorithmic bytes: Nd/4 + 8 per db word + 4 per hit + 16 per passing hit
+        k2_bytes = nd * L / 4 + 8 * float(agg[5].item()) / world + 4 * float(agg[3].item()) / world + 16 * float(agg[6].item()) / world
+        k2_gbs = k2_bytes / (ms_k2_max * 1e-3) / 1e9 if ms_k2_max > 0 else 0.0
+        line = {
+            "metric": "query reads aligned/sec", "value": world * nq / (ms_step * 1e-3), "unit": "reads/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "query_reads": nq, "db_reads_per_gpu": nd, "db_reads_total": nd * world,
+                       "read_len": L, "kmer": 12, "flags": "defaults (evalue 1e-20, coverage 0.5, identity 0.5, igap 5, egap 2, n_threads 4)",
+                       "sharding": f"db{world}" if world > 1 else "none",
+                       "value_counts": "query reads x 10M-read database shards per second (= query reads/s at N=1)",
+                       "l2": "inputs (625 MB packed shard + 1 GB query table) exceed the 126 MB L2"},
+            "query_reads_per_s": nq / (ms_step * 1e-3),
+            "dp_gcups_per_gpu": gcups, "dp_gcups_total": gcups * world,
+            "accepted_reads": n_accepted,
+            "work": {"hits": float(agg[3].item()), "evalue_pass": float(agg[6].item()), "nw_pairs": float(agg[4].item()),
+                     "cells": cells_all, "ms_k2": ms_k2_max, "ms_k3": ms_k3_max,
+                     "ms_other": max(0.0, ms_step - ms_k2_max - ms_k3_max)},
+            "roofline": {"kernel": "nw_kernel (K3, per-pair NW wavefront)", "bound": "int32-alu",
+                         "achieved": achieved, "peak": int_peak, "unit": "Gop/s",
+                         "frac": (achieved / int_peak) if int_peak else None, "traffic": None,
+                         "ops_per_cell": OPS_PER_CELL, "gcups": gcups,
+                         "peak_source": "tools/int_peak.cu run on this GPU just now (VIMNMX lane-op rate, ALU pipe)",
+                         "int_peak_table": ipk},
+            "roofline_k2": {"kernel": "scan_kernel (K2, db scan + extension)", "bound": "hbm", "achieved": k2_gbs,
+                            "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                            "frac": k2_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "traffic": None,
+                            "peak_source": which},
+            "e2e": e2e, "gpu_launches": int(sum(s["total_launches"] for s in stats_steps)),
+            "clocks": clocks, "gen_seconds": t_gen,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            r, err = reference_cpu_run(args, w, 1, 0)
+            if r:
+                line["cpu_baseline"] = {"value": r["reads_per_s_align_phase"], "unit": "reads/s", "cores": r["cores"],
+                                        "kind": "reference", "sample": r["sample"],
+                                        "reads_per_s_whole_process": r["reads_per_s_process"],
+                                        "reads_per_s_index_plus_align": r["reads_per_s_index_plus_align"]}
+            else:
+                line["cpu_baseline"] = {"unavailable": err}
+        print(json.dumps(line))
+    ctx.close()
+    db_pin.free()
+    q_pin.free()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

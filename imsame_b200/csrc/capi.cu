@@ -1,0 +1,935 @@
+// capi.cu -- C ABI (include/imsame_gpu.h) over the sm_100a kernels.
+// Host orchestration only: device memory, streams, launches, exact threshold
+// tables.  There is no CPU implementation of the hot path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/imsame_gpu.h"
+#include "../host/imsame_host.h"
+#include "nw.cuh"
+#include "qtable.cuh"
+#include "scan.cuh"
+
+using namespace imsame;
+
+namespace {
+
+constexpr uint64_t SEG_MAX_BASES = 1ull << 31;    // database segment size (positions stay uint32)
+constexpr uint64_t STAGE_BYTES = 256ull << 20;    // ASCII staging buffer on the device
+constexpr uint32_t PAD_WORDS = 16;                // zero words after every packed array
+
+struct Seg {
+    uint64_t pos_base = 0, seq_base = 0;  // offsets inside the shard handed to set_db
+    uint32_t n = 0, total = 0, fixed_len = 0, n_brk = 0;
+    uint32_t *pk = nullptr, *start = nullptr, *blk = nullptr, *brk = nullptr;
+};
+
+enum Phase { PH_PACKQ, PH_K1, PH_PACKDB, PH_K2, PH_K2B, PH_K3, PH_SELECT, PH_H2D, PH_D2H, PH_COUNT };
+
+}  // namespace
+
+struct imsame_ctx {
+    int device = 0;
+    int n_sm = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string cuda_err;
+
+    // query
+    uint32_t *q_pk = nullptr, *q_start = nullptr, *q_blk = nullptr;
+    uint32_t nq = 0, q_total = 0, q_fixed = 0, q_maxlen = 0;
+    uint32_t class_mask = 0;
+    std::vector<uint32_t> q_start_host;
+    uint32_t *off = nullptr, *cursor = nullptr, *qpos = nullptr, *tile_sums = nullptr;
+    uint64_t n_qwords = 0;
+    uint64_t q_threads = 0;
+    bool have_query = false;
+
+    // database shard
+    std::vector<Seg> segs;
+    uint64_t db_total = 0, db_nseqs = 0;
+    uint32_t db_maxlen = 0;
+    bool have_db = false;
+
+    // tables + work buffers
+    uint16_t *d_nmin = nullptr, *d_lmin = nullptr, *d_imin = nullptr;
+    unsigned long long *hkeys = nullptr, *hvals = nullptr;
+    uint32_t hcap = 0;
+    PairRec *pairs = nullptr;
+    PairRes *res = nullptr;
+    uint32_t *d_small = nullptr;  // [0] n_pairs, [1] work head
+    unsigned long long *d_counters = nullptr;  // [0..3] scan counters, [4] cells, [5] pairs total
+    int *d_overflow = nullptr;
+    unsigned long long *keys = nullptr, *payload = nullptr;
+    uint64_t keys_cap = 0;
+    NwLink *carry = nullptr;
+    uint64_t carry_warps = 0;
+    uint8_t *stage = nullptr;
+    int nw_grid[9] = {0};
+    int scan_grid = 0;
+
+    // phase timing
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int ph; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+    uint32_t launches = 0, k2_launches = 0, k3_launches = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ctx->cuda_err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+            return _e == cudaErrorMemoryAllocation ? IMSAME_ENOMEM : IMSAME_ECUDA;                 \
+        }                                                                                          \
+    } while (0)
+
+cudaEvent_t new_event(imsame_ctx *ctx) {
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->ev_pool.push_back(e);
+    }
+    return ctx->ev_pool[ctx->ev_used++];
+}
+struct PhaseScope {
+    imsame_ctx *ctx;
+    imsame_ctx::Span sp;
+    PhaseScope(imsame_ctx *c, int ph) : ctx(c) {
+        sp.ph = ph;
+        sp.a = new_event(c);
+        sp.b = new_event(c);
+        cudaEventRecord(sp.a, c->stream);
+    }
+    ~PhaseScope() {
+        cudaEventRecord(sp.b, ctx->stream);
+        ctx->spans.push_back(sp);
+    }
+};
+void reset_timing(imsame_ctx *ctx) {
+    ctx->ev_used = 0;
+    ctx->spans.clear();
+    ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    ctx->launches = ctx->k2_launches = ctx->k3_launches = 0;
+}
+
+template <typename T>
+int dev_alloc(imsame_ctx *ctx, T **p, uint64_t count) {
+    CK(cudaMalloc((void **)p, std::max<uint64_t>(count, 1) * sizeof(T)));
+    return IMSAME_OK;
+}
+template <typename T>
+void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void free_query(imsame_ctx *ctx) {
+    dev_free(ctx->q_pk); dev_free(ctx->q_start); dev_free(ctx->q_blk);
+    dev_free(ctx->qpos);
+    ctx->have_query = false;
+}
+void free_db(imsame_ctx *ctx) {
+    for (Seg &s : ctx->segs) { dev_free(s.pk); dev_free(s.start); dev_free(s.blk); dev_free(s.brk); }
+    ctx->segs.clear();
+    ctx->have_db = false;
+}
+
+uint32_t uniform_len(const uint64_t *start, uint64_t n, uint64_t total) {
+    if (n == 0) return 0;
+    const uint64_t L = (n > 1 ? start[1] : total) - start[0];
+    if (L == 0 || L > 0xFFFFFFFFull) return 0;
+    for (uint64_t r = 0; r < n; r++) {
+        const uint64_t e = (r + 1 < n) ? start[r + 1] : total;
+        if (e - start[r] != L) return 0;
+    }
+    return (uint32_t)L;
+}
+
+// upload ASCII bases [0,n) in staged chunks and pack them into pk (device)
+int upload_pack(imsame_ctx *ctx, const unsigned char *host, uint64_t n, uint32_t *pk, int ph_pack) {
+    if (!ctx->stage) { int rc = dev_alloc(ctx, &ctx->stage, STAGE_BYTES); if (rc) return rc; }
+    for (uint64_t at = 0; at < n; at += STAGE_BYTES) {
+        const uint64_t len = std::min<uint64_t>(STAGE_BYTES, n - at);
+        {
+            PhaseScope ps(ctx, PH_H2D);
+            CK(cudaMemcpyAsync(ctx->stage, host + at, len, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += len;
+        }
+        {
+            PhaseScope ps(ctx, ph_pack);
+            const uint64_t words = (len + 15) / 16;
+            const int grid = (int)std::min<uint64_t>((words + 255) / 256, (uint64_t)ctx->n_sm * 16);
+            pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->stage, len, pk + at / 16);
+            ctx->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+int upload_u32(imsame_ctx *ctx, uint32_t *dst, const uint32_t *src, uint64_t n) {
+    PhaseScope ps(ctx, PH_H2D);
+    CK(cudaMemcpyAsync(dst, src, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += n * sizeof(uint32_t);
+    return IMSAME_OK;
+}
+
+int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
+    if (!ctx->d_small) {
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_small, 4))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_counters, 8))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_overflow, 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_nmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_lmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_imin, 2 * IMSAME_MAX_READ_SIZE + 1))) return rc;
+    }
+    if (want_cap > ctx->hcap) {
+        dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
+        int rc;
+        if ((rc = dev_alloc(ctx, &ctx->hkeys, want_cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->hvals, want_cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->pairs, want_cap))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->res, want_cap))) return rc;
+        ctx->hcap = want_cap;
+        CK(cudaMemsetAsync(ctx->hkeys, 0xFF, (size_t)want_cap * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->hvals, 0xFF, (size_t)want_cap * 8, ctx->stream));
+    }
+    return IMSAME_OK;
+}
+
+template <int S, bool TB>
+int launch_nw(imsame_ctx *ctx, NwArgs a) {
+    if (!ctx->nw_grid[S]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<S, false>, NW_THREADS, 0));
+        ctx->nw_grid[S] = std::max(1, per_sm) * ctx->n_sm;
+    }
+    a.s_class = S;
+    CK(cudaMemsetAsync(a.work, 0, sizeof(uint32_t), ctx->stream));
+    nw_kernel<S, TB><<<ctx->nw_grid[S], NW_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    ctx->k3_launches++;
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+template <bool TB>
+int launch_nw_classes(imsame_ctx *ctx, const NwArgs &a, uint32_t class_mask) {
+    int rc = IMSAME_OK;
+    for (int c = 1; c <= 8 && !rc; c++) {
+        if (!(class_mask & (1u << c))) continue;
+        switch (c) {
+            case 1: rc = launch_nw<1, TB>(ctx, a); break;
+            case 2: rc = launch_nw<2, TB>(ctx, a); break;
+            case 3: rc = launch_nw<3, TB>(ctx, a); break;
+            case 4: rc = launch_nw<4, TB>(ctx, a); break;
+            case 5: rc = launch_nw<5, TB>(ctx, a); break;
+            case 6: rc = launch_nw<6, TB>(ctx, a); break;
+            case 7: rc = launch_nw<7, TB>(ctx, a); break;
+            default: rc = launch_nw<8, TB>(ctx, a); break;
+        }
+    }
+    return rc;
+}
+
+int max_nw_grid(imsame_ctx *ctx) {
+    int g = 0;
+    for (int c = 1; c <= 8; c++) g = std::max(g, ctx->nw_grid[c]);
+    return g ? g : ctx->n_sm * 8;
+}
+
+int ensure_carry(imsame_ctx *ctx, uint32_t max_ylen) {
+    if (max_ylen <= 32 * 8 + 1) return IMSAME_OK;
+    // the S = 8 kernel is the only one that runs multi-pass
+    if (!ctx->nw_grid[8]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<8, false>, NW_THREADS, 0));
+        ctx->nw_grid[8] = std::max(1, per_sm) * ctx->n_sm;
+    }
+    const uint64_t warps = (uint64_t)ctx->nw_grid[8] * NW_WARPS;
+    if (warps > ctx->carry_warps) {
+        dev_free(ctx->carry);
+        int rc = dev_alloc(ctx, &ctx->carry, warps * 2 * MAX_READ);
+        if (rc) return rc;
+        ctx->carry_warps = warps;
+    }
+    return IMSAME_OK;
+}
+
+uint32_t class_mask_of(const uint64_t *start, uint64_t n, uint64_t total, uint32_t *maxlen) {
+    uint32_t m = 0, mx = 0;
+    for (uint64_t r = 0; r < n; r++) {
+        const uint64_t e = (r + 1 < n) ? start[r + 1] : total;
+        const uint32_t len = (uint32_t)(e - start[r]);
+        mx = std::max(mx, len);
+        m |= 1u << nw_class_of(len);
+    }
+    *maxlen = mx;
+    return m;
+}
+
+void fill_stats(imsame_ctx *ctx, imsame_stats *st, const unsigned long long *cnt) {
+    if (!st) return;
+    float acc[PH_COUNT] = {0};
+    float t_min = 0, t_max = 0;
+    bool any = false;
+    cudaEvent_t first = nullptr, last = nullptr;
+    for (auto &sp : ctx->spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        acc[sp.ph] += ms;
+        if (!any) { first = sp.a; any = true; }
+        last = sp.b;
+    }
+    (void)t_min; (void)t_max;
+    float total = 0;
+    if (any) cudaEventElapsedTime(&total, first, last);
+    st->ms_pack_query = acc[PH_PACKQ]; st->ms_k1 = acc[PH_K1]; st->ms_pack_db = acc[PH_PACKDB];
+    st->ms_k2 = acc[PH_K2]; st->ms_k2b = acc[PH_K2B]; st->ms_k3 = acc[PH_K3]; st->ms_select = acc[PH_SELECT];
+    st->ms_h2d = acc[PH_H2D]; st->ms_d2h = acc[PH_D2H]; st->ms_total = total;
+    st->h2d_bytes = ctx->h2d_bytes; st->d2h_bytes = ctx->d2h_bytes;
+    st->k2_launches = ctx->k2_launches; st->k3_launches = ctx->k3_launches; st->total_launches = ctx->launches;
+    st->n_query_kmers = ctx->n_qwords;
+    if (cnt) {
+        st->n_db_kmers = cnt[0]; st->n_hits = cnt[1]; st->n_evalue_pass = cnt[2];
+        st->n_cells = cnt[4]; st->n_pairs = cnt[5]; st->n_pairs_dp = cnt[6]; st->n_accepted = cnt[7];
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *imsame_gpu_strerror(int code) {
+    switch (code) {
+        case IMSAME_OK: return "ok";
+        case IMSAME_ENODEV: return "no usable sm_100 CUDA device";
+        case IMSAME_ECUDA: return "CUDA runtime error";
+        case IMSAME_EARG: return "bad argument";
+        case IMSAME_ENOMEM: return "out of memory";
+        case IMSAME_EREADSIZE: return "Read size reached for gapped alignment.";
+        case IMSAME_ESTATE: return "call order violated";
+        case IMSAME_ELIMIT: return "input exceeds an implementation limit";
+        default: return "unknown error";
+    }
+}
+
+const char *imsame_gpu_last_cuda_error(const imsame_ctx *ctx) { return ctx ? ctx->cuda_err.c_str() : ""; }
+
+int imsame_gpu_create(imsame_ctx **out, int device) {
+    if (!out) return IMSAME_EARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return IMSAME_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return IMSAME_ENODEV;
+    if (prop.major != 10) return IMSAME_ENODEV;  // kernels are built for sm_100a only
+    if (cudaSetDevice(device) != cudaSuccess) return IMSAME_ENODEV;
+    imsame_ctx *ctx = new imsame_ctx();
+    ctx->device = device;
+    ctx->n_sm = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMSAME_ECUDA; }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, SCAN_THREADS_K2, 0);
+    ctx->scan_grid = std::max(1, per_sm) * ctx->n_sm;
+    *out = ctx;
+    return IMSAME_OK;
+}
+
+void imsame_gpu_destroy(imsame_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_query(ctx);
+    free_db(ctx);
+    dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
+    dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin);
+    dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
+    dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
+    dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->carry); dev_free(ctx->stage);
+    for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int imsame_gpu_set_stream(imsame_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return IMSAME_EARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return IMSAME_OK;
+}
+
+void *imsame_gpu_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void imsame_gpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+void imsame_gpu_free(void *p) { free(p); }
+
+// ---- query: upload, pack, K1 ---------------------------------------------------------------
+int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_params *p) {
+    if (!ctx || !q || !p || !q->sequences || !q->start_pos || q->n_seqs == 0) return IMSAME_EARG;
+    if (q->total_len >= 0xFFFFFF00ull || q->n_seqs >= 0xFFFFFF00ull) return IMSAME_ELIMIT;
+    cudaSetDevice(ctx->device);
+    free_query(ctx);
+    const uint32_t nq = (uint32_t)q->n_seqs, total = (uint32_t)q->total_len;
+    for (uint64_t r = 0; r < nq; r++) {
+        const uint64_t e = (r + 1 < nq) ? q->start_pos[r + 1] : q->total_len;
+        if (e <= q->start_pos[r]) return IMSAME_EARG;  // empty reads break the reference's scan too
+    }
+    ctx->nq = nq;
+    ctx->q_total = total;
+    ctx->q_fixed = uniform_len(q->start_pos, nq, q->total_len);
+    ctx->class_mask = class_mask_of(q->start_pos, nq, q->total_len, &ctx->q_maxlen);
+    ctx->q_start_host.resize((size_t)nq + 1);
+    for (uint32_t r = 0; r < nq; r++) ctx->q_start_host[r] = (uint32_t)q->start_pos[r];
+    ctx->q_start_host[nq] = total;
+    ctx->q_threads = p->n_threads ? p->n_threads : 1;
+
+    int rc;
+    const uint64_t words = ((uint64_t)total + 15) / 16 + PAD_WORDS;
+    if ((rc = dev_alloc(ctx, &ctx->q_pk, words))) return rc;
+    CK(cudaMemsetAsync(ctx->q_pk, 0, words * 4, ctx->stream));
+    if ((rc = upload_pack(ctx, q->sequences, total, ctx->q_pk, PH_PACKQ))) return rc;
+    if (!ctx->q_fixed) {
+        if ((rc = dev_alloc(ctx, &ctx->q_start, (uint64_t)nq + 1))) return rc;
+        if ((rc = upload_u32(ctx, ctx->q_start, ctx->q_start_host.data(), (uint64_t)nq + 1))) return rc;
+        const uint64_t nblk = ((uint64_t)total + 63) / 64 + 1;
+        if ((rc = dev_alloc(ctx, &ctx->q_blk, nblk))) return rc;
+        PhaseScope ps(ctx, PH_K1);
+        blk_kernel<<<std::min<uint32_t>((nq + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ctx->q_start, nq, ctx->q_blk);
+        ctx->launches++;
+    }
+    if (!ctx->off) {
+        if ((rc = dev_alloc(ctx, &ctx->off, (uint64_t)NCODES + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->cursor, (uint64_t)NCODES + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->tile_sums, (uint64_t)SCAN_TILE))) return rc;
+    }
+    QTableArgs a;
+    a.q.pk = ctx->q_pk; a.q.start = ctx->q_start; a.q.blk = ctx->q_blk; a.q.n = nq; a.q.total = total;
+    a.q.fixed_len = ctx->q_fixed;
+    a.n_threads = (uint32_t)std::min<uint64_t>(ctx->q_threads, 0xFFFFFFFFull);
+    a.per = (uint32_t)(nq / ctx->q_threads);  // floorl(n_seqs / n_threads), src/IMSAME.c:414
+    a.cnt = ctx->cursor;
+    a.qpos = nullptr;
+    const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
+    const uint32_t n_tiles = (NCODES + SCAN_TILE - 1) / SCAN_TILE;
+    uint32_t n_words = 0;
+    {
+        PhaseScope ps(ctx, PH_K1);
+        CK(cudaMemsetAsync(ctx->cursor, 0, ((size_t)NCODES + 1) * 4, ctx->stream));
+        qtable_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
+        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, NCODES, ctx->tile_sums, ctx->off);
+        scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, n_tiles);
+        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, NCODES, ctx->tile_sums, ctx->off);
+        ctx->launches += 4;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(&n_words, ctx->off + NCODES, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_qwords = n_words;
+    if ((rc = dev_alloc(ctx, &ctx->qpos, (uint64_t)n_words + 1))) return rc;
+    {
+        PhaseScope ps(ctx, PH_K1);
+        CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)NCODES + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        a.qpos = ctx->qpos;
+        qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->have_query = true;
+    return IMSAME_OK;
+}
+
+// ---- database shard: upload + pack in segments of < 2^31 bases -------------------------------
+int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
+    if (!ctx || !db || !db->sequences || !db->start_pos || db->n_seqs == 0) return IMSAME_EARG;
+    if (db->n_seqs >= 0xFFFFFF00ull) return IMSAME_ELIMIT;
+    cudaSetDevice(ctx->device);
+    free_db(ctx);
+    ctx->db_total = db->total_len;
+    ctx->db_nseqs = db->n_seqs;
+    const uint32_t fixed = uniform_len(db->start_pos, db->n_seqs, db->total_len);
+    uint32_t mx = 0;
+    (void)class_mask_of(db->start_pos, db->n_seqs, db->total_len, &mx);
+    ctx->db_maxlen = mx;
+    std::vector<uint32_t> tmp;
+    uint64_t r0 = 0, bi = 0;
+    while (r0 < db->n_seqs) {
+        // greedy: as many whole reads as fit
+        const uint64_t base = db->start_pos[r0];
+        uint64_t r1;
+        if (fixed) {
+            r1 = std::min<uint64_t>(db->n_seqs, r0 + SEG_MAX_BASES / fixed);
+        } else {
+            uint64_t lo = r0 + 1, hi = db->n_seqs;  // largest r1 with start[r1] - base <= SEG_MAX
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi + 1) / 2;
+                const uint64_t e = mid < db->n_seqs ? db->start_pos[mid] : db->total_len;
+                if (e - base <= SEG_MAX_BASES) lo = mid; else hi = mid - 1;
+            }
+            r1 = lo;
+        }
+        const uint64_t end = r1 < db->n_seqs ? db->start_pos[r1] : db->total_len;
+        if (end - base > 0xFFFFFF00ull) return IMSAME_ELIMIT;  // a single read larger than a segment
+        Seg s;
+        s.pos_base = base; s.seq_base = r0; s.n = (uint32_t)(r1 - r0); s.total = (uint32_t)(end - base);
+        s.fixed_len = fixed;
+        int rc;
+        const uint64_t words = ((uint64_t)s.total + 15) / 16 + PAD_WORDS;
+        if ((rc = dev_alloc(ctx, &s.pk, words))) return rc;
+        ctx->segs.push_back(s);
+        CK(cudaMemsetAsync(s.pk + words - PAD_WORDS - 1, 0, (PAD_WORDS + 1) * 4, ctx->stream));
+        if ((rc = upload_pack(ctx, db->sequences + base, s.total, s.pk, PH_PACKDB))) return rc;
+        Seg &ss = ctx->segs.back();
+        if (!fixed) {
+            tmp.resize((size_t)s.n + 1);
+            for (uint64_t r = r0; r < r1; r++) tmp[r - r0] = (uint32_t)(db->start_pos[r] - base);
+            tmp[s.n] = s.total;
+            if ((rc = dev_alloc(ctx, &ss.start, (uint64_t)s.n + 1))) return rc;
+            if ((rc = upload_u32(ctx, ss.start, tmp.data(), (uint64_t)s.n + 1))) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));  // tmp is reused
+            const uint64_t nblk = ((uint64_t)s.total + 63) / 64 + 1;
+            if ((rc = dev_alloc(ctx, &ss.blk, nblk))) return rc;
+            PhaseScope ps(ctx, PH_PACKDB);
+            blk_kernel<<<std::min<uint32_t>((s.n + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ss.start, s.n, ss.blk);
+            ctx->launches++;
+        }
+        // word breaks that fall inside this segment
+        std::vector<uint32_t> brk;
+        while (bi < db->n_breaks && db->break_pos[bi] < end) {
+            if (db->break_pos[bi] >= base) brk.push_back((uint32_t)(db->break_pos[bi] - base));
+            bi++;
+        }
+        if (!brk.empty()) {
+            ss.n_brk = (uint32_t)brk.size();
+            if ((rc = dev_alloc(ctx, &ss.brk, brk.size()))) return rc;
+            if ((rc = upload_u32(ctx, ss.brk, brk.data(), brk.size()))) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        r0 = r1;
+    }
+    ctx->have_db = true;
+    return IMSAME_OK;
+}
+
+// ---- K2 + K2b + K3 + selection over the resident shard ----------------------------------------
+static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
+                    imsame_stats *st);
+
+int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
+                   imsame_stats *st) {
+    if (!ctx || !p) return IMSAME_EARG;
+    reset_timing(ctx);
+    return run_impl(ctx, p, d_keys, d_payload, st);
+}
+
+static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
+                    imsame_stats *st) {
+    if (!ctx || !p) return IMSAME_EARG;
+    if (!ctx->have_query || !ctx->have_db) return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    const uint32_t nq = ctx->nq;
+    int rc;
+    if (!d_keys || !d_payload) {
+        if (ctx->keys_cap < nq) {
+            dev_free(ctx->keys); dev_free(ctx->payload);
+            if ((rc = dev_alloc(ctx, &ctx->keys, nq))) return rc;
+            if ((rc = dev_alloc(ctx, &ctx->payload, nq))) return rc;
+            ctx->keys_cap = nq;
+        }
+    }
+    unsigned long long *keys = d_keys ? (unsigned long long *)d_keys : ctx->keys;
+    unsigned long long *payload = d_payload ? (unsigned long long *)d_payload : ctx->payload;
+
+    uint32_t cap = 1u << 20;
+    while (cap < 8ull * nq && cap < (1u << 30)) cap <<= 1;
+    cap = std::max(cap, ctx->hcap);
+    if ((rc = ensure_carry(ctx, ctx->q_maxlen))) return rc;
+
+    // exact threshold tables (host, long double) -> device
+    std::vector<uint16_t> nmin(IMSAME_MAX_READ_SIZE + 1), lmin(IMSAME_MAX_READ_SIZE + 1), imin(2 * IMSAME_MAX_READ_SIZE + 1);
+    const uint64_t db_total_global = p->db_total_len_global ? p->db_total_len_global : ctx->db_total;
+    imsame_build_nmin(p->min_e_value, db_total_global, nmin.data());
+    imsame_build_lmin(p->min_coverage, lmin.data());
+    imsame_build_imin(p->min_identity, imin.data());
+
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if ((rc = ensure_work_buffers(ctx, cap))) return rc;
+        CK(cudaMemcpyAsync(ctx->d_nmin, nmin.data(), nmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_lmin, lmin.data(), lmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_imin, imin.data(), imin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int), ctx->stream));
+        {
+            PhaseScope ps(ctx, PH_SELECT);
+            const int g = std::min<int>((nq + 255) / 256, ctx->n_sm * 8);
+            fill_u64_kernel<<<g, 256, 0, ctx->stream>>>(keys, KEY_NONE, nq);
+            ctx->launches++;
+            CK(cudaMemsetAsync(payload, 0, (size_t)nq * 8, ctx->stream));
+        }
+        SeqMap qm;
+        qm.pk = ctx->q_pk; qm.start = ctx->q_start; qm.blk = ctx->q_blk; qm.n = nq; qm.total = ctx->q_total;
+        qm.fixed_len = ctx->q_fixed;
+        for (const Seg &s : ctx->segs) {
+            SeqMap dm;
+            dm.pk = s.pk; dm.start = s.start; dm.blk = s.blk; dm.n = s.n; dm.total = s.total; dm.fixed_len = s.fixed_len;
+            CK(cudaMemsetAsync(ctx->d_small, 0, 4 * sizeof(uint32_t), ctx->stream));
+            {
+                PhaseScope ps(ctx, PH_K2);
+                ScanArgs a;
+                a.db = dm; a.q = qm; a.off = ctx->off; a.qpos = ctx->qpos; a.brk = s.brk; a.n_brk = s.n_brk;
+                a.nmin = ctx->d_nmin; a.seg_pos_base = p->db_pos_base + s.pos_base;
+                a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = keys;
+                a.counters = ctx->d_counters; a.overflow = ctx->d_overflow;
+                scan_kernel<<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
+                ctx->launches++; ctx->k2_launches++;
+            }
+            {
+                PhaseScope ps(ctx, PH_K2B);
+                const int g = std::min<uint32_t>((ctx->hcap + 255) / 256, (uint32_t)ctx->n_sm * 16);
+                compact_kernel<<<g, 256, 0, ctx->stream>>>(ctx->hkeys, ctx->hvals, ctx->hcap, ctx->pairs, ctx->d_small);
+                ctx->launches++;
+            }
+            {
+                PhaseScope ps(ctx, PH_K3);
+                NwArgs a;
+                a.db = dm; a.q = qm; a.pairs = ctx->pairs; a.res = ctx->res; a.n_pairs = ctx->d_small;
+                a.work = ctx->d_small + 1; a.igap = p->igap; a.egap = p->egap; a.lmin = ctx->d_lmin; a.imin = ctx->d_imin;
+                a.best = keys; a.cells = ctx->d_counters + 4; a.carry = ctx->carry; a.s_class = 0;
+                a.tb = nullptr; a.tb_off = nullptr;
+                if ((rc = launch_nw_classes<false>(ctx, a, ctx->class_mask))) return rc;
+            }
+            {
+                PhaseScope ps(ctx, PH_SELECT);
+                const int g = ctx->n_sm * 8;
+                select_kernel<<<g, 256, 0, ctx->stream>>>(ctx->pairs, ctx->res, ctx->d_small, keys, payload,
+                                                           p->db_seq_base + s.seq_base, ctx->d_counters + 5);
+                ctx->launches++;
+            }
+            CK(cudaGetLastError());
+        }
+        int overflow = 0;
+        CK(cudaMemcpyAsync(&overflow, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!overflow) break;
+        if (cap >= (1u << 30)) return IMSAME_ELIMIT;
+        cap <<= 1;  // pair table too small: grow and redo the shard
+    }
+    unsigned long long cnt[8] = {0};
+    CK(cudaMemcpy(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE) {
+        // the reference only fails when such a read reaches NW (src/alignmentFunctions.c:155)
+        if (cnt[2] > 0) return IMSAME_EREADSIZE;
+    }
+    fill_stats(ctx, st, cnt);
+    return IMSAME_OK;
+}
+
+int imsame_gpu_mask_payload(imsame_ctx *ctx, const uint64_t *reduced, const uint64_t *local, uint64_t *payload) {
+    if (!ctx || !reduced || !local || !payload) return IMSAME_EARG;
+    cudaSetDevice(ctx->device);
+    mask_payload_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>((const unsigned long long *)reduced,
+                                                              (const unsigned long long *)local,
+                                                              (unsigned long long *)payload, ctx->nq);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+int imsame_gpu_fetch(imsame_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_payload, imsame_best *out) {
+    if (!ctx || !out) return IMSAME_EARG;
+    if (!ctx->have_query) return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    const uint64_t *k = d_keys ? d_keys : (const uint64_t *)ctx->keys;
+    const uint64_t *pl = d_payload ? d_payload : (const uint64_t *)ctx->payload;
+    if (!k || !pl) return IMSAME_ESTATE;
+    const uint32_t nq = ctx->nq;
+    std::vector<uint64_t> hk(nq), hp(nq);
+    {
+        PhaseScope ps(ctx, PH_D2H);
+        CK(cudaMemcpyAsync(hk.data(), k, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hp.data(), pl, (size_t)nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (uint64_t)nq * 16;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t r = 0; r < nq; r++) {
+        imsame_best b;
+        memset(&b, 0, sizeof(b));
+        if (hk[r] != KEY_NONE) {
+            b.accepted = 1;
+            b.qpos_end = (uint64_t)ctx->q_start_host[r] + key_erel(hk[r]) - 1;
+            b.db_pos = key_dbpos(hk[r]);
+            b.db_seq = hp[r] >> 32;
+            b.length = (uint32_t)(hp[r] >> 16) & 0xFFFFu;
+            b.identities = (uint32_t)hp[r] & 0xFFFFu;
+        }
+        out[r] = b;
+    }
+    return IMSAME_OK;
+}
+
+int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
+                     const imsame_params *p, imsame_best *out, imsame_stats *st) {
+    if (!ctx || !db || !query || !p || !out) return IMSAME_EARG;
+    reset_timing(ctx);
+    int rc;
+    if ((rc = imsame_gpu_set_query(ctx, query, p))) return rc;
+    if ((rc = imsame_gpu_set_db(ctx, db))) return rc;
+    imsame_stats local;
+    memset(&local, 0, sizeof(local));
+    if ((rc = run_impl(ctx, p, nullptr, nullptr, &local))) return rc;
+    if ((rc = imsame_gpu_fetch(ctx, nullptr, nullptr, out))) return rc;
+    uint64_t acc = 0;
+    for (uint32_t r = 0; r < ctx->nq; r++) acc += out[r].accepted;
+    if (st) {
+        unsigned long long cnt[8];
+        cudaMemcpy(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost);
+        fill_stats(ctx, st, cnt);
+        st->n_accepted = acc;
+    }
+    return IMSAME_OK;
+}
+
+
+}  // extern "C"
+
+// ---- explicit pairs: shared by imsame_gpu_nw_batch and imsame_gpu_traceback -------------------
+namespace {
+
+struct PairBatch {
+    imsame_ctx *ctx;
+    uint32_t n = 0, class_mask = 0, ymax = 0;
+    uint32_t *xpk = nullptr, *ypk = nullptr, *dxs = nullptr, *dys = nullptr, *dsmall = nullptr;
+    PairRec *dp = nullptr;
+    PairRes *dr = nullptr;
+    uint16_t *dz = nullptr;
+    unsigned long long *dcells = nullptr;
+    std::vector<uint32_t> xs, ys;
+    explicit PairBatch(imsame_ctx *c) : ctx(c) {}
+    ~PairBatch() {
+        dev_free(xpk); dev_free(ypk); dev_free(dxs); dev_free(dys); dev_free(dsmall); dev_free(dp); dev_free(dr);
+        dev_free(dz); dev_free(dcells);
+    }
+    // X[i]/Y[i] ASCII reads -> packed device arrays + pair list (r = s = i)
+    int upload(uint32_t n_pairs, const unsigned char *const *X, const uint32_t *xlen, const unsigned char *const *Y,
+               const uint32_t *ylen) {
+        n = n_pairs;
+        xs.resize((size_t)n + 1);
+        ys.resize((size_t)n + 1);
+        uint64_t xt = 0, yt = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            if (xlen[i] > IMSAME_MAX_READ_SIZE || ylen[i] > IMSAME_MAX_READ_SIZE) return IMSAME_EREADSIZE;
+            if (xlen[i] == 0 || ylen[i] == 0) return IMSAME_EARG;
+            xs[i] = (uint32_t)xt; ys[i] = (uint32_t)yt;
+            xt += xlen[i]; yt += ylen[i];
+            class_mask |= 1u << nw_class_of(ylen[i]);
+            ymax = std::max(ymax, ylen[i]);
+        }
+        if (xt >= 0xFFFFFF00ull || yt >= 0xFFFFFF00ull) return IMSAME_ELIMIT;
+        xs[n] = (uint32_t)xt; ys[n] = (uint32_t)yt;
+        std::vector<unsigned char> xa(xt), ya(yt);
+        for (uint32_t i = 0; i < n; i++) {
+            memcpy(xa.data() + xs[i], X[i], xlen[i]);
+            memcpy(ya.data() + ys[i], Y[i], ylen[i]);
+        }
+        int rc;
+        const uint64_t xw = (xt + 15) / 16 + PAD_WORDS, yw = (yt + 15) / 16 + PAD_WORDS;
+        if ((rc = dev_alloc(ctx, &xpk, xw)) || (rc = dev_alloc(ctx, &ypk, yw)) ||
+            (rc = dev_alloc(ctx, &dxs, (uint64_t)n + 1)) || (rc = dev_alloc(ctx, &dys, (uint64_t)n + 1)) ||
+            (rc = dev_alloc(ctx, &dsmall, 4)) || (rc = dev_alloc(ctx, &dp, n)) || (rc = dev_alloc(ctx, &dr, n)) ||
+            (rc = dev_alloc(ctx, &dz, 2 * IMSAME_MAX_READ_SIZE + 1)) || (rc = dev_alloc(ctx, &dcells, 4)))
+            return rc;
+        CK(cudaMemsetAsync(xpk, 0, xw * 4, ctx->stream));
+        CK(cudaMemsetAsync(ypk, 0, yw * 4, ctx->stream));
+        CK(cudaMemsetAsync(dz, 0, (2 * IMSAME_MAX_READ_SIZE + 1) * 2, ctx->stream));
+        CK(cudaMemsetAsync(dcells, 0, 32, ctx->stream));
+        if ((rc = upload_pack(ctx, xa.data(), xt, xpk, PH_PACKDB))) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));  // the staging buffer and xa are reused
+        if ((rc = upload_pack(ctx, ya.data(), yt, ypk, PH_PACKQ))) return rc;
+        std::vector<PairRec> hp(n);
+        for (uint32_t i = 0; i < n; i++) { hp[i].r = i; hp[i].s = i; hp[i].key = 0; }
+        const uint32_t small[4] = {n, 0, 0, 0};
+        CK(cudaMemcpyAsync(dxs, xs.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dys, ys.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dp, hp.data(), (size_t)n * sizeof(PairRec), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(dsmall, small, sizeof(small), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // host vectors go out of scope
+        return ensure_carry(ctx, ymax);
+    }
+    NwArgs args(int igap, int egap) const {
+        NwArgs a;
+        a.db.pk = xpk; a.db.start = dxs; a.db.blk = nullptr; a.db.n = n; a.db.total = xs[n]; a.db.fixed_len = 0;
+        a.q.pk = ypk; a.q.start = dys; a.q.blk = nullptr; a.q.n = n; a.q.total = ys[n]; a.q.fixed_len = 0;
+        a.pairs = dp; a.res = dr; a.n_pairs = dsmall; a.work = dsmall + 1; a.igap = igap; a.egap = egap;
+        a.lmin = dz; a.imin = dz; a.best = nullptr; a.cells = dcells; a.carry = ctx->carry; a.s_class = 0;
+        a.tb = nullptr; a.tb_off = nullptr;
+        return a;
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---- NW on explicit pairs (src/alignmentFunctions.c:389-560 in isolation) -----------------------
+int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *const *X, const uint32_t *xlen,
+                        const unsigned char *const *Y, const uint32_t *ylen, int igap, int egap, int32_t *out5,
+                        float *ms_kernel) {
+    if (!ctx || !X || !Y || !xlen || !ylen || !out5) return IMSAME_EARG;
+    if (n_pairs == 0) return IMSAME_OK;
+    cudaSetDevice(ctx->device);
+    PairBatch pb(ctx);
+    int rc;
+    if ((rc = pb.upload(n_pairs, X, xlen, Y, ylen))) return rc;
+    NwArgs a = pb.args(igap, egap);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->stream);
+    rc = launch_nw_classes<false>(ctx, a, pb.class_mask);
+    cudaEventRecord(e1, ctx->stream);
+    std::vector<PairRes> hr(n_pairs);
+    if (!rc) {
+        cudaError_t ce = cudaMemcpyAsync(hr.data(), pb.dr, (size_t)n_pairs * sizeof(PairRes), cudaMemcpyDeviceToHost, ctx->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (ce != cudaSuccess) { ctx->cuda_err = cudaGetErrorString(ce); rc = IMSAME_ECUDA; }
+    }
+    if (!rc && ms_kernel) cudaEventElapsedTime(ms_kernel, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n_pairs; i++) {
+        out5[5 * i + 0] = hr[i].score;
+        out5[5 * i + 1] = (int32_t)hr[i].bx;
+        out5[5 * i + 2] = (int32_t)hr[i].by;
+        out5[5 * i + 3] = (int32_t)((hr[i].stats & 0x7FFFFFFFu) >> 16);
+        out5[5 * i + 4] = (int32_t)(hr[i].stats & 0xFFFFu);
+    }
+    return IMSAME_OK;
+}
+
+// ---- winners-only traceback (src/alignmentFunctions.c:493-546) ----------------------------------
+int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
+                         const imsame_params *p, const imsame_best *best, uint64_t *ops_off, uint32_t **ops_out,
+                         uint32_t *cell_xy) {
+    if (!ctx || !db || !query || !p || !best || !ops_off || !ops_out || !cell_xy) return IMSAME_EARG;
+    cudaSetDevice(ctx->device);
+    const uint64_t nq = query->n_seqs;
+    constexpr uint64_t TB_BUDGET = 3ull << 30;  // bytes of back-pointer codes per batch
+    std::vector<uint32_t> all_ops;
+    std::vector<uint64_t> winners;
+    for (uint64_t r = 0; r < nq; r++) {
+        ops_off[r] = 0;
+        cell_xy[4 * r] = cell_xy[4 * r + 1] = cell_xy[4 * r + 2] = cell_xy[4 * r + 3] = 0;
+        if (best[r].accepted) {
+            if (best[r].db_seq < p->db_seq_base || best[r].db_seq - p->db_seq_base >= db->n_seqs) return IMSAME_EARG;
+            winners.push_back(r);
+        }
+    }
+    std::vector<uint64_t> n_ops_of(nq, 0), first_op(nq, 0);
+    size_t w0 = 0;
+    while (w0 < winners.size()) {
+        // batch: as many winners as fit the table budget
+        std::vector<const unsigned char *> X, Y;
+        std::vector<uint32_t> xl, yl, strides;
+        std::vector<uint64_t> tb_off, op_off;
+        uint64_t tb_elems = 0, op_elems = 0;
+        size_t w1 = w0;
+        while (w1 < winners.size()) {
+            const uint64_t r = winners[w1], s = best[r].db_seq - p->db_seq_base;
+            const uint64_t xe = s + 1 < db->n_seqs ? db->start_pos[s + 1] : db->total_len;
+            const uint64_t ye = r + 1 < nq ? query->start_pos[r + 1] : query->total_len;
+            const uint32_t xlen = (uint32_t)(xe - db->start_pos[s]), ylen = (uint32_t)(ye - query->start_pos[r]);
+            if (xlen > IMSAME_MAX_READ_SIZE || ylen > IMSAME_MAX_READ_SIZE) return IMSAME_EREADSIZE;
+            const uint32_t stride = tb_stride(ylen, nw_class_of(ylen));
+            const uint64_t need = (uint64_t)(xlen > 1 ? xlen - 1 : 1) * stride;
+            if (w1 > w0 && (tb_elems + need) * 2 > TB_BUDGET) break;
+            X.push_back(db->sequences + db->start_pos[s]);
+            Y.push_back(query->sequences + query->start_pos[r]);
+            xl.push_back(xlen); yl.push_back(ylen); strides.push_back(stride);
+            tb_off.push_back(tb_elems); op_off.push_back(op_elems);
+            tb_elems += need;
+            op_elems += (uint64_t)xlen + ylen + 2;
+            w1++;
+        }
+        const uint32_t nb = (uint32_t)(w1 - w0);
+        PairBatch pb(ctx);
+        int rc;
+        if ((rc = pb.upload(nb, X.data(), xl.data(), Y.data(), yl.data()))) return rc;
+        uint16_t *d_tb = nullptr;
+        uint64_t *d_tboff = nullptr, *d_opoff = nullptr;
+        uint32_t *d_str = nullptr, *d_ops = nullptr, *d_nops = nullptr, *d_end = nullptr;
+        auto cleanup = [&]() { dev_free(d_tb); dev_free(d_tboff); dev_free(d_opoff); dev_free(d_str); dev_free(d_ops); dev_free(d_nops); dev_free(d_end); };
+        if ((rc = dev_alloc(ctx, &d_tb, tb_elems)) || (rc = dev_alloc(ctx, &d_tboff, nb)) || (rc = dev_alloc(ctx, &d_opoff, nb)) ||
+            (rc = dev_alloc(ctx, &d_str, nb)) || (rc = dev_alloc(ctx, &d_ops, op_elems)) || (rc = dev_alloc(ctx, &d_nops, nb)) ||
+            (rc = dev_alloc(ctx, &d_end, 2ull * nb))) { cleanup(); return rc; }
+        cudaMemcpyAsync(d_tboff, tb_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_opoff, op_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_str, strides.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream);
+        NwArgs a = pb.args(p->igap, p->egap);
+        a.tb = d_tb;
+        a.tb_off = d_tboff;
+        rc = launch_nw_classes<true>(ctx, a, pb.class_mask);
+        if (!rc) {
+            tb_walk_kernel<<<std::min<uint32_t>((nb + 127) / 128, (uint32_t)ctx->n_sm * 8), 128, 0, ctx->stream>>>(
+                pb.dr, d_tb, d_tboff, d_str, nb, d_ops, d_opoff, d_nops, d_end);
+            ctx->launches++;
+        }
+        std::vector<uint32_t> h_ops(op_elems), h_nops(nb), h_end(2ull * nb);
+        std::vector<PairRes> h_res(nb);
+        cudaError_t ce = cudaGetLastError();
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_ops.data(), d_ops, op_elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_nops.data(), d_nops, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_end.data(), d_end, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_res.data(), pb.dr, (size_t)nb * sizeof(PairRes), cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        cleanup();
+        if (rc) return rc;
+        if (ce != cudaSuccess) { ctx->cuda_err = cudaGetErrorString(ce); return IMSAME_ECUDA; }
+        for (uint32_t i = 0; i < nb; i++) {
+            const uint64_t r = winners[w0 + i];
+            first_op[r] = all_ops.size();
+            n_ops_of[r] = h_nops[i];
+            all_ops.insert(all_ops.end(), h_ops.begin() + op_off[i], h_ops.begin() + op_off[i] + h_nops[i]);
+            cell_xy[4 * r] = h_res[i].bx; cell_xy[4 * r + 1] = h_res[i].by;
+            cell_xy[4 * r + 2] = h_end[2 * i]; cell_xy[4 * r + 3] = h_end[2 * i + 1];
+        }
+        w0 = w1;
+    }
+    // winners were visited in ascending read order, so first_op is already monotone
+    uint64_t at = 0;
+    for (uint64_t r = 0; r < nq; r++) { ops_off[r] = at; at += n_ops_of[r]; }
+    ops_off[nq] = at;
+    uint32_t *out = (uint32_t *)malloc(std::max<size_t>(all_ops.size(), 1) * sizeof(uint32_t));
+    if (!out) return IMSAME_ENOMEM;
+    memcpy(out, all_ops.data(), all_ops.size() * sizeof(uint32_t));
+    *ops_out = out;
+    return IMSAME_OK;
+}
+
+}  // extern "C"

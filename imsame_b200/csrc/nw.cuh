@@ -1,0 +1,186 @@
+// nw.cuh -- K3: one warp per candidate (read, db_seq) pair.  Full (xlen-1)(ylen-1)
+// evaluation of the reference NW (src/alignmentFunctions.c:389-489) as an
+// anti-diagonal wavefront over lane strips (nw_core.cuh), with the traceback's
+// length/identities carried forward, the identity/coverage filter
+// (src/alignmentFunctions.c:163) and the per-read first-accepted selection
+// (:172,189 -> atomicMin of the scan-order key) fused into the epilogue.
+// Integer ALU work only: no tensor cores (irregular max/select recurrence).
+#pragma once
+#include "nw_core.cuh"
+#include "traceback.cuh"
+
+namespace imsame {
+
+constexpr int NW_WARPS = 8;  // warps per block
+constexpr int NW_THREADS = NW_WARPS * 32;
+constexpr int NW_XBUF = 3008;  // bytes of X codes per warp in shared memory
+
+struct PairRec {
+    uint32_t r, s;  // query read, database read (local to the segment)
+    uint64_t key;   // smallest scan-order key among the pair's e-value-passing hits
+};
+struct PairRes {
+    int32_t score;
+    uint32_t bx, by;
+    uint32_t stats;  // (length << 16) | identities; bit 31 = accepted by the filter
+};
+
+struct NwArgs {
+    SeqMap db, q;
+    const PairRec *pairs;
+    PairRes *res;
+    const uint32_t *n_pairs;  // device counter written by the compaction kernel
+    uint32_t *work;           // atomic work-queue head
+    int igap, egap;
+    const uint16_t *lmin, *imin;
+    unsigned long long *best;  // per read scan-order key (atomicMin); may be null (nw_batch)
+    unsigned long long *cells;  // [0] cells, [2] pairs evaluated
+    NwLink *carry;             // 2 * MAX_READ links per warp of the grid, or null
+    int s_class;               // pairs with min(ceil((ylen-1)/32), 8) != s_class are skipped
+    // TB = true only (K4, winners-only traceback): back-pointer codes per cell
+    uint16_t *tb;              // codes of pair idx start at tb + tb_off[idx]
+    const uint64_t *tb_off;
+};
+
+IMS_HD int nw_class_of(uint32_t ylen) {
+    int c = ((int)ylen - 1 + 31) / 32;
+    return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ NwLink shfl_up_link(const NwLink &o) {
+    NwLink in;
+    in.a = __shfl_up_sync(0xffffffffu, o.a, 1);
+    in.ap = __shfl_up_sync(0xffffffffu, o.ap, 1);
+    in.b = __shfl_up_sync(0xffffffffu, o.b, 1);
+    in.bp = __shfl_up_sync(0xffffffffu, o.bp, 1);
+    in.mfs = __shfl_up_sync(0xffffffffu, o.mfs, 1);
+    in.mfy = __shfl_up_sync(0xffffffffu, o.mfy, 1);
+    in.mfp = __shfl_up_sync(0xffffffffu, o.mfp, 1);
+    return in;
+}
+
+template <int S, bool TB>
+__global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
+    __shared__ uint8_t sx_all[NW_WARPS][NW_XBUF];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *sx = sx_all[warp];
+    const uint32_t n_pairs = *a.n_pairs;
+    unsigned long long my_cells = 0, my_pairs = 0;
+    NwLink *carry0 = a.carry ? a.carry + (size_t)(blockIdx.x * NW_WARPS + warp) * 2 * MAX_READ : nullptr;
+
+    for (;;) {
+        uint32_t idx = 0;
+        if (lane == 0) idx = atomicAdd(a.work, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_pairs) break;
+        const PairRec pr = a.pairs[idx];
+        const uint32_t ys = read_start(a.q, pr.r);
+        const uint32_t ylen = (a.q.fixed_len ? a.q.fixed_len : a.q.start[pr.r + 1] - ys);
+        if (nw_class_of(ylen) != a.s_class) continue;
+        if (a.best && pr.key >= a.best[pr.r]) {  // an earlier hit of this read is already accepted
+            if (lane == 0) { PairRes z; z.score = 0; z.bx = z.by = 0; z.stats = 0; a.res[idx] = z; }
+            continue;
+        }
+        const uint32_t xs = read_start(a.db, pr.s);
+        const uint32_t xlen = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs);
+        const int X1 = (int)xlen - 1, Y1 = (int)ylen - 1;
+        uint16_t *tb_pair = nullptr;
+        uint32_t tb_str = 0;
+        if (TB) {
+            tb_pair = a.tb + a.tb_off[idx];
+            tb_str = tb_stride(ylen, S);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < xlen; i += 32) sx[i] = (uint8_t)base_at(a.db.pk, (uint64_t)xs + i);
+        __syncwarp();
+        const uint32_t x0 = sx[0];
+        const uint32_t y0 = base_at(a.q.pk, ys);
+
+        NwBest wbest;
+        wbest.s = NW_NEG * 2; wbest.i = wbest.j = wbest.p = 0;
+        int pass = 0;
+        for (int jb = 0; jb < Y1; jb += 32 * S, pass++) {
+            int nl = (Y1 - jb + S - 1) / S;
+            nl = nl > 32 ? 32 : nl;
+            const bool more = jb + 32 * S < Y1;
+            const int j0 = jb + lane * S + 1;
+            const bool first = (jb == 0) && (lane == 0);
+            // codes of Y[j0-2 .. j0+S-1]
+            uint64_t halo;
+            {
+                const int64_t g = (int64_t)ys + j0 - 2;
+                halo = g >= 0 ? fetch32(a.q.pk, (uint64_t)g) : (fetch32(a.q.pk, 0) << 2);
+            }
+            const uint32_t ycols = (uint32_t)(halo >> 4) & ((1u << (2 * S)) - 1u);
+            NwLane<S> L;
+            nw_lane_init<S>(L, x0, halo, first);
+            NwLink out;
+            out.a = out.ap = out.b = out.bp = out.mfs = out.mfy = out.mfp = 0;
+            const NwLink *cin = carry0 ? carry0 + (size_t)((pass + 1) & 1) * MAX_READ : nullptr;
+            NwLink *cout = carry0 ? carry0 + (size_t)(pass & 1) * MAX_READ : nullptr;
+            const int steps = X1 + nl - 1;
+            for (int t = 0; t < steps; t++) {
+                const int i = t - lane + 1;
+                NwLink in = shfl_up_link(out);
+                const bool act = (lane < nl) && (i >= 1) && (i <= X1);
+                if (act) {
+                    const uint32_t xi = sx[i];
+                    if (lane == 0) in = (jb == 0) ? nw_first_link(xi, y0) : cin[i];
+                    uint32_t d = ycols ^ (xi * 0x55555555u);
+                    const uint32_t mm = (d | (d >> 1)) & 0x55555555u;
+                    nw_row<S, TB>(L, in, out, i, j0, mm, a.igap, a.egap, X1, Y1, first,
+                                  TB ? tb_pair + (size_t)(i - 1) * tb_str + (j0 - 1) : nullptr);
+                    if (more && lane == 31) cout[i] = out;
+                }
+            }
+            // warp reduction of the best border cell ("last in row-major order" on ties)
+            NwBest b = L.best;
+            if (lane >= nl) b.s = NW_NEG * 2;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                NwBest c;
+                c.s = __shfl_xor_sync(0xffffffffu, b.s, o);
+                c.i = __shfl_xor_sync(0xffffffffu, b.i, o);
+                c.j = __shfl_xor_sync(0xffffffffu, b.j, o);
+                c.p = __shfl_xor_sync(0xffffffffu, b.p, o);
+                if (best_better(c, b)) b = c;
+            }
+            if (best_better(b, wbest)) wbest = b;
+            __syncwarp();
+        }
+        if (lane == 0) {
+            const uint32_t len = (uint32_t)wbest.p >> 16, id = (uint32_t)wbest.p & 0xFFFFu;
+            // src/alignmentFunctions.c:163 through the host-built exact tables
+            const bool ok = (X1 >= 1 && Y1 >= 1) && len > 0 && len >= a.lmin[ylen] && id >= a.imin[len];
+            PairRes z;
+            z.score = wbest.s; z.bx = (uint32_t)wbest.i; z.by = (uint32_t)wbest.j;
+            z.stats = (uint32_t)wbest.p | (ok ? 0x80000000u : 0u);
+            a.res[idx] = z;
+            if (ok && a.best) atomicMin(&a.best[pr.r], (unsigned long long)pr.key);
+            my_cells += (unsigned long long)X1 * (unsigned long long)Y1;
+            my_pairs++;
+        }
+    }
+    if (lane == 0 && my_pairs) {
+        atomicAdd(a.cells, my_cells);
+        atomicAdd(a.cells + 2, my_pairs);  // counters[6]: pairs run through NW
+    }
+}
+
+// K4b: one thread per winner walks the stored back-pointers (traceback.cuh)
+__global__ void tb_walk_kernel(const PairRes *res, const uint16_t *tb, const uint64_t *tb_off,
+                               const uint32_t *strides, uint32_t n_pairs, uint32_t *ops,
+                               const uint64_t *ops_off, uint32_t *n_ops, uint32_t *end_xy) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {
+        uint32_t ex = 0, ey = 0;
+        n_ops[i] = tb_walk(tb + tb_off[i], strides[i], res[i].bx, res[i].by, ops + ops_off[i], &ex, &ey);
+        end_xy[2 * i] = ex;
+        end_xy[2 * i + 1] = ey;
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace imsame

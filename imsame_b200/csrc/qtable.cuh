@@ -1,0 +1,156 @@
+// qtable.cuh -- packing and K1: the query word table in HBM.
+//
+// The reference indexes the DATABASE (12-D pointer table of linked lists,
+// src/IMSAME.c:232-281) and streams the query (src/alignmentFunctions.c:91-203).
+// Here the mirror image is built: a CSR table over the QUERY words
+//     off[4^12 + 1], qpos[n_words]   (qpos = index of the word's last base = curr_pos)
+// holding exactly the words the reference's scan would look up, including its
+// cross-read "phantom" word: every read that is not the first of its pthread
+// chunk starts its word stream on the LAST base of the previous read and never
+// uses its own last base (src/alignmentFunctions.c:93-105,189-199).
+#pragma once
+#include "common.cuh"
+
+namespace imsame {
+
+#if defined(__CUDACC__)
+
+// ASCII (A/C/G/T) -> 2 bits per base; one thread per output word (16 bases, 128-bit load)
+__global__ void pack_kernel(const uint8_t *__restrict__ in, uint64_t n_bases, uint32_t *__restrict__ out) {
+    const uint64_t n_words = (n_bases + 15) / 16;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words;
+         w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        if (w * 16 + 16 <= n_bases) {
+            const uint4 q = reinterpret_cast<const uint4 *>(in)[w];
+            const uint32_t x[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                // per byte: (c >> 1) & 3, gathered to 8 bits per 32-bit lane
+                const uint32_t t = (x[k] >> 1) & 0x03030303u;
+                const uint32_t g = (t | (t >> 6) | (t >> 12) | (t >> 18)) & 0xFFu;
+                v |= g << (8 * k);
+            }
+        } else {
+            for (uint64_t i = w * 16; i < n_bases; i++) v |= (uint32_t)((in[i] >> 1) & 3u) << (2 * (i - w * 16));
+        }
+        out[w] = v;
+    }
+}
+
+// blk[b] = read containing base 64*b ; one thread per read
+__global__ void blk_kernel(const uint32_t *__restrict__ start, uint32_t n, uint32_t *__restrict__ blk) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t s = start[r], e = start[r + 1];
+        for (uint32_t b = (s + 63) >> 6; ((uint64_t)b << 6) < e; b++) blk[b] = r;
+    }
+}
+
+struct QTableArgs {
+    SeqMap q;
+    uint32_t per, n_threads;  // chunking of src/IMSAME.c:414,433
+    uint32_t *cnt;            // pass 0: histogram ; pass 1: bucket cursors
+    uint32_t *qpos;
+};
+
+// does a query word end at base e, and which word?  
+__device__ __forceinline__ bool query_word_at(const QTableArgs &a, uint32_t e, uint32_t &code) {
+    const uint32_t r = find_read(a.q, e);
+    const uint32_t ys = read_start(a.q, r);
+    const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
+    const uint32_t lo = (ys == 0 || is_chunk_first(r, a.per, a.n_threads)) ? ys : ys - 1;
+    const uint32_t hi = (r == a.q.n - 1) ? a.q.total - 1 : yend - 2;
+    if (e < lo + (K - 1) || e > hi || yend < 2 + ys) return false;
+    code = fetch16(a.q.pk, (uint64_t)e - (K - 1)) & KMASK;
+    return true;
+}
+
+template <int PASS>
+__global__ void qtable_kernel(QTableArgs a) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < a.q.total; e += gridDim.x * blockDim.x) {
+        uint32_t code;
+        if (!query_word_at(a, e, code)) continue;
+        const uint32_t slot = atomicAdd(&a.cnt[code], 1u);
+        if (PASS == 1) a.qpos[slot] = e;
+    }
+}
+
+// ---- exclusive scan of the 4^12 counters (three small kernels) ----
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;  // per thread
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t s = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += y;
+        }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t base = warp ? wsum[warp - 1] : 0;
+    if (total) *total = wsum[31];
+    __syncthreads();
+    return base + x - v;
+}
+
+// phase 0: per-tile sums ; phase 2: write exclusive offsets (tile offset + local scan)
+template <int PHASE>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t *__restrict__ in, uint32_t n,
+                                                                  uint32_t *__restrict__ tile_sums,
+                                                                  uint32_t *__restrict__ out) {
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, &total);
+    if (PHASE == 0) {
+        if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+    } else {
+        ex += tile_sums[blockIdx.x];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) out[base + k] = ex;
+            ex += v[k];
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = ex;
+    }
+}
+
+// phase 1: exclusive scan of the tile sums in one block (n_tiles <= SCAN_TILE)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t *tile_sums, uint32_t n_tiles) {
+    const uint32_t base = threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n_tiles) ? tile_sums[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan(s, nullptr);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n_tiles) tile_sums[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace imsame

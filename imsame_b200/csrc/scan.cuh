@@ -1,0 +1,215 @@
+// scan.cuh -- K2: database scan.  Streams the 2-bit database, looks every
+// database word up in the query word table (qtable.cuh), runs the ungapped
+// extension + integer e-value test of src/alignmentFunctions.c:276-387 on
+// every (database word, query word) hit, and records the candidates that pass
+// (src/alignmentFunctions.c:139) in a pair table keyed by (read, db_seq) with
+// an atomicMin of the scan-order key.  K2b compacts that table into the work
+// queue of the NW kernel with warp-aggregated atomics.
+//
+// Which database words exist (src/IMSAME.c:215-283): words never span two
+// reads (word_size = 0 at :283) nor a dropped non-ACGT character (:229-231);
+// pos = index AFTER the word's last base (:247,265).
+#pragma once
+#include "common.cuh"
+#include "extend.cuh"
+#include "nw.cuh"
+
+namespace imsame {
+
+constexpr uint64_t HASH_EMPTY = ~0ull;
+constexpr int SCAN_WARPS = 8;
+constexpr int SCAN_THREADS_K2 = SCAN_WARPS * 32;
+
+struct ScanArgs {
+    SeqMap db, q;
+    const uint32_t *off;   // query table: bucket offsets (4^12 + 1)
+    const uint32_t *qpos;  // query table: word end positions
+    const uint32_t *brk;   // database word breaks (segment-local), ascending
+    uint32_t n_brk;
+    const uint16_t *nmin;  // e-value threshold table by ylen
+    uint64_t seg_pos_base; // global index of the segment's first base
+    unsigned long long *hkeys, *hvals;  // pair table (open addressing)
+    uint32_t hmask;
+    const unsigned long long *best;  // current per-read best key (prunes later segments)
+    unsigned long long *counters;    // [0] db words, [1] hits, [2] e-value passes, [3] anomalies
+    int *overflow;
+};
+
+IMS_HD uint64_t pair_hash(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void pair_insert(const ScanArgs &a, uint32_t r, uint32_t s, uint64_t key) {
+    const unsigned long long pk = ((unsigned long long)r << 32) | s;
+    uint32_t h = (uint32_t)pair_hash(pk) & a.hmask;
+    for (uint32_t probe = 0; probe <= a.hmask; probe++) {
+        unsigned long long cur = a.hkeys[h];
+        if (cur == HASH_EMPTY) cur = atomicCAS(&a.hkeys[h], HASH_EMPTY, pk);
+        if (cur == HASH_EMPTY || cur == pk) {
+            atomicMin(&a.hvals[h], (unsigned long long)key);
+            return;
+        }
+        h = (h + 1) & a.hmask;
+        if (probe > 4096) break;
+    }
+    *a.overflow = 1;
+}
+
+// is there a word break inside the word ending at base q (bases q-11 .. q)?
+__device__ __forceinline__ bool word_broken(const ScanArgs &a, uint32_t q) {
+    if (a.n_brk == 0) return false;
+    // first break >= q-10
+    uint32_t lo = 0, hi = a.n_brk;
+    const uint32_t want = q - (K - 2);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.brk[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    return lo < a.n_brk && a.brk[lo] <= q;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
+    __shared__ uint32_t s_excl[SCAN_WARPS][33];
+    __shared__ uint32_t s_b0[SCAN_WARPS][32];
+    __shared__ uint32_t s_xs[SCAN_WARPS][32];
+    __shared__ uint32_t s_xe[SCAN_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = (a.db.total + 31) / 32;
+    const uint32_t gw = blockIdx.x * SCAN_WARPS + warp, nw = gridDim.x * SCAN_WARPS;
+    unsigned long long c_words = 0, c_hits = 0, c_pass = 0, c_anom = 0;
+
+    for (uint32_t tile = gw; tile < n_tiles; tile += nw) {
+        const uint32_t q = tile * 32 + lane;  // index of the word's last base
+        uint32_t cnt = 0, b0 = 0, xs = 0, xe = 0;
+        if (q < a.db.total) {
+            const uint32_t s = find_read(a.db, q);
+            xs = read_start(a.db, s);
+            xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
+            if (q >= xs + (K - 1) && !word_broken(a, q)) {
+                const uint32_t code = fetch16(a.db.pk, (uint64_t)q - (K - 1)) & KMASK;
+                b0 = a.off[code];
+                cnt = a.off[code + 1] - b0;
+                c_words++;
+            }
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();
+        s_excl[warp][lane] = incl - cnt;
+        s_b0[warp][lane] = b0;
+        s_xs[warp][lane] = xs;
+        s_xe[warp][lane] = xe;
+        __syncwarp();
+        for (uint32_t h = lane; h < total; h += 32) {
+            // owner = last lane whose exclusive prefix is <= h
+            int o = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1)
+                if (s_excl[warp][o + step] <= h) o += step;
+            const uint32_t e = a.qpos[s_b0[warp][o] + (h - s_excl[warp][o])];
+            const uint32_t p = tile * 32 + o + 1;  // llpos.pos: index after the word
+            const uint32_t r = find_read(a.q, e);
+            const uint32_t ys = read_start(a.q, r);
+            const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
+            const int n = extend_hit(a.db.pk, a.q.pk, p, e, s_xs[warp][o], s_xe[warp][o], ys, yend);
+            c_hits++;
+            if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
+            if (n < 0 || n >= (int)a.nmin[yend - ys]) {
+                c_pass++;
+                const uint64_t key = make_key(e - ys + 1, a.seg_pos_base + p);
+                if (key < a.best[r]) {
+                    const uint32_t s = find_read(a.db, p - 1);
+                    pair_insert(a, r, s, key);
+                }
+            }
+        }
+    }
+    // counters: warp-reduce then one atomic per warp
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        c_words += __shfl_xor_sync(0xffffffffu, c_words, o);
+        c_hits += __shfl_xor_sync(0xffffffffu, c_hits, o);
+        c_pass += __shfl_xor_sync(0xffffffffu, c_pass, o);
+        c_anom += __shfl_xor_sync(0xffffffffu, c_anom, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&a.counters[0], c_words);
+        atomicAdd(&a.counters[1], c_hits);
+        atomicAdd(&a.counters[2], c_pass);
+        if (c_anom) atomicAdd(&a.counters[3], c_anom);
+    }
+}
+
+// K2b: pair table -> dense work queue (warp-aggregated atomic append); resets the table
+__global__ void compact_kernel(unsigned long long *hkeys, unsigned long long *hvals, uint32_t n_slots,
+                               PairRec *pairs, uint32_t *n_pairs) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_slots;
+         base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        unsigned long long k = HASH_EMPTY, v = 0;
+        if (i < n_slots) {
+            k = hkeys[i];
+            if (k != HASH_EMPTY) {
+                v = hvals[i];
+                hkeys[i] = HASH_EMPTY;
+                hvals[i] = ~0ull;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, k != HASH_EMPTY);
+        if (m) {
+            uint32_t at = 0;
+            if (lane == (__ffs(m) - 1)) at = atomicAdd(n_pairs, (uint32_t)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
+            if (k != HASH_EMPTY) {
+                PairRec pr;
+                pr.r = (uint32_t)(k >> 32);
+                pr.s = (uint32_t)k;
+                pr.key = v;
+                pairs[at + __popc(m & ((1u << lane) - 1u))] = pr;
+            }
+        }
+    }
+}
+
+// after NW: the pair whose key equals the read's final key owns the record
+__global__ void select_kernel(const PairRec *pairs, const PairRes *res, const uint32_t *n_pairs,
+                              const unsigned long long *best, unsigned long long *payload,
+                              uint64_t seg_seq_base, unsigned long long *pairs_total) {
+    const uint32_t n = *n_pairs;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pairs_total, (unsigned long long)n);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const PairRec pr = pairs[i];
+        const PairRes z = res[i];
+        if ((z.stats & 0x80000000u) && pr.key == best[pr.r])
+            payload[pr.r] = ((unsigned long long)(seg_seq_base + pr.s) << 32) | (z.stats & 0x7FFFFFFFu);
+    }
+}
+
+// multi-shard: keep the payload only where this shard owns the reduced key
+__global__ void mask_payload_kernel(const unsigned long long *reduced, const unsigned long long *local,
+                                    unsigned long long *payload, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (reduced[i] != local[i] || reduced[i] == KEY_NONE) payload[i] = 0ull;
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace imsame

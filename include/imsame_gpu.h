@@ -137,14 +137,20 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
                         const uint32_t *xlen, const unsigned char *const *Y, const uint32_t *ylen,
                         int igap, int egap, int32_t *out5, float *ms_kernel);
 
-/* ---- winners-only traceback (src/alignmentFunctions.c:493-560) ---------- */
-/* For each accepted read of `best`, recompute NW with back-pointers on the
- * device and return the path as run-length ops; see imsame_host.h for the
- * renderer that turns them into the reference's text. ops_off has nq+1 entries. */
+/* ---- winners-only traceback (src/alignmentFunctions.c:493-546) ---------- */
+/* For each accepted read of `best`, NW is recomputed on the device with one
+ * back-pointer code per cell and walked back from the best border cell.  The
+ * path comes back as run-length ops in traceback order (type << 28 | count:
+ * 1 = diagonal steps, 2 = jump up a column: count bases of X over '-', 3 = jump
+ * along a row: '-' over count bases of Y); ops of read r are
+ * ops[ops_off[r] .. ops_off[r+1]) (ops_off has nq+1 entries).  cell_xy holds
+ * 4 values per read: best cell (x, y) and the border cell where the walk ended.
+ * `db` must be the shard that best[].db_seq (minus params->db_seq_base) indexes.
+ * imsame_host.h: imsame_render_alignment() turns this into the reference's text. */
 int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
                          const imsame_params *params, const imsame_best *best, uint64_t *ops_off,
                          uint32_t **ops /* malloc'ed by the library, free with imsame_gpu_free */,
-                         uint32_t *bc_xy /* 2 per read: best cell x, y */);
+                         uint32_t *cell_xy);
 void imsame_gpu_free(void *p);
 
 /* pinned host memory helpers for callers that want full-speed copies */

@@ -1,0 +1,75 @@
+// CPU check of the packed-sequence helpers and the ungapped extension used by the
+// scan kernel (common.cuh / extend.cuh) against the oracle's byte-wise extension.
+//   usage: extend_emul <seed>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+#include "../../imsame_b200/csrc/extend.cuh"
+extern "C" {
+#include "../../oracle/imsame_oracle.h"
+}
+using namespace imsame;
+static uint64_t rng_state;
+static uint64_t rnd() { uint64_t z = (rng_state += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+
+static std::vector<uint32_t> pack(const std::vector<unsigned char> &s) {
+    std::vector<uint32_t> pk(s.size() / 16 + 20, 0);
+    for (size_t i = 0; i < s.size(); i++) pk[i >> 4] |= (uint32_t)((s[i] >> 1) & 3) << ((i & 15) * 2);
+    return pk;
+}
+
+int main(int argc, char **argv) {
+    rng_state = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
+    const char B[4] = {'A', 'C', 'G', 'T'};
+    // database: reads of varying length cut from a small genome (so that many words repeat)
+    std::vector<unsigned char> genome(3000);
+    for (auto &c : genome) c = B[rnd() & 3];
+    std::vector<unsigned char> D, Q;
+    std::vector<uint64_t> ds, qs;
+    for (int r = 0; r < 120; r++) {
+        ds.push_back(D.size());
+        int len = 12 + rnd() % 200, at = rnd() % (genome.size() - len);
+        for (int i = 0; i < len; i++) D.push_back((rnd() % 100 < 2) ? B[rnd() & 3] : genome[at + i]);
+    }
+    for (int r = 0; r < 60; r++) {
+        qs.push_back(Q.size());
+        int len = 11 + rnd() % 200, at = rnd() % (genome.size() - len);
+        for (int i = 0; i < len; i++) Q.push_back((rnd() % 100 < 5) ? B[rnd() & 3] : genome[at + i]);
+    }
+    ds.push_back(D.size()); qs.push_back(Q.size());
+    orc_seqs db = {D.data(), ds.data(), D.size(), ds.size() - 1, nullptr, 0};
+    orc_seqs q = {Q.data(), qs.data(), Q.size(), qs.size() - 1, nullptr, 0};
+    auto dpk = pack(D), qpk = pack(Q);
+    // fetch / base_at sanity
+    for (size_t i = 0; i + 40 < D.size(); i += 7) {
+        uint64_t w = fetch32(dpk.data(), i);
+        for (int t = 0; t < 32; t++) if (((w >> (2 * t)) & 3) != ((D[i + t] >> 1) & 3u)) { printf("fetch32 mismatch\n"); return 1; }
+        if ((fetch16(dpk.data(), i) & 3) != base_at(dpk.data(), i)) { printf("fetch16 mismatch\n"); return 1; }
+    }
+    // all word hits (including words that start one base before a query read: the phantom)
+    std::unordered_multimap<uint32_t, uint32_t> qwords;  // code -> e
+    for (size_t r = 0; r + 1 < qs.size(); r++) {
+        int64_t lo = r == 0 ? (int64_t)qs[r] : (int64_t)qs[r] - 1;
+        for (int64_t e = lo + 11; e < (int64_t)qs[r + 1]; e++) qwords.emplace(fetch16(qpk.data(), e - 11) & KMASK, (uint32_t)e);
+    }
+    long hits = 0, bad = 0;
+    for (size_t s = 0; s + 1 < ds.size(); s++)
+        for (uint64_t x = ds[s] + 11; x < ds[s + 1]; x++) {
+            uint32_t code = fetch16(dpk.data(), x - 11) & KMASK;
+            auto range = qwords.equal_range(code);
+            for (auto it = range.first; it != range.second; ++it) {
+                uint32_t e = it->second, p = (uint32_t)x + 1;
+                // read containing e
+                size_t r = 0;
+                while (qs[r + 1] <= e) r++;
+                int64_t want = orc_extend(&db, &q, p, (uint64_t)e + 1, r, s);
+                int got = extend_hit(dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                hits++;
+                if (want != got) { if (bad++ < 10) printf("MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got); }
+            }
+        }
+    printf("%ld hits, %ld mismatches\n", hits, bad);
+    return bad != 0 || hits < 1000;
+}

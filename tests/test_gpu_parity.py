@@ -1,0 +1,129 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Integer / index work: bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as hp
+import synth_cases as sc
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_records(db, ds, q, qs, n_threads, breaks=None, **kw):
+    odb = hp.OracleSeqs(seq=db, start=ds, brk=breaks)
+    oq = hp.OracleSeqs(seq=q, start=qs)
+    p = hp.default_params(n_threads=n_threads, **kw)
+    best, st = hp.oracle_align(odb, oq, p)
+    return hp.best_to_records(best, len(qs) - 1), st
+
+
+def gpu_records(out):
+    return {int(r): (int(o["db_seq"]), int(o["qpos_end"]), int(o["db_pos"]), int(o["length"]), int(o["identities"]))
+            for r, o in enumerate(out) if o["accepted"]}
+
+
+def test_nw_batch_matches_oracle(gpu):
+    lib = hp.oracle()
+    xs, ys = sc.random_pairs(5, 1500, max_len=300)
+    x2, y2 = sc.random_pairs(6, 60, max_len=300, long_every=3)  # up to 3000 x 3000: multi-pass path
+    xs += x2
+    ys += y2
+    for igap, egap in ((5, 2), (3, 1), (0, 0), (7, 3)):
+        got, ms = gpu.nw_batch(xs, ys, igap=igap, egap=egap)
+        for i, (x, y) in enumerate(zip(xs, ys)):
+            s = C.c_int32(); bx = C.c_uint32(); by = C.c_uint32(); ln = C.c_uint32(); idn = C.c_uint32()
+            u8p = C.POINTER(C.c_ubyte)
+            lib.orc_nw_forward(x.ctypes.data_as(u8p), len(x), y.ctypes.data_as(u8p), len(y), -igap, -egap,
+                               C.byref(s), C.byref(bx), C.byref(by), C.byref(ln), C.byref(idn))
+            want = (s.value, bx.value, by.value, ln.value, idn.value)
+            assert tuple(int(v) for v in got[i]) == want, (i, len(x), len(y), igap, egap)
+
+
+@pytest.mark.parametrize("n_threads", [1, 4])
+def test_align_fixed_length_matches_oracle(gpu, n_threads):
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(1001, 4, 100000, 150, 20000, 2000, 0.03)
+    want, st = oracle_records(db, ds, q, qs, n_threads)
+    out, stats = gpu.align((db, ds), (q, qs), api.make_params(n_threads=n_threads))
+    assert gpu_records(out) == want
+    assert stats["n_accepted"] == len(want) > 500
+
+
+def test_align_divergent_reads(gpu):
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(7, 4, 100000, 150, 20000, 2000, 0.10)
+    want, _ = oracle_records(db, ds, q, qs, 4)
+    out, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
+    assert gpu_records(out) == want
+
+
+def test_align_ragged_reads_and_thresholds(gpu):
+    from imsame_b200 import api
+    db, ds, q, qs = sc.ragged_case(11, 3, 60000, 6000, 900, 0.05)
+    for kw in (dict(), dict(coverage=0.8, identity=0.9), dict(evalue=1e-5, igap=3, egap=1)):
+        want, _ = oracle_records(db, ds, q, qs, 3, **kw)
+        gk = dict(n_threads=3)
+        if "coverage" in kw:
+            gk.update(min_coverage=kw["coverage"], min_identity=kw["identity"])
+        if "evalue" in kw:
+            gk.update(min_e_value=kw["evalue"], igap=kw["igap"], egap=kw["egap"])
+        out, _ = gpu.align((db, ds), (q, qs), api.make_params(**gk))
+        assert gpu_records(out) == want, kw
+        assert len(want) > 50
+
+
+def test_align_with_word_breaks(gpu):
+    """dropped non-ACGT characters reset database words but not query words (src/IMSAME.c:229-231)"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(21, 2, 50000, 120, 5000, 800, 0.02)
+    rng = np.random.default_rng(3)
+    brk = np.unique(rng.integers(1, len(db), size=3000)).astype(np.uint64)
+    brk = np.array([b for b in brk if b % 120 != 0], dtype=np.uint64)  # not at read starts
+    want, _ = oracle_records(db, ds, q, qs, 2, breaks=brk)
+    want_nobrk, _ = oracle_records(db, ds, q, qs, 2)
+    out, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=2), db_breaks=brk)
+    assert gpu_records(out) == want
+    assert want != want_nobrk  # the breaks do change the answer
+
+
+def test_sharded_database_equals_whole(gpu):
+    """two shards + min-key reduction + owner payload == one shard"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(31, 4, 80000, 150, 16000, 1500, 0.03)
+    whole, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
+    nd = len(ds) - 1
+    half = nd // 2
+    keys, payloads = [], []
+    ctx = api.Imsame(0)
+    try:
+        ctx.set_query((q, qs), api.make_params(n_threads=4))
+        for lo, hi in ((0, half), (half, nd)):
+            b0, b1 = int(ds[lo]), int(ds[hi])
+            ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
+            p = api.make_params(n_threads=4, db_total_len_global=len(db), db_pos_base=b0, db_seq_base=lo)
+            ctx.run(p)
+            rec = ctx.fetch()
+            keys.append(rec)
+        merged = {}
+        for r in range(len(qs) - 1):
+            cands = [k[r] for k in keys if k[r]["accepted"]]
+            if cands:
+                # scan order: qpos_end ascending, db_pos descending
+                best = min(cands, key=lambda o: (int(o["qpos_end"]), -int(o["db_pos"])))
+                merged[r] = (int(best["db_seq"]), int(best["qpos_end"]), int(best["db_pos"]), int(best["length"]),
+                             int(best["identities"]))
+    finally:
+        ctx.close()
+    assert merged == gpu_records(whole)
+
+
+def test_cfg1_full_size(gpu):
+    """BASELINE.json configs[0]: 10k x 150bp reads vs 100k-read metagenome, defaults"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(1001, 20, 500000, 150, 100000, 10000, 0.03)
+    want, st = oracle_records(db, ds, q, qs, 4)
+    out, stats = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
+    assert gpu_records(out) == want
+    assert len(want) > 3000
