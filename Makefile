@@ -10,11 +10,12 @@ CFLAGS    := -O3 -fPIC -Wall -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE $(OMPF
 NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
              -Xcompiler -fPIC,-Wall -Xptxas -v
 OUT       := imsame_b200/_lib
-HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/host/synth.c
+HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/host/synth.c \
+             imsame_b200/host/render.c
 GPU_SRC   := imsame_b200/csrc/capi.cu
 GPU_HDR   := $(wildcard imsame_b200/csrc/*.cuh) include/imsame_gpu.h
 
-all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
+all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so bin/IMSAME bin/revComp bin/all_vs_all_metagenomes_IMSAME.sh
 
 $(OUT)/libimsame_host.so: $(HOST_SRC) imsame_b200/host/imsame_host.h include/imsame_gpu.h
 	@mkdir -p $(OUT)
@@ -29,7 +30,7 @@ $(OUT)/libimsame_gpu.so: $(GPU_SRC) $(GPU_HDR) imsame_b200/host/thresholds.c
 bin/IMSAME: imsame_b200/host/imsame_main.c $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
 	@mkdir -p bin
 	$(CC) $(CFLAGS) -fPIE imsame_b200/host/imsame_main.c -L$(OUT) -limsame_host -limsame_gpu \
-	    -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lm -o $@
+	    -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lpthread -lm -o $@
 
 bin/revComp: imsame_b200/host/revcomp_main.c
 	@mkdir -p bin
@@ -38,6 +39,10 @@ bin/revComp: imsame_b200/host/revcomp_main.c
 tools: tools/int_peak
 tools/int_peak: tools/int_peak.cu
 	$(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -o $@ tools/int_peak.cu
+
+bin/all_vs_all_metagenomes_IMSAME.sh: scripts/all_vs_all_metagenomes_IMSAME.sh
+	@mkdir -p bin
+	cp scripts/all_vs_all_metagenomes_IMSAME.sh $@ && chmod +x $@
 
 oracle: oracle/_build/liboracle.so
 oracle/_build/liboracle.so: oracle/imsame_oracle.c oracle/imsame_oracle.h

@@ -60,7 +60,7 @@ class Stats(C.Structure):
 SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "imsame_gpu_last_cuda_error",
            "imsame_gpu_set_stream", "imsame_gpu_align", "imsame_gpu_set_query", "imsame_gpu_set_db",
            "imsame_gpu_run", "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch",
-           "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
+           "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
 _lib = None
 
@@ -97,6 +97,10 @@ def lib():
         l.imsame_gpu_fetch.argtypes = [vp, vp, vp, vp]
         l.imsame_gpu_nw_batch.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp,
                                           C.POINTER(C.c_float)]
+        l.imsame_gpu_traceback.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(SeqInfo), C.POINTER(Params), vp, vp,
+                                           C.POINTER(C.POINTER(C.c_uint32)), vp]
+        l.imsame_gpu_free.argtypes = [vp]
+        l.imsame_gpu_free.restype = None
         l.imsame_gpu_host_alloc.argtypes = [u64]
         l.imsame_gpu_host_alloc.restype = vp
         l.imsame_gpu_host_free.argtypes = [vp]
@@ -238,6 +242,24 @@ class Imsame:
         out = np.zeros(self.nq, dtype=BEST_DTYPE)
         self._check(lib().imsame_gpu_fetch(self._h, C.c_void_p(d_keys), C.c_void_p(d_payload), out.ctypes.data))
         return out
+
+    # -- winners-only traceback (device) + text (host/render.c): the body of the .align records
+    def traceback(self, db, query, best, params=None, db_breaks=None):
+        """returns (ops_off uint64[nq+1], ops uint32[], cell_xy uint32[nq,4])"""
+        params = params or make_params()
+        d, k1 = _seqinfo(db[0], db[1], db_breaks)
+        q, k2 = _seqinfo(query[0], query[1])
+        nq = int(q.n_seqs)
+        best = np.ascontiguousarray(best, dtype=BEST_DTYPE)
+        ops_off = np.zeros(nq + 1, dtype=np.uint64)
+        cell = np.zeros((nq, 4), dtype=np.uint32)
+        ops_p = C.POINTER(C.c_uint32)()
+        self._check(lib().imsame_gpu_traceback(self._h, C.byref(d), C.byref(q), C.byref(params), best.ctypes.data,
+                                               ops_off.ctypes.data, C.byref(ops_p), cell.ctypes.data))
+        n = int(ops_off[nq])
+        ops = np.ctypeslib.as_array(ops_p, shape=(max(n, 1),))[:n].copy()
+        lib().imsame_gpu_free(C.cast(ops_p, C.c_void_p))
+        return ops_off, ops, cell
 
     # -- NW on explicit pairs
     def nw_batch(self, xs, ys, igap=5, egap=2):

@@ -45,7 +45,7 @@ int imsame_format_header(char *dst, uint64_t read, uint64_t db_seq, uint32_t len
                          uint64_t ylen);
 /* alignment text from a device traceback (ops = run-length path from the best
  * cell back to the border, see csrc/traceback.cuh), src/alignmentFunctions.c:230-271,493-560.
- * Returns bytes written (without the terminating 0). dst needs 4*(xlen+ylen)+256 bytes. */
+ * Returns bytes written (without the terminating 0). dst needs 6*(xlen+ylen)+256 bytes. */
 uint64_t imsame_render_alignment(char *dst, const unsigned char *X, uint32_t xlen, const unsigned char *Y,
                                  uint32_t ylen, uint32_t bx, uint32_t by, const uint32_t *ops,
                                  uint64_t n_ops);

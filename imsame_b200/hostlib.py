@@ -37,8 +37,25 @@ def lib():
         l.imsame_synth_query_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                                C.c_double, C.c_uint32, C.c_void_p]
         l.imsame_synth_write_fasta.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_char]
+        l.imsame_format_header.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64]
+        l.imsame_render_alignment.restype = C.c_uint64
+        l.imsame_render_alignment.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.c_void_p, C.c_uint64]
         _lib = l
     return _lib
+
+
+def render_record(read, db_seq, length, identities, x, y, bx, by, ops):
+    """header + alignment text of one .align record (src/alignmentFunctions.c:167-168)"""
+    x = np.ascontiguousarray(x, dtype=np.uint8)
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    ops = np.ascontiguousarray(ops, dtype=np.uint32)
+    hdr = C.create_string_buffer(256)
+    hl = lib().imsame_format_header(hdr, read, db_seq, length, identities, len(y))
+    buf = C.create_string_buffer(6 * (len(x) + len(y)) + 256)
+    tl = lib().imsame_render_alignment(buf, x.ctypes.data, len(x), y.ctypes.data, len(y), int(bx), int(by),
+                                       ops.ctypes.data, len(ops))
+    return hdr.raw[:hl] + buf.raw[:tl]
 
 
 class SynthPool:

@@ -370,7 +370,7 @@ int orc_align_sequential(const orc_seqs *db, const orc_seqs *q, const orc_params
                     uint64_t pos = ix.pos[h - 1], s = ix.sid[h - 1];
                     z.hits++;
                     int64_t n = orc_extend(db, q, pos, cp + 1, cr, s);
-                    if (!(orc_evalue(n, ylen, db->total_len) < p->min_e_value)) continue;
+                    if (!(orc_evalue(n, ylen, p->db_total_len_global ? p->db_total_len_global : db->total_len) < p->min_e_value)) continue;
                     z.evalue_pass++;
                     uint64_t xlen = db->start[s + 1] - db->start[s];
                     if (xlen > ORC_MAX_READ || ylen > ORC_MAX_READ) { free_index(&ix); free(text); return -5; }
@@ -435,7 +435,7 @@ int orc_align_bulk(const orc_seqs *db, const orc_seqs *q, const orc_params *p, o
                 /* key order: e ascending, pos descending; skip anything not better */
                 if (b->accepted && !((uint64_t)e < b->qpos_end || ((uint64_t)e == b->qpos_end && pos > b->db_pos))) continue;
                 int64_t n = orc_extend(db, q, pos, (uint64_t)e + 1, r, s);
-                if (!(orc_evalue(n, ylen, db->total_len) < p->min_e_value)) continue;
+                if (!(orc_evalue(n, ylen, p->db_total_len_global ? p->db_total_len_global : db->total_len) < p->min_e_value)) continue;
                 z.evalue_pass++;
                 uint64_t ci;
                 for (ci = 0; ci < cn; ci++) if (cache[ci].s == s) break;

@@ -44,6 +44,8 @@ typedef struct {
     int igap, egap;     /* negated, as stored in HashTableArgs (src/IMSAME.c:565,568) */
     uint64_t n_threads; /* only defines the chunk starts (src/IMSAME.c:414,433) */
     int k;              /* seed length; the reference has FIXED_K = 12 */
+    /* database shards (multi-GPU tests): 0 = db is the whole database */
+    uint64_t db_total_len_global; /* database->total_len used by the e-value (src/alignmentFunctions.c:384) */
 } orc_params;
 
 typedef struct {

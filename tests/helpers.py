@@ -26,7 +26,7 @@ class OrcSeqs(C.Structure):
 class OrcParams(C.Structure):
     _fields_ = [("min_e_value", C.c_longdouble), ("min_coverage", C.c_longdouble),
                 ("min_identity", C.c_longdouble), ("igap", C.c_int), ("egap", C.c_int),
-                ("n_threads", C.c_uint64), ("k", C.c_int)]
+                ("n_threads", C.c_uint64), ("k", C.c_int), ("db_total_len_global", C.c_uint64)]
 
 
 class OrcBest(C.Structure):
@@ -74,7 +74,7 @@ def oracle():
     return _oracle
 
 
-def default_params(n_threads=4, evalue=None, coverage=0.5, identity=0.5, igap=5, egap=2):
+def default_params(n_threads=4, evalue=None, coverage=0.5, identity=0.5, igap=5, egap=2, db_total_len_global=0):
     """Thresholds exactly as src/IMSAME.c:44-47,552-569 derives them."""
     p = OrcParams()
     if evalue is None:
@@ -87,6 +87,7 @@ def default_params(n_threads=4, evalue=None, coverage=0.5, identity=0.5, igap=5,
     p.egap = -int(egap)
     p.n_threads = n_threads
     p.k = 12
+    p.db_total_len_global = db_total_len_global
     return p
 
 

@@ -1,0 +1,127 @@
+"""Host-side C (no GPU): FASTA ingest, exact threshold tables, renderer + device-function
+emulators, revComp, C-ABI symbol export, CLI argument handling."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as hp
+
+G = os.path.join(hp.ROOT, "tests", "golden")
+
+
+@pytest.mark.parametrize("name,is_db", [("dirty.db.fa", True), ("dirty.q.fa", False), ("synth150.db.fa", True)])
+def test_fasta_loader_matches_oracle_loader(built, name, is_db):
+    from imsame_b200 import hostlib as H
+    seq, start, brk = H.load_fasta(os.path.join(G, name), is_db)
+    o = hp.OracleSeqs(os.path.join(G, name), is_db)
+    oseq, ostart, obrk = o.numpy()
+    assert np.array_equal(seq, oseq) and np.array_equal(start, ostart)
+    if is_db:
+        assert np.array_equal(brk, obrk)
+        if name.startswith("dirty"):
+            assert len(brk) > 10
+    assert set(np.unique(seq)) <= set(b"ACGT")
+
+
+def test_threshold_tables_are_exact(built):
+    from imsame_b200 import api, hostlib as H
+    lib = hp.oracle()
+    for min_e, total in ((api.default_evalue(), 15_000_000), (1e-5, 2_500_000_000), (0.5, 1000)):
+        nmin, lmin, imin = H.threshold_tables(min_e, 0.5, 0.5, total)
+        for ylen in (11, 12, 100, 150, 250, 2999, 3000):
+            n = int(nmin[ylen])
+            if n == 65535:
+                continue
+            assert lib.orc_evalue(n, ylen, total) < min_e
+            if n > 0:
+                assert not (lib.orc_evalue(n - 1, ylen, total) < min_e)
+    assert int(H.threshold_tables(api.default_evalue(), 0.5, 0.5, 15_000_000)[0][150]) == 61
+    assert int(H.threshold_tables(api.default_evalue(), 0.5, 0.5, 2_500_000_000)[0][250]) == 66
+    for cov, ident in ((0.5, 0.5), (0.3, 0.6), (0.8, 0.9), (1.0, 1.0)):
+        _, lmin, imin = H.threshold_tables(1e-20, cov, ident, 1000)
+        ld = np.longdouble
+        for ylen in (1, 7, 150, 250, 3000):
+            l = int(lmin[ylen])
+            assert ld(l) / ld(ylen) >= ld(cov) and not (ld(l - 1) / ld(ylen) >= ld(cov))
+        for ln in (1, 10, 149, 300, 6000):
+            i = int(imin[ln])
+            assert ld(i) / ld(ln) >= ld(ident) and (i == 0 or not (ld(i - 1) / ld(ln) >= ld(ident)))
+        assert imin[0] == 65535
+
+
+@pytest.mark.parametrize("prog,args", [("nw_emul", ["400", "3"]), ("extend_emul", ["5"]), ("tb_emul", ["300", "4"])])
+def test_device_functions_on_cpu(built, prog, args, tmp_path):
+    """the HD functions the kernels are made of (nw_core.cuh, extend.cuh, traceback.cuh) + render.c,
+    compiled for the host and stepped as a 32-lane warp, against the oracle"""
+    exe = str(tmp_path / prog)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    objs = []
+    for src in ("oracle/imsame_oracle.c", "imsame_b200/host/render.c"):
+        o = str(tmp_path / (os.path.basename(src) + ".o"))
+        subprocess.check_call([cc, "-O2", "-c", os.path.join(hp.ROOT, src), "-o", o])
+        objs.append(o)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(hp.ROOT, "tests", "emul", prog + ".cpp")]
+                          + objs + ["-lm"])
+    r = subprocess.run([exe] + args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "0 mismatches" in r.stdout
+
+
+def test_revcomp_matches_reference_semantics(built, tmp_path):
+    src = tmp_path / "in.fa"
+    src.write_bytes(b">a x\nACGTNnacgu\nGG\n>b\nTTTT\nCA\n>c only header\n>d\nacgtRYKM\n")
+    out = tmp_path / "out.fa"
+    subprocess.check_call([os.path.join(hp.ROOT, "bin", "revComp"), str(src), str(out)])
+    assert out.read_bytes() == b">d\nMKYRacgt\n>c only header\n\n>b\nTGAAAA\n>a x\nCCacgtnNACGT\n"
+    if os.path.exists(hp.REF_REVCOMP):
+        ref = tmp_path / "ref.fa"
+        subprocess.check_call([hp.REF_REVCOMP, str(src), str(ref)])
+        assert ref.read_bytes() == out.read_bytes()
+        ref2 = tmp_path / "ref2.fa"
+        out2 = tmp_path / "out2.fa"
+        subprocess.check_call([hp.REF_REVCOMP, os.path.join(G, "dirty.db.fa"), str(ref2)])
+        subprocess.check_call([os.path.join(hp.ROOT, "bin", "revComp"), os.path.join(G, "dirty.db.fa"), str(out2)])
+        assert ref2.read_bytes() == out2.read_bytes()
+
+
+def test_c_abi_exports_every_declared_symbol(built):
+    from imsame_b200 import api
+    hdr = open(os.path.join(hp.ROOT, "include", "imsame_gpu.h")).read()
+    declared = set(re.findall(r"\b(imsame_gpu_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(api.SYMBOLS), declared ^ set(api.SYMBOLS)
+    lib = C.CDLL(api.GPU_SO)
+    for name in sorted(declared):
+        assert getattr(lib, name) is not None
+    lib.imsame_gpu_strerror.restype = C.c_char_p
+    assert lib.imsame_gpu_strerror(-5) == b"Read size reached for gapped alignment."
+
+
+def test_no_gpu_means_error_not_fallback(built):
+    """without a CUDA device the product path must fail loudly"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from imsame_b200 import api
+    with pytest.raises(api.ImsameError) as e:
+        api.Imsame(0)
+    assert e.value.code == -1
+
+
+def test_cli_flags_and_errors(built, tmp_path):
+    exe = os.path.join(hp.ROOT, "bin", "IMSAME")
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert r.returncode == 1 and "USAGE:" in r.stdout and "-n_threads" in r.stdout
+    r = subprocess.run([exe, "-query", str(tmp_path / "missing.fa")], capture_output=True, text=True)
+    assert r.returncode == 255 and r.stdout == "ERR**** A query and database is required ****\n"
+    q = os.path.join(G, "dirty.q.fa")
+    r = subprocess.run([exe, "-query", q, "-db", q, "-coverage", "0"], capture_output=True, text=True)
+    assert r.returncode == 255 and "Min-coverage must be larger than zero" in r.stdout
+    if hp.have_reference():
+        for args in (["--help"], ["-query", "nope"], ["-query", q, "-db", q, "-identity", "-1"]):
+            a = subprocess.run([exe] + args, capture_output=True, text=True)
+            b = subprocess.run([hp.REF_BIN] + args, capture_output=True, text=True)
+            assert (a.returncode, a.stdout) == (b.returncode, b.stdout)

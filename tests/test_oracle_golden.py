@@ -1,0 +1,70 @@
+"""The oracle (CPU restatement) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  Runs anywhere: needs neither /root/reference nor a GPU."""
+import os
+
+import pytest
+
+import helpers as hp
+
+G = os.path.join(hp.ROOT, "tests", "golden")
+CASES = {
+    "synth150": dict(),
+    "dirty": dict(coverage=0.3, identity=0.6, evalue=1e-10, igap=4, egap=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_t1_bytes_equal_reference(name, tmp_path):
+    db = hp.OracleSeqs(os.path.join(G, f"{name}.db.fa"), True)
+    q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
+    out = str(tmp_path / "o.align")
+    best, st = hp.oracle_align(db, q, hp.default_params(n_threads=1, **CASES[name]), out_path=out)
+    assert open(out, "rb").read() == open(os.path.join(G, f"{name}.t1.align"), "rb").read()
+    want = open(os.path.join(G, f"{name}.stdout")).read()
+    assert f"[INFO] {st.accepted} reads ({q.s.n_seqs}) from the query were found in the database ({db.s.n_seqs})" in want
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_t4_headers_equal_reference(name, tmp_path):
+    """-n_threads changes which reads see the cross-read 'phantom' word"""
+    db = hp.OracleSeqs(os.path.join(G, f"{name}.db.fa"), True)
+    q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
+    out = str(tmp_path / "o.align")
+    hp.oracle_align(db, q, hp.default_params(n_threads=4, **CASES[name]), out_path=out)
+    got = sorted(l for l in open(out, "rb").read().split(b"\n") if hp.HEADER_RE.match(l))
+    want = [l for l in open(os.path.join(G, f"{name}.t4.headers"), "rb").read().split(b"\n") if l]
+    assert got == want
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("n_threads", [1, 3, 4])
+def test_bulk_min_key_form_equals_scan_order(name, n_threads):
+    """winner(read) = argmin (k-mer end asc, db pos desc) over accepted candidates == first accepted"""
+    db = hp.OracleSeqs(os.path.join(G, f"{name}.db.fa"), True)
+    q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
+    p = hp.default_params(n_threads=n_threads, **CASES[name])
+    a, _ = hp.oracle_align(db, q, p)
+    b, _ = hp.oracle_align(db, q, p, bulk=True)
+    nq = int(q.s.n_seqs)
+    assert hp.best_to_records(a, nq) == hp.best_to_records(b, nq)
+    assert len(hp.best_to_records(a, nq)) > 5
+
+
+@pytest.mark.skipif(not hp.have_reference(), reason="oracle/_ref/IMSAME not built (no /root/reference here)")
+@pytest.mark.parametrize("seed,div,n_threads", [(1001, 0.03, 1), (7, 0.10, 4), (99, 0.20, 8)])
+def test_oracle_vs_live_reference(seed, div, n_threads, tmp_path):
+    """fresh seeded inputs through the real reference binary"""
+    from imsame_b200 import hostlib as H
+    pool = H.SynthPool(seed, 3, 60000)
+    nd, nq, L = 6000, 600, 150
+    dbf, qf, ref_out, orc_out = (str(tmp_path / n) for n in ("db.fa", "q.fa", "ref.align", "orc.align"))
+    H.write_fasta(dbf, pool.db_reads(0, nd, L), nd, L, "d")
+    H.write_fasta(qf, pool.query_reads(0, nq, L, div), nq, L, "q")
+    pool.close()
+    hp.run_reference(qf, dbf, ref_out, n_threads=n_threads)
+    db, q = hp.OracleSeqs(dbf, True), hp.OracleSeqs(qf, False)
+    hp.oracle_align(db, q, hp.default_params(n_threads=n_threads), out_path=orc_out)
+    if n_threads == 1:
+        assert open(ref_out, "rb").read() == open(orc_out, "rb").read()
+    assert hp.parse_align_headers(ref_out) == hp.parse_align_headers(orc_out)
+    assert len(hp.parse_align_headers(ref_out)) > 100
