@@ -58,7 +58,7 @@ struct imsame_ctx {
     bool have_db = false;
 
     // tables + work buffers
-    uint16_t *d_nmin = nullptr, *d_lmin = nullptr, *d_imin = nullptr;
+    uint16_t *d_nmin = nullptr, *d_lmin = nullptr, *d_imin = nullptr, *d_lut = nullptr;
     unsigned long long *hkeys = nullptr, *hvals = nullptr;
     uint32_t hcap = 0;
     PairRec *pairs = nullptr;
@@ -194,6 +194,10 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
         if ((rc = dev_alloc(ctx, &ctx->d_nmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_lmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_imin, 2 * IMSAME_MAX_READ_SIZE + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_lut, EXT_LUT_SIZE))) return rc;
+        std::vector<uint16_t> lut(EXT_LUT_SIZE);
+        build_ext_lut(lut.data());
+        CK(cudaMemcpy(ctx->d_lut, lut.data(), EXT_LUT_SIZE * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     if (want_cap > ctx->hcap) {
         dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
@@ -356,7 +360,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     free_query(ctx);
     free_db(ctx);
     dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
-    dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin);
+    dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
     dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->carry); dev_free(ctx->stage);
@@ -603,7 +607,7 @@ static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, u
                 PhaseScope ps(ctx, PH_K2);
                 ScanArgs a;
                 a.db = dm; a.q = qm; a.off = ctx->off; a.qpos = ctx->qpos; a.brk = s.brk; a.n_brk = s.n_brk;
-                a.nmin = ctx->d_nmin; a.seg_pos_base = p->db_pos_base + s.pos_base;
+                a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
                 a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = keys;
                 a.counters = ctx->d_counters; a.overflow = ctx->d_overflow;
                 scan_kernel<<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);

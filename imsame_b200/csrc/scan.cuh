@@ -27,6 +27,7 @@ struct ScanArgs {
     const uint32_t *brk;   // database word breaks (segment-local), ascending
     uint32_t n_brk;
     const uint16_t *nmin;  // e-value threshold table by ylen
+    const uint16_t *lut;   // extension walk table (extend.cuh), EXT_LUT_SIZE entries
     uint64_t seg_pos_base; // global index of the segment's first base
     unsigned long long *hkeys, *hvals;  // pair table (open addressing)
     uint32_t hmask;
@@ -80,6 +81,9 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
     __shared__ uint32_t s_xs[SCAN_WARPS][32];
     __shared__ uint32_t s_xe[SCAN_WARPS][32];
+    __shared__ uint16_t s_lut[EXT_LUT_SIZE];
+    for (int i = threadIdx.x; i < EXT_LUT_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = (a.db.total + 31) / 32;
     const uint32_t gw = blockIdx.x * SCAN_WARPS + warp, nw = gridDim.x * SCAN_WARPS;
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             const uint32_t r = find_read(a.q, e);
             const uint32_t ys = read_start(a.q, r);
             const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
-            const int n = extend_hit(a.db.pk, a.q.pk, p, e, s_xs[warp][o], s_xe[warp][o], ys, yend);
+            const int n = extend_hit_lut(s_lut, a.db.pk, a.q.pk, p, e, s_xs[warp][o], s_xe[warp][o], ys, yend);
             c_hits++;
             if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
             if (n < 0 || n >= (int)a.nmin[yend - ys]) {

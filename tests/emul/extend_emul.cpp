@@ -54,6 +54,8 @@ int main(int argc, char **argv) {
         int64_t lo = r == 0 ? (int64_t)qs[r] : (int64_t)qs[r] - 1;
         for (int64_t e = lo + 11; e < (int64_t)qs[r + 1]; e++) qwords.emplace(fetch16(qpk.data(), e - 11) & KMASK, (uint32_t)e);
     }
+    std::vector<uint16_t> lut(EXT_LUT_SIZE);
+    build_ext_lut(lut.data());
     long hits = 0, bad = 0;
     for (size_t s = 0; s + 1 < ds.size(); s++)
         for (uint64_t x = ds[s] + 11; x < ds[s + 1]; x++) {
@@ -66,7 +68,9 @@ int main(int argc, char **argv) {
                 while (qs[r + 1] <= e) r++;
                 int64_t want = orc_extend(&db, &q, p, (uint64_t)e + 1, r, s);
                 int got = extend_hit(dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                int got2 = extend_hit_lut(lut.data(), dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
                 hits++;
+                if (want != got2) { if (bad++ < 10) printf("LUT MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got2); }
                 if (want != got) { if (bad++ < 10) printf("MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got); }
             }
         }
