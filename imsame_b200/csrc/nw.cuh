@@ -115,26 +115,35 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
             }
             const uint32_t ycols = (uint32_t)(halo >> 4) & ((1u << (2 * S)) - 1u);
             NwLane<S> L;
-            nw_lane_init<S>(L, x0, halo, first);
+            nw_lane_init<S>(L, x0, halo, first, lane);
+            const int cl = (Y1 - 1 - jb) % S;  // slot of the last column inside its strip (warp-uniform)
+            const bool owns_last = (Y1 >= j0) && (Y1 < j0 + S);
             NwLink out;
             out.a = out.ap = out.b = out.bp = out.mfs = out.mfy = out.mfp = 0;
             const NwLink *cin = carry0 ? carry0 + (size_t)((pass + 1) & 1) * MAX_READ : nullptr;
             NwLink *cout = carry0 ? carry0 + (size_t)(pass & 1) * MAX_READ : nullptr;
             const int steps = X1 + nl - 1;
-            for (int t = 0; t < steps; t++) {
-                const int i = t - lane + 1;
-                NwLink in = shfl_up_link(out);
-                const bool act = (lane < nl) && (i >= 1) && (i <= X1);
-                if (act) {
-                    const uint32_t xi = sx[i];
-                    if (lane == 0) in = (jb == 0) ? nw_first_link(xi, y0) : cin[i];
-                    uint32_t d = ycols ^ (xi * 0x55555555u);
-                    const uint32_t mm = (d | (d >> 1)) & 0x55555555u;
-                    nw_row<S, TB>(L, in, out, i, j0, mm, a.igap, a.egap, X1, Y1, first,
-                                  TB ? tb_pair + (size_t)(i - 1) * tb_str + (j0 - 1) : nullptr);
-                    if (more && lane == 31) cout[i] = out;
-                }
+            // lane l works on row t - l + 1; the two row histories swap roles with the step parity
+#define IMS_NW_STEP(T_, PREV1, PREV2)                                                                   \
+    {                                                                                                   \
+        const int i = (T_) - lane + 1;                                                                  \
+        NwLink in = shfl_up_link(out);                                                                  \
+        const bool act = (lane < nl) && (i >= 1) && (i <= X1);                                          \
+        if (act) {                                                                                      \
+            const uint32_t xi = sx[i];                                                                  \
+            if (lane == 0) in = (jb == 0) ? nw_first_link(xi, y0) : cin[i];                             \
+            const uint32_t d_ = ycols ^ (xi * 0x55555555u);                                             \
+            const uint32_t mm = (d_ | (d_ >> 1)) & 0x55555555u;                                         \
+            nw_row<S, TB>(L, PREV1, PREV2, in, out, i, j0, mm, a.igap, a.egap, X1, Y1, cl, owns_last,   \
+                          first, TB ? tb_pair + (size_t)(i - 1) * tb_str + (j0 - 1) : nullptr);         \
+            if (more && lane == 31) cout[i] = out;                                                      \
+        }                                                                                               \
+    }
+            for (int t = 0; t < steps; t += 2) {
+                IMS_NW_STEP(t, L.r0, L.r1)
+                if (t + 1 < steps) IMS_NW_STEP(t + 1, L.r1, L.r0)
             }
+#undef IMS_NW_STEP
             // warp reduction of the best border cell ("last in row-major order" on ties)
             NwBest b = L.best;
             if (lane >= nl) b.s = NW_NEG * 2;
@@ -151,12 +160,12 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
             __syncwarp();
         }
         if (lane == 0) {
-            const uint32_t len = (uint32_t)wbest.p >> 16, id = (uint32_t)wbest.p & 0xFFFFu;
+            const uint32_t len = nw_stat_len(wbest.p), id = nw_stat_ids(wbest.p);
             // src/alignmentFunctions.c:163 through the host-built exact tables
             const bool ok = (X1 >= 1 && Y1 >= 1) && len > 0 && len >= a.lmin[ylen] && id >= a.imin[len];
             PairRes z;
             z.score = wbest.s; z.bx = (uint32_t)wbest.i; z.by = (uint32_t)wbest.j;
-            z.stats = (uint32_t)wbest.p | (ok ? 0x80000000u : 0u);
+            z.stats = (len << 16) | id | (ok ? 0x80000000u : 0u);
             a.res[idx] = z;
             if (ok && a.best) atomicMin(&a.best[pr.r], (unsigned long long)pr.key);
             my_cells += (unsigned long long)X1 * (unsigned long long)Y1;

@@ -28,7 +28,7 @@ static NwBest run_pair(const unsigned char *X, int xlen, const unsigned char *Y,
             int j0 = jb + l * S + 1;
             uint64_t halo = 0;
             for (int k = 0; k < S + 2; k++) { int j = j0 - 2 + k; uint64_t c = (j >= 0 && j < ylen) ? code(Y[j]) : 0; halo |= c << (2 * k); }
-            nw_lane_init<S>(lanes[l], code(X[0]), halo, jb == 0 && l == 0);
+            nw_lane_init<S>(lanes[l], code(X[0]), halo, jb == 0 && l == 0, l);
         }
         for (int t = 0; t <= X1 + nl - 2; t++) {
             for (int l = nl - 1; l >= 0; l--) {
@@ -39,7 +39,9 @@ static NwBest run_pair(const unsigned char *X, int xlen, const unsigned char *Y,
                 uint32_t mm = 0;
                 for (int c = 0; c < S; c++) { int j = j0 + c; uint32_t y = j < ylen ? code(Y[j]) : 0; if (y != code(X[i])) mm |= 1u << (2 * c); }
                 NwLink out;
-                nw_row<S>(lanes[l], in, out, i, j0, mm, igap, egap, X1, Y1, jb == 0 && l == 0);
+                { const int cl = (Y1 - 1 - jb) % S; const bool owns = Y1 >= j0 && Y1 < j0 + S;
+                  if (t & 1) nw_row<S>(lanes[l], lanes[l].r1, lanes[l].r0, in, out, i, j0, mm, igap, egap, X1, Y1, cl, owns, jb == 0 && l == 0);
+                  else nw_row<S>(lanes[l], lanes[l].r0, lanes[l].r1, in, out, i, j0, mm, igap, egap, X1, Y1, cl, owns, jb == 0 && l == 0); }
                 outs[l] = out;
                 if (l == 31) carry_next[i] = out;
             }
@@ -89,11 +91,11 @@ int main(int argc, char **argv) {
             case 4: b = run_pair<3>(X.data(), xlen, Y.data(), ylen, igap, egap); break;
             default: b = run_pair<4>(X.data(), xlen, Y.data(), ylen, igap, egap); break;
         }
-        bool ok = b.s == os && (uint32_t)b.i == obx && (uint32_t)b.j == oby && (uint32_t)(b.p >> 16) == olen && (uint32_t)(b.p & 0xFFFF) == oid;
+        bool ok = b.s == os && (uint32_t)b.i == obx && (uint32_t)b.j == oby && nw_stat_len(b.p) == olen && nw_stat_ids(b.p) == oid;
         if (!ok) {
             bad++;
             if (bad < 10) printf("MISMATCH it=%d xlen=%d ylen=%d gaps=%d,%d: emul (%d,%d,%d,%d,%d) oracle (%d,%u,%u,%u,%u)\n", it, xlen, ylen, igap, egap,
-                                 b.s, b.i, b.j, b.p >> 16, b.p & 0xFFFF, os, obx, oby, olen, oid);
+                                 b.s, b.i, b.j, (int)nw_stat_len(b.p), (int)nw_stat_ids(b.p), os, obx, oby, olen, oid);
         }
     }
     printf("%d cases, %d mismatches\n", n, bad);

@@ -32,7 +32,7 @@ static NwBest run_pair_tb(const unsigned char *X, int xlen, const unsigned char 
             int j0 = jb + l * S + 1;
             uint64_t halo = 0;
             for (int k = 0; k < S + 2; k++) { int j = j0 - 2 + k; uint64_t c = (j >= 0 && j < ylen) ? code(Y[j]) : 0; halo |= c << (2 * k); }
-            nw_lane_init<S>(lanes[l], code(X[0]), halo, jb == 0 && l == 0);
+            nw_lane_init<S>(lanes[l], code(X[0]), halo, jb == 0 && l == 0, l);
         }
         for (int t = 0; t <= X1 + nl - 2; t++)
             for (int l = nl - 1; l >= 0; l--) {
@@ -43,8 +43,10 @@ static NwBest run_pair_tb(const unsigned char *X, int xlen, const unsigned char 
                 uint32_t mm = 0;
                 for (int c = 0; c < S; c++) { int j = j0 + c; uint32_t y = j < ylen ? code(Y[j]) : 0; if (y != code(X[i])) mm |= 1u << (2 * c); }
                 NwLink out;
-                nw_row<S, true>(lanes[l], in, out, i, j0, mm, igap, egap, X1, Y1, jb == 0 && l == 0,
-                                tb.data() + (size_t)(i - 1) * stride + (j0 - 1));
+                { const int cl = (Y1 - 1 - jb) % S; const bool owns = Y1 >= j0 && Y1 < j0 + S;
+                  uint16_t *tbr = tb.data() + (size_t)(i - 1) * stride + (j0 - 1);
+                  if (t & 1) nw_row<S, true>(lanes[l], lanes[l].r1, lanes[l].r0, in, out, i, j0, mm, igap, egap, X1, Y1, cl, owns, jb == 0 && l == 0, tbr);
+                  else nw_row<S, true>(lanes[l], lanes[l].r0, lanes[l].r1, in, out, i, j0, mm, igap, egap, X1, Y1, cl, owns, jb == 0 && l == 0, tbr); }
                 outs[l] = out;
                 if (l == 31) carry_next[i] = out;
             }
@@ -95,8 +97,8 @@ int main(int argc, char **argv) {
         uint32_t ex, ey;
         uint32_t nops = tb_walk(tb.data(), stride, (uint32_t)b.i, (uint32_t)b.j, ops.data(), &ex, &ey);
         uint64_t tl = imsame_render_alignment(got.data(), X.data(), xlen, Y.data(), ylen, (uint32_t)b.i, (uint32_t)b.j, ops.data(), nops);
-        bool ok = b.s == os && (uint32_t)b.i == obx && (uint32_t)b.j == oby && (uint32_t)(b.p >> 16) == olen &&
-                  (uint32_t)(b.p & 0xFFFF) == oid && tl == strlen(want.data()) && memcmp(got.data(), want.data(), tl) == 0;
+        bool ok = b.s == os && (uint32_t)b.i == obx && (uint32_t)b.j == oby && nw_stat_len(b.p) == olen &&
+                  nw_stat_ids(b.p) == oid && tl == strlen(want.data()) && memcmp(got.data(), want.data(), tl) == 0;
         if (!ok) { bad++; if (bad < 5) printf("MISMATCH it=%d xlen=%d ylen=%d\n--- want\n%s--- got\n%s", it, xlen, ylen, want.data(), got.data()); }
     }
     printf("%d cases, %d mismatches\n", n, bad);
