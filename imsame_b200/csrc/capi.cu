@@ -68,6 +68,7 @@ struct imsame_ctx {
     int *d_overflow = nullptr;
     unsigned long long *keys = nullptr, *payload = nullptr;
     uint64_t keys_cap = 0;
+    uint32_t *d_bins = nullptr;  // [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors | then NBINS work heads
     NwLink *carry = nullptr;
     uint64_t carry_warps = 0;
     uint8_t *stage = nullptr;
@@ -221,7 +222,6 @@ int launch_nw(imsame_ctx *ctx, NwArgs a) {
         ctx->nw_grid[S] = std::max(1, per_sm) * ctx->n_sm;
     }
     a.s_class = S;
-    CK(cudaMemsetAsync(a.work, 0, sizeof(uint32_t), ctx->stream));
     nw_kernel<S, TB><<<ctx->nw_grid[S], NW_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     ctx->k3_launches++;
@@ -230,10 +230,9 @@ int launch_nw(imsame_ctx *ctx, NwArgs a) {
 }
 
 template <bool TB>
-int launch_nw_classes(imsame_ctx *ctx, const NwArgs &a, uint32_t class_mask) {
+int launch_nw_class(imsame_ctx *ctx, const NwArgs &a, int c) {
     int rc = IMSAME_OK;
-    for (int c = 1; c <= 8 && !rc; c++) {
-        if (!(class_mask & (1u << c))) continue;
+    {
         switch (c) {
             case 1: rc = launch_nw<1, TB>(ctx, a); break;
             case 2: rc = launch_nw<2, TB>(ctx, a); break;
@@ -244,6 +243,19 @@ int launch_nw_classes(imsame_ctx *ctx, const NwArgs &a, uint32_t class_mask) {
             case 7: rc = launch_nw<7, TB>(ctx, a); break;
             default: rc = launch_nw<8, TB>(ctx, a); break;
         }
+    }
+    return rc;
+}
+
+// unsorted explicit pairs: every class kernel walks the whole list and skips the other classes
+template <bool TB>
+int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 9 zeroed */) {
+    int rc = IMSAME_OK;
+    a.check_class = 1;
+    for (int c = 1; c <= 8 && !rc; c++) {
+        if (!(class_mask & (1u << c))) continue;
+        a.work = work_heads + c;
+        rc = launch_nw_class<TB>(ctx, a, c);
     }
     return rc;
 }
@@ -363,7 +375,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
-    dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->carry); dev_free(ctx->stage);
+    dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->d_bins); dev_free(ctx->carry); dev_free(ctx->stage);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -567,11 +579,16 @@ static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, u
             ctx->keys_cap = nq;
         }
     }
+    if (!ctx->d_bins && (rc = dev_alloc(ctx, &ctx->d_bins, 6ull * NW_NBINS + 8))) return rc;
     unsigned long long *keys = d_keys ? (unsigned long long *)d_keys : ctx->keys;
     unsigned long long *payload = d_payload ? (unsigned long long *)d_payload : ctx->payload;
 
+    // pair table: the reference semantics let ~0.2-0.4 % of random hits through the e-value test
+    // (idents counts every match of the walk, src/alignmentFunctions.c:323,346), i.e. ~100 candidate
+    // database reads per query read against a 10 M-read database; start at 64 slots per read per
+    // segment and grow on overflow
     uint32_t cap = 1u << 20;
-    while (cap < 8ull * nq && cap < (1u << 30)) cap <<= 1;
+    while (cap < 64ull * nq && cap < (1u << 28)) cap <<= 1;
     cap = std::max(cap, ctx->hcap);
     if ((rc = ensure_carry(ctx, ctx->q_maxlen))) return rc;
 
@@ -613,20 +630,39 @@ static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, u
                 scan_kernel<<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
                 ctx->launches++; ctx->k2_launches++;
             }
+            uint32_t *bin_count = ctx->d_bins, *bin_off = ctx->d_bins + NW_NBINS, *bin_work = ctx->d_bins + 3 * NW_NBINS + 4;
+            uint32_t *launch_range = ctx->d_bins + 4 * NW_NBINS + 4;
             {
                 PhaseScope ps(ctx, PH_K2B);
-                const int g = std::min<uint32_t>((ctx->hcap + 255) / 256, (uint32_t)ctx->n_sm * 16);
-                compact_kernel<<<g, 256, 0, ctx->stream>>>(ctx->hkeys, ctx->hvals, ctx->hcap, ctx->pairs, ctx->d_small);
-                ctx->launches++;
+                CK(cudaMemsetAsync(ctx->d_bins, 0, (6ull * NW_NBINS + 8) * sizeof(uint32_t), ctx->stream));
+                BinArgs b;
+                b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.q = qm;
+                b.band_width = (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS;
+                b.bin_count = bin_count; b.bin_off = bin_off; b.pairs = ctx->pairs;
+                const int g = std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS),
+                                                 (uint32_t)ctx->n_sm * 8);
+                bin_kernel<0><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
+                bin_offsets_kernel<<<1, 32, 0, ctx->stream>>>(bin_count, bin_off, launch_range, ctx->d_small,
+                                                            (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u);
+                bin_kernel<1><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
+                ctx->launches += 3;
             }
             {
                 PhaseScope ps(ctx, PH_K3);
                 NwArgs a;
-                a.db = dm; a.q = qm; a.pairs = ctx->pairs; a.res = ctx->res; a.n_pairs = ctx->d_small;
-                a.work = ctx->d_small + 1; a.igap = p->igap; a.egap = p->egap; a.lmin = ctx->d_lmin; a.imin = ctx->d_imin;
+                a.db = dm; a.q = qm; a.pairs = ctx->pairs; a.res = ctx->res;
+                a.igap = p->igap; a.egap = p->egap; a.lmin = ctx->d_lmin; a.imin = ctx->d_imin;
                 a.best = keys; a.cells = ctx->d_counters + 4; a.carry = ctx->carry; a.s_class = 0;
-                a.tb = nullptr; a.tb_off = nullptr;
-                if ((rc = launch_nw_classes<false>(ctx, a, ctx->class_mask))) return rc;
+                a.tb = nullptr; a.tb_off = nullptr; a.check_class = 0;
+                // ascending bands: an accepted early candidate prunes the read's later ones
+                for (int band = 0; band < NW_BANDS; band++)
+                    for (int c = 1; c <= 8; c++) {
+                        if (!(ctx->class_mask & (1u << c))) continue;
+                        const int bin = c * NW_BANDS + band;
+                        a.range = launch_range + 2 * bin;
+                        a.work = bin_work + bin;
+                        if ((rc = launch_nw_class<false>(ctx, a, c))) return rc;
+                    }
             }
             {
                 PhaseScope ps(ctx, PH_SELECT);
@@ -765,7 +801,7 @@ struct PairBatch {
         const uint64_t xw = (xt + 15) / 16 + PAD_WORDS, yw = (yt + 15) / 16 + PAD_WORDS;
         if ((rc = dev_alloc(ctx, &xpk, xw)) || (rc = dev_alloc(ctx, &ypk, yw)) ||
             (rc = dev_alloc(ctx, &dxs, (uint64_t)n + 1)) || (rc = dev_alloc(ctx, &dys, (uint64_t)n + 1)) ||
-            (rc = dev_alloc(ctx, &dsmall, 4)) || (rc = dev_alloc(ctx, &dp, n)) || (rc = dev_alloc(ctx, &dr, n)) ||
+            (rc = dev_alloc(ctx, &dsmall, 16)) || (rc = dev_alloc(ctx, &dp, n)) || (rc = dev_alloc(ctx, &dr, n)) ||
             (rc = dev_alloc(ctx, &dz, 2 * IMSAME_MAX_READ_SIZE + 1)) || (rc = dev_alloc(ctx, &dcells, 4)))
             return rc;
         CK(cudaMemsetAsync(xpk, 0, xw * 4, ctx->stream));
@@ -777,7 +813,8 @@ struct PairBatch {
         if ((rc = upload_pack(ctx, ya.data(), yt, ypk, PH_PACKQ))) return rc;
         std::vector<PairRec> hp(n);
         for (uint32_t i = 0; i < n; i++) { hp[i].r = i; hp[i].s = i; hp[i].key = 0; }
-        const uint32_t small[4] = {n, 0, 0, 0};
+        uint32_t small[16] = {0};
+        small[1] = n;  // range = [0, n); small[4..] = per-class work heads
         CK(cudaMemcpyAsync(dxs, xs.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(dys, ys.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(dp, hp.data(), (size_t)n * sizeof(PairRec), cudaMemcpyHostToDevice, ctx->stream));
@@ -789,9 +826,10 @@ struct PairBatch {
         NwArgs a;
         a.db.pk = xpk; a.db.start = dxs; a.db.blk = nullptr; a.db.n = n; a.db.total = xs[n]; a.db.fixed_len = 0;
         a.q.pk = ypk; a.q.start = dys; a.q.blk = nullptr; a.q.n = n; a.q.total = ys[n]; a.q.fixed_len = 0;
-        a.pairs = dp; a.res = dr; a.n_pairs = dsmall; a.work = dsmall + 1; a.igap = igap; a.egap = egap;
+        a.pairs = dp; a.res = dr; a.range = dsmall; a.work = dsmall + 4; a.igap = igap; a.egap = egap;
         a.lmin = dz; a.imin = dz; a.best = nullptr; a.cells = dcells; a.carry = ctx->carry; a.s_class = 0;
         a.tb = nullptr; a.tb_off = nullptr;
+        a.check_class = 1;
         return a;
     }
 };
@@ -815,7 +853,7 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
-    rc = launch_nw_classes<false>(ctx, a, pb.class_mask);
+    rc = launch_nw_classes<false>(ctx, a, pb.class_mask, pb.dsmall + 4);
     cudaEventRecord(e1, ctx->stream);
     std::vector<PairRes> hr(n_pairs);
     if (!rc) {
@@ -898,7 +936,7 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
         NwArgs a = pb.args(p->igap, p->egap);
         a.tb = d_tb;
         a.tb_off = d_tboff;
-        rc = launch_nw_classes<true>(ctx, a, pb.class_mask);
+        rc = launch_nw_classes<true>(ctx, a, pb.class_mask, pb.dsmall + 4);
         if (!rc) {
             tb_walk_kernel<<<std::min<uint32_t>((nb + 127) / 128, (uint32_t)ctx->n_sm * 8), 128, 0, ctx->stream>>>(
                 pb.dr, d_tb, d_tboff, d_str, nb, d_ops, d_opoff, d_nops, d_end);

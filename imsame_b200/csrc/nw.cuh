@@ -29,14 +29,20 @@ struct NwArgs {
     SeqMap db, q;
     const PairRec *pairs;
     PairRes *res;
-    const uint32_t *n_pairs;  // device counter written by the compaction kernel
-    uint32_t *work;           // atomic work-queue head
+    uint32_t *work;           // atomic work-queue head (relative to range[0])
     int igap, egap;
     const uint16_t *lmin, *imin;
     unsigned long long *best;  // per read scan-order key (atomicMin); may be null (nw_batch)
     unsigned long long *cells;  // [0] cells, [2] pairs evaluated
     NwLink *carry;             // 2 * MAX_READ links per warp of the grid, or null
     int s_class;               // pairs with min(ceil((ylen-1)/32), 8) != s_class are skipped
+    // Work range: pairs[range[0] .. range[1]) (device-resident offsets written by the binning
+    // kernels).  The scan orders candidates into (NW class, k-mer-end band) bins and the bins of
+    // a class are launched in ascending band order: the reference stops at a read's first
+    // accepted hit (src/alignmentFunctions.c:172,189), so once an early band has accepted a
+    // read, all its later candidates are pruned by the key comparison below instead of aligned.
+    const uint32_t *range;
+    int check_class;  // 1: unsorted explicit pairs (nw_batch / traceback): skip other classes here
     // TB = true only (K4, winners-only traceback): back-pointer codes per cell
     uint16_t *tb;              // codes of pair idx start at tb + tb_off[idx]
     const uint64_t *tb_off;
@@ -66,19 +72,19 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
     __shared__ uint8_t sx_all[NW_WARPS][NW_XBUF];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *sx = sx_all[warp];
-    const uint32_t n_pairs = *a.n_pairs;
+    const uint32_t r_begin = a.range[0], r_end = a.range[1];
     unsigned long long my_cells = 0, my_pairs = 0;
     NwLink *carry0 = a.carry ? a.carry + (size_t)(blockIdx.x * NW_WARPS + warp) * 2 * MAX_READ : nullptr;
 
     for (;;) {
         uint32_t idx = 0;
         if (lane == 0) idx = atomicAdd(a.work, 1u);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n_pairs) break;
+        idx = __shfl_sync(0xffffffffu, idx, 0) + r_begin;
+        if (idx >= r_end) break;
         const PairRec pr = a.pairs[idx];
         const uint32_t ys = read_start(a.q, pr.r);
         const uint32_t ylen = (a.q.fixed_len ? a.q.fixed_len : a.q.start[pr.r + 1] - ys);
-        if (nw_class_of(ylen) != a.s_class) continue;
+        if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
         if (a.best && pr.key >= a.best[pr.r]) {  // an earlier hit of this read is already accepted
             if (lane == 0) { PairRes z; z.score = 0; z.bx = z.by = 0; z.stats = 0; a.res[idx] = z; }
             continue;

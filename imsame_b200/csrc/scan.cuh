@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     unsigned long long c_words = 0, c_hits = 0, c_pass = 0, c_anom = 0;
 
     for (uint32_t tile = gw; tile < n_tiles; tile += nw) {
+        if (*(volatile int *)a.overflow) break;  // pair table too small: the host grows it and reruns
         const uint32_t q = tile * 32 + lane;  // index of the word's last base
         uint32_t cnt = 0, b0 = 0, xs = 0, xe = 0;
         if (q < a.db.total) {
@@ -156,35 +157,103 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     }
 }
 
-// K2b: pair table -> dense work queue (warp-aggregated atomic append); resets the table
-__global__ void compact_kernel(unsigned long long *hkeys, unsigned long long *hvals, uint32_t n_slots,
-                               PairRec *pairs, uint32_t *n_pairs) {
-    const int lane = threadIdx.x & 31;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n_slots;
-         base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + lane;
-        unsigned long long k = HASH_EMPTY, v = 0;
-        if (i < n_slots) {
-            k = hkeys[i];
-            if (k != HASH_EMPTY) {
-                v = hvals[i];
-                hkeys[i] = HASH_EMPTY;
-                hvals[i] = ~0ull;
+// K2b: pair table -> work queue ordered by (NW class, k-mer-end band).  Three small kernels:
+// histogram of the occupied slots per bin, exclusive scan of the NBINS counters, scatter with
+// block-aggregated atomics (one global atomic per bin per block); the scatter also resets the table.
+constexpr int NW_BANDS = 32;
+constexpr int NW_NBINS = 9 * NW_BANDS;  // classes 1..8
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_ITEMS = 16;  // slots per thread
+
+struct BinArgs {
+    unsigned long long *hkeys, *hvals;
+    uint32_t n_slots;
+    SeqMap q;
+    uint32_t band_width;  // k-mer-end positions per band
+    uint32_t *bin_count;  // NW_NBINS
+    uint32_t *bin_off;    // NW_NBINS + 1 (exclusive offsets), then NW_NBINS cursors
+    PairRec *pairs;
+};
+
+__device__ __forceinline__ int pair_bin(const BinArgs &a, unsigned long long pk, unsigned long long key) {
+    const uint32_t r = (uint32_t)(pk >> 32);
+    const uint32_t ylen = a.q.fixed_len ? a.q.fixed_len : a.q.start[r + 1] - a.q.start[r];
+    uint32_t band = key_erel(key) / a.band_width;
+    band = band < (uint32_t)NW_BANDS ? band : (uint32_t)NW_BANDS - 1;
+    return nw_class_of(ylen) * NW_BANDS + (int)band;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(BIN_THREADS) bin_kernel(BinArgs a) {
+    __shared__ uint32_t s_cnt[NW_NBINS];
+    __shared__ uint32_t s_base[NW_NBINS];
+    for (int i = threadIdx.x; i < NW_NBINS; i += BIN_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const uint32_t chunk = BIN_THREADS * BIN_ITEMS;
+    for (uint32_t base = blockIdx.x * chunk; base < a.n_slots; base += gridDim.x * chunk) {
+        unsigned long long k[BIN_ITEMS], v[BIN_ITEMS];
+        int bin[BIN_ITEMS];
+        uint32_t loc[BIN_ITEMS];
+#pragma unroll
+        for (int t = 0; t < BIN_ITEMS; t++) {
+            const uint32_t i = base + t * BIN_THREADS + threadIdx.x;
+            k[t] = i < a.n_slots ? a.hkeys[i] : HASH_EMPTY;
+            bin[t] = -1;
+            if (k[t] != HASH_EMPTY) {
+                v[t] = a.hvals[i];
+                bin[t] = pair_bin(a, k[t], v[t]);
+                loc[t] = atomicAdd(&s_cnt[bin[t]], 1u);
+                if (PASS == 1) { a.hkeys[i] = HASH_EMPTY; a.hvals[i] = ~0ull; }
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, k != HASH_EMPTY);
-        if (m) {
-            uint32_t at = 0;
-            if (lane == (__ffs(m) - 1)) at = atomicAdd(n_pairs, (uint32_t)__popc(m));
-            at = __shfl_sync(0xffffffffu, at, __ffs(m) - 1);
-            if (k != HASH_EMPTY) {
+        __syncthreads();
+        if (PASS == 0) continue;  // counts are flushed once at the end
+        for (int i = threadIdx.x; i < NW_NBINS; i += BIN_THREADS) {
+            s_base[i] = s_cnt[i] ? atomicAdd(&a.bin_off[NW_NBINS + 1 + i], s_cnt[i]) : 0u;
+            s_cnt[i] = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < BIN_ITEMS; t++)
+            if (bin[t] >= 0) {
                 PairRec pr;
-                pr.r = (uint32_t)(k >> 32);
-                pr.s = (uint32_t)k;
-                pr.key = v;
-                pairs[at + __popc(m & ((1u << lane) - 1u))] = pr;
+                pr.r = (uint32_t)(k[t] >> 32);
+                pr.s = (uint32_t)k[t];
+                pr.key = v[t];
+                a.pairs[s_base[bin[t]] + loc[t]] = pr;
             }
+        __syncthreads();
+    }
+    if (PASS == 0)
+        for (int i = threadIdx.x; i < NW_NBINS; i += BIN_THREADS)
+            if (s_cnt[i]) atomicAdd(&a.bin_count[i], s_cnt[i]);
+}
+
+// exclusive scan of the bin counters; initialises the scatter cursors and n_pairs, and writes the
+// work range of every (class, launch) : bands are merged into fewer launches when there are too
+// few candidates to fill the GPU per band (min_per_launch), later launches of a class stay empty.
+__global__ void bin_offsets_kernel(const uint32_t *bin_count, uint32_t *bin_off, uint32_t *launch_range,
+                                   uint32_t *n_pairs, uint32_t min_per_launch) {
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int i = 0; i < NW_NBINS; i++) {
+            bin_off[i] = acc;
+            bin_off[NW_NBINS + 1 + i] = acc;
+            acc += bin_count[i];
         }
+        bin_off[NW_NBINS] = acc;
+        *n_pairs = acc;
+        uint32_t launches = acc / (min_per_launch ? min_per_launch : 1u);
+        launches = launches < 1u ? 1u : (launches > (uint32_t)NW_BANDS ? (uint32_t)NW_BANDS : launches);
+        const uint32_t merge = ((uint32_t)NW_BANDS + launches - 1) / launches;  // bands per launch
+        for (int c = 0; c < 9; c++)
+            for (uint32_t b = 0; b < (uint32_t)NW_BANDS; b++) {
+                const uint32_t lo = b * merge, hi = (b + 1) * merge;
+                const uint32_t b0 = lo < (uint32_t)NW_BANDS ? lo : (uint32_t)NW_BANDS;
+                const uint32_t b1 = hi < (uint32_t)NW_BANDS ? hi : (uint32_t)NW_BANDS;
+                launch_range[2 * (c * NW_BANDS + b)] = bin_off[c * NW_BANDS + b0];
+                launch_range[2 * (c * NW_BANDS + b) + 1] = bin_off[c * NW_BANDS + b1];
+            }
     }
 }
 
