@@ -20,7 +20,7 @@ using namespace imsame;
 
 namespace {
 
-constexpr uint64_t SEG_MAX_BASES = 1ull << 31;    // database segment size (positions stay uint32)
+constexpr uint64_t SEG_MAX_BASES = 1ull << 29;    // database segment size (positions stay uint32; bounds the pair table)
 constexpr uint64_t STAGE_BYTES = 256ull << 20;    // ASCII staging buffer on the device
 constexpr uint32_t PAD_WORDS = 16;                // zero words after every packed array
 

@@ -1,0 +1,87 @@
+"""GPU, >= 2 devices: database sharded over two ranks with the NCCL min-key / owner-payload
+reduction (exactly what bench.py runs) equals the single-GPU result; CLI -gpus 2 equals -gpus 1."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import helpers as hp
+import synth_cases as sc
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, tmpdir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    sys.path.insert(0, os.path.join(hp.ROOT, "tests"))
+    from imsame_b200 import api, sharding
+    db, ds, q, qs = sc.fixed_case(31, 4, 80000, 150, 16000, 1500, 0.03)
+    nd, nq = len(ds) - 1, len(qs) - 1
+    lo, hi = sharding.shard_range(nd, rank, world)
+    b0, b1 = int(ds[lo]), int(ds[hi])
+    ctx = api.Imsame(rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    p = api.make_params(n_threads=4, db_total_len_global=len(db), db_pos_base=b0, db_seq_base=lo)
+    ctx.set_query((q, qs), p)
+    ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
+    keys = torch.empty(nq, dtype=torch.int64, device="cuda")
+    payload = torch.empty(nq, dtype=torch.int64, device="cuda")
+    ctx.run(p, keys.data_ptr(), payload.data_ptr())
+
+    def mask(kr, kl, pl):
+        ctx.mask_payload(kr.data_ptr(), kl.data_ptr(), pl.data_ptr())
+    sharding.reduce_best(keys, payload, dist, mask)
+    rec = ctx.fetch(keys.data_ptr(), payload.data_ptr())
+    if rank == 0:
+        np.save(os.path.join(tmpdir, "rec.npy"), rec)
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_nccl_sharded_equals_single_gpu(gpu, tmp_path):
+    import torch.multiprocessing as mp
+    from imsame_b200 import api
+    port = 29700 + (os.getpid() % 1000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    rec = np.load(tmp_path / "rec.npy")
+    db, ds, q, qs = sc.fixed_case(31, 4, 80000, 150, 16000, 1500, 0.03)
+    whole, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
+    for f in ("accepted", "db_seq", "qpos_end", "db_pos", "length", "identities"):
+        assert np.array_equal(rec[f], whole[f]), f
+    assert int(whole["accepted"].sum()) > 300
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_cli_two_gpus_equals_one(gpu, tmp_path):
+    from imsame_b200 import hostlib as H
+    pool = H.SynthPool(606, 3, 60000)
+    nd, nq, L = 9000, 800, 150
+    dbf, qf = str(tmp_path / "db.fa"), str(tmp_path / "q.fa")
+    H.write_fasta(dbf, pool.db_reads(0, nd, L), nd, L, "d")
+    H.write_fasta(qf, pool.query_reads(0, nq, L, 0.05), nq, L, "q")
+    pool.close()
+    exe = os.path.join(hp.ROOT, "bin", "IMSAME")
+    outs = []
+    for g in ("1", "2"):
+        o = str(tmp_path / f"o{g}.align")
+        subprocess.check_call([exe, "-query", qf, "-db", dbf, "-out", o, "-n_threads", "4", "-gpus", g],
+                              stdout=subprocess.DEVNULL)
+        outs.append(open(o, "rb").read())
+    assert outs[0] == outs[1] and len(outs[0]) > 10000
