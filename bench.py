@@ -211,6 +211,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+    # torchrun pins OMP_NUM_THREADS=1; the synthetic generator (host/synth.c) is OpenMP
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -239,20 +243,22 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")
-    keys_local = torch.empty(nq, dtype=torch.int64, device="cuda")
     payload = torch.empty(nq, dtype=torch.int64, device="cuda")
 
     ctx.set_query((q_pin.array, qs), params)
     ctx.set_db((db_pin.array, ds))
     torch.cuda.synchronize()
 
+    def exchange():
+        dist.all_reduce(keys, op=dist.ReduceOp.MIN)          # C1: min-key reduction over NVLink (8 MB)
+
     def step():
-        st = ctx.run(params, keys.data_ptr(), payload.data_ptr())
-        if world > 1:
-            keys_local.copy_(keys)
-            dist.all_reduce(keys, op=dist.ReduceOp.MIN)      # C1: min-key reduction over NVLink
-            ctx.mask_payload(keys.data_ptr(), keys_local.data_ptr(), payload.data_ptr())
-            dist.all_reduce(payload, op=dist.ReduceOp.MAX)   # owner's payload
+        if world == 1:
+            return ctx.run(params, keys.data_ptr(), payload.data_ptr())
+        # shards exchange the per-read keys between k-mer-end bands, so an accepted early hit in one
+        # shard prunes the later candidates of that read in every shard (the reference's early exit)
+        st = ctx.run_stepped(params, keys.data_ptr(), payload.data_ptr(), exchange=exchange, exchange_every=2)
+        dist.all_reduce(payload, op=dist.ReduceOp.MAX)       # the owner's payload (others are zero)
         return st
 
     def barrier():

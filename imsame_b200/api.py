@@ -59,7 +59,9 @@ class Stats(C.Structure):
 # every symbol declared in include/imsame_gpu.h
 SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "imsame_gpu_last_cuda_error",
            "imsame_gpu_set_stream", "imsame_gpu_align", "imsame_gpu_set_query", "imsame_gpu_set_db",
-           "imsame_gpu_run", "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch",
+           "imsame_gpu_run", "imsame_gpu_n_segments", "imsame_gpu_n_bands", "imsame_gpu_run_begin",
+           "imsame_gpu_run_scan", "imsame_gpu_run_band", "imsame_gpu_run_select", "imsame_gpu_run_end",
+           "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch",
            "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
 _lib = None
@@ -93,6 +95,12 @@ def lib():
         l.imsame_gpu_set_query.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(Params)]
         l.imsame_gpu_set_db.argtypes = [vp, C.POINTER(SeqInfo)]
         l.imsame_gpu_run.argtypes = [vp, C.POINTER(Params), vp, vp, C.POINTER(Stats)]
+        l.imsame_gpu_n_segments.argtypes = [vp]
+        l.imsame_gpu_run_begin.argtypes = [vp, C.POINTER(Params), vp, vp]
+        l.imsame_gpu_run_scan.argtypes = [vp, C.c_int]
+        l.imsame_gpu_run_band.argtypes = [vp, C.c_int, C.c_int]
+        l.imsame_gpu_run_select.argtypes = [vp, C.c_int]
+        l.imsame_gpu_run_end.argtypes = [vp, C.POINTER(Stats)]
         l.imsame_gpu_mask_payload.argtypes = [vp, vp, vp, vp]
         l.imsame_gpu_fetch.argtypes = [vp, vp, vp, vp]
         l.imsame_gpu_nw_batch.argtypes = [vp, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp,
@@ -233,6 +241,27 @@ class Imsame:
         self._check(lib().imsame_gpu_run(self._h, C.byref(params), C.c_void_p(d_keys), C.c_void_p(d_payload),
                                          C.byref(st)))
         return st.as_dict()
+
+    def run_stepped(self, params=None, d_keys=0, d_payload=0, exchange=None, exchange_every=1):
+        """imsame_gpu_run in steps; `exchange()` is called between bands (multi-GPU: all-reduce MIN of the
+        keys), every `exchange_every` bands and after the last band of each segment."""
+        params = params or make_params()
+        L = lib()
+        self._check(L.imsame_gpu_run_begin(self._h, C.byref(params), C.c_void_p(d_keys), C.c_void_p(d_payload)))
+        nb = L.imsame_gpu_n_bands()
+        for seg in range(L.imsame_gpu_n_segments(self._h)):
+            self._check(L.imsame_gpu_run_scan(self._h, seg))
+            for band in range(nb):
+                self._check(L.imsame_gpu_run_band(self._h, seg, band))
+                if exchange is not None and ((band + 1) % exchange_every == 0 or band == nb - 1):
+                    exchange()
+            self._check(L.imsame_gpu_run_select(self._h, seg))
+        st = Stats()
+        self._check(L.imsame_gpu_run_end(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def n_segments(self):
+        return lib().imsame_gpu_n_segments(self._h)
 
     def mask_payload(self, d_keys_reduced, d_keys_local, d_payload):
         self._check(lib().imsame_gpu_mask_payload(self._h, C.c_void_p(d_keys_reduced), C.c_void_p(d_keys_local),

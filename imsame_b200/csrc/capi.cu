@@ -66,8 +66,12 @@ struct imsame_ctx {
     uint32_t *d_small = nullptr;  // [0] n_pairs, [1] work head
     unsigned long long *d_counters = nullptr;  // [0..3] scan counters, [4] cells, [5] pairs total
     int *d_overflow = nullptr;
-    unsigned long long *keys = nullptr, *payload = nullptr;
+    unsigned long long *keys = nullptr, *payload = nullptr, *pkey = nullptr;
     uint64_t keys_cap = 0;
+    // state of a run in progress (run_begin .. run_end)
+    unsigned long long *run_keys = nullptr, *run_payload = nullptr;
+    imsame_params run_params;
+    bool run_active = false;
     uint32_t *d_bins = nullptr;  // [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors | then NBINS work heads
     NwLink *carry = nullptr;
     uint64_t carry_warps = 0;
@@ -190,7 +194,7 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
     if (!ctx->d_small) {
         int rc;
         if ((rc = dev_alloc(ctx, &ctx->d_small, 4))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_counters, 8))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_counters, 16))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_overflow, 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_nmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_lmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
@@ -375,7 +379,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
-    dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->d_bins); dev_free(ctx->carry); dev_free(ctx->stage);
+    dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->pkey); dev_free(ctx->d_bins); dev_free(ctx->carry); dev_free(ctx->stage);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -553,44 +557,58 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
     return IMSAME_OK;
 }
 
-// ---- K2 + K2b + K3 + selection over the resident shard ----------------------------------------
-static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
-                    imsame_stats *st);
+}  // extern "C"
 
-int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
-                   imsame_stats *st) {
-    if (!ctx || !p) return IMSAME_EARG;
-    reset_timing(ctx);
-    return run_impl(ctx, p, d_keys, d_payload, st);
+// ---- K2 + K2b + K3 + selection over the resident shard ----------------------------------------
+// Stepping form (used by multi-GPU callers to exchange the per-read keys between bands):
+//   run_begin ; for seg: run_scan(seg) ; for band: run_band(seg, band) [; all-reduce(keys, MIN)] ;
+//   run_select(seg) ; run_end.   imsame_gpu_run() is exactly that sequence without the exchange.
+namespace {
+
+SeqMap query_map(const imsame_ctx *ctx) {
+    SeqMap qm;
+    qm.pk = ctx->q_pk; qm.start = ctx->q_start; qm.blk = ctx->q_blk; qm.n = ctx->nq; qm.total = ctx->q_total;
+    qm.fixed_len = ctx->q_fixed;
+    return qm;
+}
+SeqMap seg_map(const Seg &s) {
+    SeqMap dm;
+    dm.pk = s.pk; dm.start = s.start; dm.blk = s.blk; dm.n = s.n; dm.total = s.total; dm.fixed_len = s.fixed_len;
+    return dm;
 }
 
-static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
-                    imsame_stats *st) {
+}  // namespace
+
+extern "C" int imsame_gpu_n_segments(const imsame_ctx *ctx) { return ctx ? (int)ctx->segs.size() : 0; }
+extern "C" int imsame_gpu_n_bands(void) { return NW_BANDS; }
+
+extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload) {
     if (!ctx || !p) return IMSAME_EARG;
     if (!ctx->have_query || !ctx->have_db) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     const uint32_t nq = ctx->nq;
     int rc;
-    if (!d_keys || !d_payload) {
-        if (ctx->keys_cap < nq) {
-            dev_free(ctx->keys); dev_free(ctx->payload);
-            if ((rc = dev_alloc(ctx, &ctx->keys, nq))) return rc;
-            if ((rc = dev_alloc(ctx, &ctx->payload, nq))) return rc;
-            ctx->keys_cap = nq;
-        }
+    if (ctx->keys_cap < nq) {
+        dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->pkey);
+        if ((rc = dev_alloc(ctx, &ctx->keys, nq))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->payload, nq))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->pkey, nq))) return rc;
+        ctx->keys_cap = nq;
     }
     if (!ctx->d_bins && (rc = dev_alloc(ctx, &ctx->d_bins, 6ull * NW_NBINS + 8))) return rc;
-    unsigned long long *keys = d_keys ? (unsigned long long *)d_keys : ctx->keys;
-    unsigned long long *payload = d_payload ? (unsigned long long *)d_payload : ctx->payload;
+    ctx->run_keys = d_keys ? (unsigned long long *)d_keys : ctx->keys;
+    ctx->run_payload = d_payload ? (unsigned long long *)d_payload : ctx->payload;
+    ctx->run_params = *p;
 
     // pair table: the reference semantics let ~0.2-0.4 % of random hits through the e-value test
     // (idents counts every match of the walk, src/alignmentFunctions.c:323,346), i.e. ~100 candidate
     // database reads per query read against a 10 M-read database; start at 64 slots per read per
-    // segment and grow on overflow
+    // segment and grow on overflow (run_scan)
     uint32_t cap = 1u << 20;
     while (cap < 64ull * nq && cap < (1u << 28)) cap <<= 1;
     cap = std::max(cap, ctx->hcap);
     if ((rc = ensure_carry(ctx, ctx->q_maxlen))) return rc;
+    if ((rc = ensure_work_buffers(ctx, cap))) return rc;
 
     // exact threshold tables (host, long double) -> device
     std::vector<uint16_t> nmin(IMSAME_MAX_READ_SIZE + 1), lmin(IMSAME_MAX_READ_SIZE + 1), imin(2 * IMSAME_MAX_READ_SIZE + 1);
@@ -598,96 +616,155 @@ static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, u
     imsame_build_nmin(p->min_e_value, db_total_global, nmin.data());
     imsame_build_lmin(p->min_coverage, lmin.data());
     imsame_build_imin(p->min_identity, imin.data());
+    CK(cudaMemcpyAsync(ctx->d_nmin, nmin.data(), nmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_lmin, lmin.data(), lmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_imin, imin.data(), imin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    {
+        PhaseScope ps(ctx, PH_SELECT);
+        const int g = std::min<int>((nq + 255) / 256, ctx->n_sm * 8);
+        fill_u64_kernel<<<g, 256, 0, ctx->stream>>>(ctx->run_keys, KEY_NONE, nq);
+        fill_u64_kernel<<<g, 256, 0, ctx->stream>>>(ctx->pkey, KEY_NONE, nq);
+        ctx->launches += 2;
+        CK(cudaMemsetAsync(ctx->run_payload, 0, (size_t)nq * 8, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // the host tables go out of scope
+    ctx->run_active = true;
+    return IMSAME_OK;
+}
 
-    for (int attempt = 0; attempt < 6; attempt++) {
-        if ((rc = ensure_work_buffers(ctx, cap))) return rc;
-        CK(cudaMemcpyAsync(ctx->d_nmin, nmin.data(), nmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_lmin, lmin.data(), lmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_imin, imin.data(), imin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+// K2 + K2b for one segment: scan, extend, collect candidates, sort them into (class, band) bins
+extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    const Seg &s = ctx->segs[seg];
+    const imsame_params *p = &ctx->run_params;
+    const SeqMap qm = query_map(ctx), dm = seg_map(s);
+    int rc;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        CK(cudaMemsetAsync(ctx->d_small, 0, 4 * sizeof(uint32_t), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int), ctx->stream));
+        // counters of a failed attempt must not be kept: snapshot/restore is avoided by scanning into scratch
+        CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
         {
-            PhaseScope ps(ctx, PH_SELECT);
-            const int g = std::min<int>((nq + 255) / 256, ctx->n_sm * 8);
-            fill_u64_kernel<<<g, 256, 0, ctx->stream>>>(keys, KEY_NONE, nq);
-            ctx->launches++;
-            CK(cudaMemsetAsync(payload, 0, (size_t)nq * 8, ctx->stream));
-        }
-        SeqMap qm;
-        qm.pk = ctx->q_pk; qm.start = ctx->q_start; qm.blk = ctx->q_blk; qm.n = nq; qm.total = ctx->q_total;
-        qm.fixed_len = ctx->q_fixed;
-        for (const Seg &s : ctx->segs) {
-            SeqMap dm;
-            dm.pk = s.pk; dm.start = s.start; dm.blk = s.blk; dm.n = s.n; dm.total = s.total; dm.fixed_len = s.fixed_len;
-            CK(cudaMemsetAsync(ctx->d_small, 0, 4 * sizeof(uint32_t), ctx->stream));
-            {
-                PhaseScope ps(ctx, PH_K2);
-                ScanArgs a;
-                a.db = dm; a.q = qm; a.off = ctx->off; a.qpos = ctx->qpos; a.brk = s.brk; a.n_brk = s.n_brk;
-                a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
-                a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = keys;
-                a.counters = ctx->d_counters; a.overflow = ctx->d_overflow;
-                scan_kernel<<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
-                ctx->launches++; ctx->k2_launches++;
-            }
-            uint32_t *bin_count = ctx->d_bins, *bin_off = ctx->d_bins + NW_NBINS, *bin_work = ctx->d_bins + 3 * NW_NBINS + 4;
-            uint32_t *launch_range = ctx->d_bins + 4 * NW_NBINS + 4;
-            {
-                PhaseScope ps(ctx, PH_K2B);
-                CK(cudaMemsetAsync(ctx->d_bins, 0, (6ull * NW_NBINS + 8) * sizeof(uint32_t), ctx->stream));
-                BinArgs b;
-                b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.q = qm;
-                b.band_width = (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS;
-                b.bin_count = bin_count; b.bin_off = bin_off; b.pairs = ctx->pairs;
-                const int g = std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS),
-                                                 (uint32_t)ctx->n_sm * 8);
-                bin_kernel<0><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
-                bin_offsets_kernel<<<1, 32, 0, ctx->stream>>>(bin_count, bin_off, launch_range, ctx->d_small,
-                                                            (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u);
-                bin_kernel<1><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
-                ctx->launches += 3;
-            }
-            {
-                PhaseScope ps(ctx, PH_K3);
-                NwArgs a;
-                a.db = dm; a.q = qm; a.pairs = ctx->pairs; a.res = ctx->res;
-                a.igap = p->igap; a.egap = p->egap; a.lmin = ctx->d_lmin; a.imin = ctx->d_imin;
-                a.best = keys; a.cells = ctx->d_counters + 4; a.carry = ctx->carry; a.s_class = 0;
-                a.tb = nullptr; a.tb_off = nullptr; a.check_class = 0;
-                // ascending bands: an accepted early candidate prunes the read's later ones
-                for (int band = 0; band < NW_BANDS; band++)
-                    for (int c = 1; c <= 8; c++) {
-                        if (!(ctx->class_mask & (1u << c))) continue;
-                        const int bin = c * NW_BANDS + band;
-                        a.range = launch_range + 2 * bin;
-                        a.work = bin_work + bin;
-                        if ((rc = launch_nw_class<false>(ctx, a, c))) return rc;
-                    }
-            }
-            {
-                PhaseScope ps(ctx, PH_SELECT);
-                const int g = ctx->n_sm * 8;
-                select_kernel<<<g, 256, 0, ctx->stream>>>(ctx->pairs, ctx->res, ctx->d_small, keys, payload,
-                                                           p->db_seq_base + s.seq_base, ctx->d_counters + 5);
-                ctx->launches++;
-            }
-            CK(cudaGetLastError());
+            PhaseScope ps(ctx, PH_K2);
+            ScanArgs a;
+            a.db = dm; a.q = qm; a.off = ctx->off; a.qpos = ctx->qpos; a.brk = s.brk; a.n_brk = s.n_brk;
+            a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
+            a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
+            a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;
+            scan_kernel<<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
+            ctx->launches++; ctx->k2_launches++;
         }
         int overflow = 0;
         CK(cudaMemcpyAsync(&overflow, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (!overflow) break;
-        if (cap >= (1u << 30)) return IMSAME_ELIMIT;
-        cap <<= 1;  // pair table too small: grow and redo the shard
+        if (ctx->hcap >= (1u << 30) || attempt == 7) return IMSAME_ELIMIT;
+        if ((rc = ensure_work_buffers(ctx, ctx->hcap * 2))) return rc;  // reallocates + clears the table
+    }
+    uint32_t *bin_count = ctx->d_bins, *bin_off = ctx->d_bins + NW_NBINS;
+    uint32_t *launch_range = ctx->d_bins + 4 * NW_NBINS + 4;
+    {
+        PhaseScope ps(ctx, PH_K2B);
+        add_counters_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->d_counters + 8, 4);
+        CK(cudaMemsetAsync(ctx->d_bins, 0, (6ull * NW_NBINS + 8) * sizeof(uint32_t), ctx->stream));
+        BinArgs b;
+        b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.q = qm;
+        b.band_width = (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS;
+        b.bin_count = bin_count; b.bin_off = bin_off; b.pairs = ctx->pairs;
+        const int g = std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS),
+                                         (uint32_t)ctx->n_sm * 8);
+        bin_kernel<0><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
+        bin_offsets_kernel<<<1, 32, 0, ctx->stream>>>(bin_count, bin_off, launch_range, ctx->d_small,
+                                                    (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u);
+        bin_kernel<1><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
+        ctx->launches += 4;
+    }
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+// K3 for one band of one segment (every NW class present in the query)
+extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size() || band < 0 || band >= NW_BANDS)
+        return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    const imsame_params *p = &ctx->run_params;
+    uint32_t *bin_work = ctx->d_bins + 3 * NW_NBINS + 4, *launch_range = ctx->d_bins + 4 * NW_NBINS + 4;
+    PhaseScope ps(ctx, PH_K3);
+    NwArgs a;
+    a.db = seg_map(ctx->segs[seg]); a.q = query_map(ctx); a.pairs = ctx->pairs; a.res = ctx->res;
+    a.igap = p->igap; a.egap = p->egap; a.lmin = ctx->d_lmin; a.imin = ctx->d_imin;
+    a.best = ctx->run_keys; a.cells = ctx->d_counters + 4; a.carry = ctx->carry; a.s_class = 0;
+    a.tb = nullptr; a.tb_off = nullptr; a.check_class = 0;
+    int rc;
+    for (int c = 1; c <= 8; c++) {
+        if (!(ctx->class_mask & (1u << c))) continue;
+        const int bin = c * NW_BANDS + band;
+        a.range = launch_range + 2 * bin;
+        a.work = bin_work + bin;
+        if ((rc = launch_nw_class<false>(ctx, a, c))) return rc;
+    }
+    return IMSAME_OK;
+}
+
+// record fields of the pairs of this segment that currently own their read's key
+extern "C" int imsame_gpu_run_select(imsame_ctx *ctx, int seg) {
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    PhaseScope ps(ctx, PH_SELECT);
+    select_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->pairs, ctx->res, ctx->d_small, ctx->run_keys,
+                                                        ctx->run_payload, ctx->pkey,
+                                                        ctx->run_params.db_seq_base + ctx->segs[seg].seq_base,
+                                                        ctx->d_counters + 5);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+// drop payloads that a later, smaller key (another segment or, after a reduction, another shard) superseded
+extern "C" int imsame_gpu_run_end(imsame_ctx *ctx, imsame_stats *st) {
+    if (!ctx || !ctx->run_active) return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    {
+        PhaseScope ps(ctx, PH_SELECT);
+        mask_payload_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->run_keys, ctx->pkey, ctx->run_payload, ctx->nq);
+        ctx->launches++;
     }
     unsigned long long cnt[8] = {0};
-    CK(cudaMemcpy(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->run_active = false;
     if (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE) {
         // the reference only fails when such a read reaches NW (src/alignmentFunctions.c:155)
         if (cnt[2] > 0) return IMSAME_EREADSIZE;
     }
     fill_stats(ctx, st, cnt);
     return IMSAME_OK;
+}
+
+static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
+                    imsame_stats *st) {
+    int rc;
+    if ((rc = imsame_gpu_run_begin(ctx, p, d_keys, d_payload))) return rc;
+    for (int seg = 0; seg < (int)ctx->segs.size(); seg++) {
+        if ((rc = imsame_gpu_run_scan(ctx, seg))) return rc;
+        // ascending bands: an accepted early candidate prunes the read's later ones
+        for (int band = 0; band < NW_BANDS; band++)
+            if ((rc = imsame_gpu_run_band(ctx, seg, band))) return rc;
+        if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
+    }
+    return imsame_gpu_run_end(ctx, st);
+}
+
+extern "C" {
+
+int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
+                   imsame_stats *st) {
+    if (!ctx || !p) return IMSAME_EARG;
+    reset_timing(ctx);
+    return run_impl(ctx, p, d_keys, d_payload, st);
 }
 
 int imsame_gpu_mask_payload(imsame_ctx *ctx, const uint64_t *reduced, const uint64_t *local, uint64_t *payload) {

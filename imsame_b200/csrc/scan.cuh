@@ -260,14 +260,16 @@ __global__ void bin_offsets_kernel(const uint32_t *bin_count, uint32_t *bin_off,
 // after NW: the pair whose key equals the read's final key owns the record
 __global__ void select_kernel(const PairRec *pairs, const PairRes *res, const uint32_t *n_pairs,
                               const unsigned long long *best, unsigned long long *payload,
-                              uint64_t seg_seq_base, unsigned long long *pairs_total) {
+                              unsigned long long *pkey, uint64_t seg_seq_base, unsigned long long *pairs_total) {
     const uint32_t n = *n_pairs;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pairs_total, (unsigned long long)n);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const PairRec pr = pairs[i];
         const PairRes z = res[i];
-        if ((z.stats & 0x80000000u) && pr.key == best[pr.r])
+        if ((z.stats & 0x80000000u) && pr.key == best[pr.r]) {
             payload[pr.r] = ((unsigned long long)(seg_seq_base + pr.s) << 32) | (z.stats & 0x7FFFFFFFu);
+            pkey[pr.r] = pr.key;  // the key this payload belongs to (run_end drops superseded payloads)
+        }
     }
 }
 
@@ -276,6 +278,10 @@ __global__ void mask_payload_kernel(const unsigned long long *reduced, const uns
                                     unsigned long long *payload, uint32_t n) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         if (reduced[i] != local[i] || reduced[i] == KEY_NONE) payload[i] = 0ull;
+}
+
+__global__ void add_counters_kernel(unsigned long long *dst, const unsigned long long *src, int n) {
+    if ((int)threadIdx.x < n) dst[threadIdx.x] += src[threadIdx.x];
 }
 
 __global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, uint64_t n) {

@@ -121,6 +121,24 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db);
  * or NULL to use the context's own. */
 int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *params, uint64_t *d_keys,
                    uint64_t *d_payload, imsame_stats *stats);
+/* The same run in steps, for callers that exchange the keys between GPUs while it runs
+ * (database shards: the earliest accepted hit of a read may live in another shard, and knowing
+ * it early prunes this shard's later candidates exactly like the reference's early exit,
+ * src/alignmentFunctions.c:172,189):
+ *     run_begin(params, d_keys, d_payload)
+ *     for seg in [0, n_segments):   run_scan(seg)
+ *         for band in [0, n_bands): run_band(seg, band)    [caller: all-reduce(d_keys, MIN)]
+ *         run_select(seg)
+ *     run_end(stats)                                        [caller: all-reduce(d_payload, MAX)]
+ * Bands order a read's candidates by the position of their k-mer inside the read; run_end zeroes
+ * every payload whose key is no longer the read's key, so the owner's payload survives a MAX. */
+int imsame_gpu_n_segments(const imsame_ctx *ctx);
+int imsame_gpu_n_bands(void);
+int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *params, uint64_t *d_keys, uint64_t *d_payload);
+int imsame_gpu_run_scan(imsame_ctx *ctx, int seg);
+int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band);
+int imsame_gpu_run_select(imsame_ctx *ctx, int seg);
+int imsame_gpu_run_end(imsame_ctx *ctx, imsame_stats *stats);
 /* after a min-reduction of the keys across shards: zero the payload of every
  * read this shard does not own, so that a max-reduction yields the owner's */
 int imsame_gpu_mask_payload(imsame_ctx *ctx, const uint64_t *d_keys_reduced,

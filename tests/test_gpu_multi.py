@@ -41,11 +41,17 @@ def _worker(rank, world, port, tmpdir):
     ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")
     payload = torch.empty(nq, dtype=torch.int64, device="cuda")
-    ctx.run(p, keys.data_ptr(), payload.data_ptr())
+    if os.environ.get("IMSAME_TEST_STEPPED", "1") == "1":
+        # keys exchanged between bands (what bench.py does), payload of the owner at the end
+        ctx.run_stepped(p, keys.data_ptr(), payload.data_ptr(),
+                        exchange=lambda: dist.all_reduce(keys, op=dist.ReduceOp.MIN), exchange_every=3)
+        dist.all_reduce(payload, op=dist.ReduceOp.MAX)
+    else:
+        ctx.run(p, keys.data_ptr(), payload.data_ptr())
 
-    def mask(kr, kl, pl):
-        ctx.mask_payload(kr.data_ptr(), kl.data_ptr(), pl.data_ptr())
-    sharding.reduce_best(keys, payload, dist, mask)
+        def mask(kr, kl, pl):
+            ctx.mask_payload(kr.data_ptr(), kl.data_ptr(), pl.data_ptr())
+        sharding.reduce_best(keys, payload, dist, mask)
     rec = ctx.fetch(keys.data_ptr(), payload.data_ptr())
     if rank == 0:
         np.save(os.path.join(tmpdir, "rec.npy"), rec)
@@ -55,10 +61,12 @@ def _worker(rank, world, port, tmpdir):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-def test_nccl_sharded_equals_single_gpu(gpu, tmp_path):
+@pytest.mark.parametrize("stepped", ["1", "0"])
+def test_nccl_sharded_equals_single_gpu(gpu, tmp_path, stepped):
     import torch.multiprocessing as mp
     from imsame_b200 import api
-    port = 29700 + (os.getpid() % 1000)
+    os.environ["IMSAME_TEST_STEPPED"] = stepped
+    port = 29700 + (os.getpid() % 1000) + int(stepped)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     rec = np.load(tmp_path / "rec.npy")
     db, ds, q, qs = sc.fixed_case(31, 4, 80000, 150, 16000, 1500, 0.03)
