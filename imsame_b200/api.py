@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-GPU_SO = os.path.join(_HERE, "_lib", "libimsame_gpu.so")
+GPU_SO = os.environ.get("IMSAME_GPU_SO") or os.path.join(_HERE, "_lib", "libimsame_gpu.so")  # override: experiments
 
 KEY_NONE = 0x7FFFFFFFFFFFFFFF
 

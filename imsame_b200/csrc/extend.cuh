@@ -153,3 +153,75 @@ IMS_HD int extend_hit_lut(const uint16_t *lut, const uint32_t *dpk, const uint32
 }
 
 }  // namespace imsame
+
+// ---------------------------------------------------------------------------------------
+// Window-at-a-time form for the scan kernel: the walk of one hit is a small state machine
+// that consumes one 32-base window (forward or backward) per call, four table steps with
+// no data-dependent branch, so that the 32 hits of a warp stay converged: every lane
+// executes the same window body until all walks of the warp are finished.
+namespace imsame {
+
+struct ExtState {
+    int phase;  // 0 forward, 1 backward, 2 done
+    int t;      // steps already taken in this phase
+    int sc;     // current score (units of POINT)
+    int hr, fe; // forward: high_right, last step that reached it (-1: none)   (:324-327)
+    int hl, be; // backward: high_left, last step that reached it (-1: none)   (:347-351)
+    int idn;    // idents
+    int fmax, bmax;  // steps available inside both reads
+};
+
+IMS_HD void ext_init(ExtState &s, uint32_t p, uint32_t e, uint32_t xs, uint32_t xend, uint32_t ys, uint32_t yend) {
+    const int fd = (int)(xend - p), fq = (int)(yend - (e + 1));
+    const int bd = (int)(p - K - xs), bq = (int)e - (K - 1) - (int)ys;  // -1 for the phantom word
+    s.fmax = fq < fd ? fq : fd;
+    s.bmax = bq < bd ? bq : bd;
+    s.t = 0;
+    s.sc = K; s.hr = K; s.fe = -1; s.hl = K; s.be = -1; s.idn = K;
+    s.phase = s.fmax > 0 ? 0 : (s.bmax > 0 ? 1 : 2);
+}
+
+IMS_HD void ext_window(ExtState &s, const uint16_t *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
+                       uint32_t e) {
+    const bool bwd = s.phase == 1;
+    const int maxs = bwd ? s.bmax : s.fmax;
+    const int rem = maxs - s.t;
+    const int64_t sd = bwd ? (int64_t)p - (K + 1) - s.t - 31 : (int64_t)p + s.t;
+    const int64_t sq = bwd ? (int64_t)e - K - s.t - 31 : (int64_t)e + 1 + s.t;
+    const uint64_t a = sd >= 0 ? fetch32(dpk, (uint64_t)sd) : (fetch32(dpk, 0) << (2 * (int)(-sd)));
+    const uint64_t b = sq >= 0 ? fetch32(qpk, (uint64_t)sq) : (fetch32(qpk, 0) << (2 * (int)(-sq)));
+    uint32_t mm = mismatch32(a, b);
+    if (bwd) mm = brev32(mm);                    // step u <-> bit u in both directions
+    if (rem < 32) mm |= 0xFFFFFFFFu << rem;      // steps past the read end: mismatches (never counted)
+    int sc = s.sc, hi = bwd ? s.hl : s.hr, last = bwd ? s.be : s.fe, idn = s.idn;
+    bool term = false;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+        const uint32_t m = (mm >> c) & 0xFFu;
+        int row = sc < EXT_LUT_ROWS ? sc : EXT_LUT_ROWS;
+        row = row < 1 ? 1 : row;
+        const uint32_t ent = lut[(row - 1) * 256 + m];
+        if (!term) {
+            idn += (int)(ent & 15u);
+            const int cand = sc + (int)((ent >> 5) & 15u) - 1;
+            if (cand >= hi) { hi = cand; last = s.t + c + (int)((ent >> 9) & 15u) - 1; }
+            sc += 8 - 2 * popc32(m);
+            term = (ent & 16u) != 0;
+        }
+    }
+    s.idn = idn;
+    const bool phase_over = term || rem <= 32;
+    if (!bwd) {
+        s.hr = hi; s.fe = last;
+        if (phase_over) { s.phase = s.bmax > 0 ? 1 : 2; s.t = 0; s.sc = hi; }  // backward restarts from high_right (:339)
+        else { s.t += 32; s.sc = sc; }
+    } else {
+        s.hl = hi; s.be = last;
+        if (phase_over) s.phase = 2;
+        else { s.t += 32; s.sc = sc; }
+    }
+}
+
+IMS_HD int ext_result(const ExtState &s) { return 2 * s.idn - (s.fe + K + s.be + 1); }
+
+}  // namespace imsame

@@ -76,7 +76,47 @@ __device__ __forceinline__ bool word_broken(const ScanArgs &a, uint32_t q) {
     return lo < a.n_brk && a.brk[lo] <= q;
 }
 
+// A walk that is still running after SCAN_FAST_WINDOWS windows (a true overlap: up to a whole
+// read in both directions) is parked in a per-warp queue; parked walks are finished 32 at a time,
+// so the many short walks of random hits never wait for the few long ones.
+constexpr int SCAN_FAST_WINDOWS = 3;
+constexpr int SCAN_QCAP = 64;
+
+struct ParkedWalk {
+    uint32_t p, e, ys, yend;
+    ExtState st;
+};
+
+__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t p, uint32_t e, uint32_t ys, uint32_t yend,
+                                           const ExtState &st, unsigned long long &c_pass,
+                                           unsigned long long &c_anom) {
+    const int n = ext_result(st);
+    if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
+    if (n < 0 || n >= (int)a.nmin[yend - ys]) {
+        c_pass++;
+        const uint32_t r = find_read(a.q, e);
+        const uint64_t key = make_key(e - ys + 1, a.seg_pos_base + p);
+        if (key < a.best[r]) {
+            const uint32_t s = find_read(a.db, p - 1);
+            pair_insert(a, r, s, key);
+        }
+    }
+}
+
+// finish `count` (<= 32) parked walks, one per lane
+__device__ __forceinline__ void drain_parked(const ScanArgs &a, const uint16_t *s_lut, const ParkedWalk *q, int count,
+                                             int lane, unsigned long long &c_pass, unsigned long long &c_anom) {
+    ParkedWalk w;
+    w.st.phase = 2;
+    w.p = w.e = w.ys = w.yend = 0;
+    if (lane < count) w = q[lane];
+    while (__any_sync(0xffffffffu, w.st.phase < 2))
+        if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e);
+    if (lane < count) finish_hit(a, w.p, w.e, w.ys, w.yend, w.st, c_pass, c_anom);
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
+    __shared__ ParkedWalk s_park[SCAN_WARPS][SCAN_QCAP];
     __shared__ uint32_t s_excl[SCAN_WARPS][33];
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
     __shared__ uint32_t s_xs[SCAN_WARPS][32];
@@ -88,6 +128,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     const uint32_t n_tiles = (a.db.total + 31) / 32;
     const uint32_t gw = blockIdx.x * SCAN_WARPS + warp, nw = gridDim.x * SCAN_WARPS;
     unsigned long long c_words = 0, c_hits = 0, c_pass = 0, c_anom = 0;
+    int n_parked = 0;  // warp-uniform
 
     for (uint32_t tile = gw; tile < n_tiles; tile += nw) {
         if (*(volatile int *)a.overflow) break;  // pair table too small: the host grows it and reruns
@@ -117,30 +158,48 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
         s_xs[warp][lane] = xs;
         s_xe[warp][lane] = xe;
         __syncwarp();
-        for (uint32_t h = lane; h < total; h += 32) {
-            // owner = last lane whose exclusive prefix is <= h
-            int o = 0;
+        for (uint32_t h0 = 0; h0 < total; h0 += 32) {
+            const uint32_t h = h0 + lane;
+            const bool live = h < total;
+            uint32_t e = 0, p = 0, r = 0, ys = 0, yend = 0;
+            ExtState st;
+            st.phase = 2;
+            if (live) {
+                // owner = last lane whose exclusive prefix is <= h
+                int o = 0;
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1)
-                if (s_excl[warp][o + step] <= h) o += step;
-            const uint32_t e = a.qpos[s_b0[warp][o] + (h - s_excl[warp][o])];
-            const uint32_t p = tile * 32 + o + 1;  // llpos.pos: index after the word
-            const uint32_t r = find_read(a.q, e);
-            const uint32_t ys = read_start(a.q, r);
-            const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
-            const int n = extend_hit_lut(s_lut, a.db.pk, a.q.pk, p, e, s_xs[warp][o], s_xe[warp][o], ys, yend);
-            c_hits++;
-            if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
-            if (n < 0 || n >= (int)a.nmin[yend - ys]) {
-                c_pass++;
-                const uint64_t key = make_key(e - ys + 1, a.seg_pos_base + p);
-                if (key < a.best[r]) {
-                    const uint32_t s = find_read(a.db, p - 1);
-                    pair_insert(a, r, s, key);
+                for (int step = 16; step >= 1; step >>= 1)
+                    if (s_excl[warp][o + step] <= h) o += step;
+                e = a.qpos[s_b0[warp][o] + (h - s_excl[warp][o])];
+                p = tile * 32 + o + 1;  // llpos.pos: index after the word
+                r = find_read(a.q, e);
+                ys = read_start(a.q, r);
+                yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
+                ext_init(st, p, e, s_xs[warp][o], s_xe[warp][o], ys, yend);
+                c_hits++;
+            }
+            // all walks of the warp advance one 32-base window per iteration (extend.cuh)
+            for (int it = 0; it < SCAN_FAST_WINDOWS && __any_sync(0xffffffffu, st.phase < 2); it++)
+                if (st.phase < 2) ext_window(st, s_lut, a.db.pk, a.q.pk, p, e);
+            const bool unfinished = st.phase < 2;
+            if (live && !unfinished) finish_hit(a, p, e, ys, yend, st, c_pass, c_anom);
+            const unsigned park = __ballot_sync(0xffffffffu, unfinished);
+            if (park) {
+                if (unfinished) {
+                    ParkedWalk &w = s_park[warp][n_parked + __popc(park & ((1u << lane) - 1u))];
+                    w.p = p; w.e = e; w.ys = ys; w.yend = yend; w.st = st;
+                }
+                n_parked += __popc(park);
+                __syncwarp();
+                if (n_parked >= 32) {
+                    n_parked -= 32;
+                    drain_parked(a, s_lut, &s_park[warp][n_parked], 32, lane, c_pass, c_anom);
+                    __syncwarp();
                 }
             }
         }
     }
+    if (n_parked) drain_parked(a, s_lut, &s_park[warp][0], n_parked, lane, c_pass, c_anom);
     // counters: warp-reduce then one atomic per warp
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {

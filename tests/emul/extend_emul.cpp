@@ -69,6 +69,10 @@ int main(int argc, char **argv) {
                 int64_t want = orc_extend(&db, &q, p, (uint64_t)e + 1, r, s);
                 int got = extend_hit(dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
                 int got2 = extend_hit_lut(lut.data(), dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                ExtState st;
+                ext_init(st, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                while (st.phase < 2) ext_window(st, lut.data(), dpk.data(), qpk.data(), p, e);
+                if (want != ext_result(st)) { if (bad++ < 10) printf("WINDOW MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, ext_result(st)); }
                 hits++;
                 if (want != got2) { if (bad++ < 10) printf("LUT MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got2); }
                 if (want != got) { if (bad++ < 10) printf("MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got); }
