@@ -248,13 +248,15 @@ class Imsame:
         params = params or make_params()
         L = lib()
         self._check(L.imsame_gpu_run_begin(self._h, C.byref(params), C.c_void_p(d_keys), C.c_void_p(d_payload)))
-        nb = L.imsame_gpu_n_bands()
-        for seg in range(L.imsame_gpu_n_segments(self._h)):
+        nb, nseg = L.imsame_gpu_n_bands(), L.imsame_gpu_n_segments(self._h)
+        for seg in range(nseg):
             self._check(L.imsame_gpu_run_scan(self._h, seg))
-            for band in range(nb):
+        for band in range(nb):  # band-major over all segments: global scan order of the candidates
+            for seg in range(nseg):
                 self._check(L.imsame_gpu_run_band(self._h, seg, band))
-                if exchange is not None and ((band + 1) % exchange_every == 0 or band == nb - 1):
-                    exchange()
+            if exchange is not None and ((band + 1) % exchange_every == 0 or band == nb - 1):
+                exchange()
+        for seg in range(nseg):
             self._check(L.imsame_gpu_run_select(self._h, seg))
         st = Stats()
         self._check(L.imsame_gpu_run_end(self._h, C.byref(st)))

@@ -23,6 +23,7 @@ namespace {
 constexpr uint64_t SEG_MAX_BASES = 1ull << 29;    // database segment size (positions stay uint32; bounds the pair table)
 constexpr uint64_t STAGE_BYTES = 256ull << 20;    // ASCII staging buffer on the device
 constexpr uint32_t PAD_WORDS = 16;                // zero words after every packed array
+constexpr uint32_t BINS_STRIDE = 6 * NW_NBINS + 8;
 
 struct Seg {
     uint64_t pos_base = 0, seq_base = 0;  // offsets inside the shard handed to set_db
@@ -72,7 +73,12 @@ struct imsame_ctx {
     unsigned long long *run_keys = nullptr, *run_payload = nullptr;
     imsame_params run_params;
     bool run_active = false;
-    uint32_t *d_bins = nullptr;  // [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors | then NBINS work heads
+    // per segment (stride BINS_STRIDE): [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors |
+    // NBINS work heads | 2*NBINS launch ranges
+    uint32_t *d_bins = nullptr;
+    uint32_t bins_segs = 0;
+    uint64_t pairs_cap = 0;                       // capacity of pairs / res (all segments of a run)
+    std::vector<uint64_t> seg_pair_base, seg_pair_count;
     NwLink *carry = nullptr;
     uint64_t carry_warps = 0;
     uint8_t *stage = nullptr;
@@ -205,16 +211,32 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
         CK(cudaMemcpy(ctx->d_lut, lut.data(), EXT_LUT_SIZE * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     if (want_cap > ctx->hcap) {
-        dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
+        dev_free(ctx->hkeys); dev_free(ctx->hvals);
         int rc;
         if ((rc = dev_alloc(ctx, &ctx->hkeys, want_cap))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->hvals, want_cap))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->pairs, want_cap))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->res, want_cap))) return rc;
         ctx->hcap = want_cap;
         CK(cudaMemsetAsync(ctx->hkeys, 0xFF, (size_t)want_cap * 8, ctx->stream));
         CK(cudaMemsetAsync(ctx->hvals, 0xFF, (size_t)want_cap * 8, ctx->stream));
     }
+    return IMSAME_OK;
+}
+
+// the candidate list of a whole run (all segments) lives in pairs/res; grown geometrically, contents kept
+int ensure_pairs(imsame_ctx *ctx, uint64_t need) {
+    if (need <= ctx->pairs_cap) return IMSAME_OK;
+    uint64_t cap = std::max<uint64_t>(ctx->pairs_cap, 1u << 20);
+    while (cap < need) cap += cap / 2;
+    PairRec *np = nullptr;
+    PairRes *nr = nullptr;
+    int rc;
+    if ((rc = dev_alloc(ctx, &np, cap))) return rc;
+    if ((rc = dev_alloc(ctx, &nr, cap))) { cudaFree(np); return rc; }
+    if (ctx->pairs && ctx->pairs_cap)
+        CK(cudaMemcpyAsync(np, ctx->pairs, ctx->pairs_cap * sizeof(PairRec), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx->pairs); dev_free(ctx->res);
+    ctx->pairs = np; ctx->res = nr; ctx->pairs_cap = cap;
     return IMSAME_OK;
 }
 
@@ -595,7 +617,15 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
         if ((rc = dev_alloc(ctx, &ctx->pkey, nq))) return rc;
         ctx->keys_cap = nq;
     }
-    if (!ctx->d_bins && (rc = dev_alloc(ctx, &ctx->d_bins, 6ull * NW_NBINS + 8))) return rc;
+    const uint32_t nseg = (uint32_t)ctx->segs.size();
+    if (ctx->bins_segs < nseg) {
+        dev_free(ctx->d_bins);
+        if ((rc = dev_alloc(ctx, &ctx->d_bins, (uint64_t)nseg * BINS_STRIDE))) return rc;
+        ctx->bins_segs = nseg;
+    }
+    ctx->seg_pair_base.assign(nseg, 0);
+    ctx->seg_pair_count.assign(nseg, 0);
+    if ((rc = ensure_pairs(ctx, 32ull * nq))) return rc;
     ctx->run_keys = d_keys ? (unsigned long long *)d_keys : ctx->keys;
     ctx->run_payload = d_payload ? (unsigned long long *)d_payload : ctx->payload;
     ctx->run_params = *p;
@@ -663,25 +693,46 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
         if (ctx->hcap >= (1u << 30) || attempt == 7) return IMSAME_ELIMIT;
         if ((rc = ensure_work_buffers(ctx, ctx->hcap * 2))) return rc;  // reallocates + clears the table
     }
-    uint32_t *bin_count = ctx->d_bins, *bin_off = ctx->d_bins + NW_NBINS;
-    uint32_t *launch_range = ctx->d_bins + 4 * NW_NBINS + 4;
+    uint32_t *bins = ctx->d_bins + (size_t)seg * BINS_STRIDE;
+    uint32_t *bin_count = bins, *bin_off = bins + NW_NBINS, *launch_range = bins + 4 * NW_NBINS + 4;
+    uint64_t base = 0;
+    for (int k = 0; k < seg; k++) base += ctx->seg_pair_count[k];
+    if (base >= 0xFFFFFFFFull) return IMSAME_ELIMIT;
+    BinArgs b;
+    b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.q = qm;
+    b.band_width = (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS;
+    b.bin_count = bin_count; b.bin_off = bin_off; b.pairs = ctx->pairs;
+    const int g = std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS),
+                                     (uint32_t)ctx->n_sm * 8);
+    uint32_t n_seg_pairs = 0;
     {
         PhaseScope ps(ctx, PH_K2B);
         add_counters_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->d_counters + 8, 4);
-        CK(cudaMemsetAsync(ctx->d_bins, 0, (6ull * NW_NBINS + 8) * sizeof(uint32_t), ctx->stream));
-        BinArgs b;
-        b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.q = qm;
-        b.band_width = (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS;
-        b.bin_count = bin_count; b.bin_off = bin_off; b.pairs = ctx->pairs;
-        const int g = std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS),
-                                         (uint32_t)ctx->n_sm * 8);
+        CK(cudaMemsetAsync(bins, 0, BINS_STRIDE * sizeof(uint32_t), ctx->stream));
         bin_kernel<0><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
         bin_offsets_kernel<<<1, 32, 0, ctx->stream>>>(bin_count, bin_off, launch_range, ctx->d_small,
-                                                    (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u);
-        bin_kernel<1><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
-        ctx->launches += 4;
+                                                    (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u, (uint32_t)base);
+        ctx->launches += 3;
     }
+    CK(cudaMemcpyAsync(&n_seg_pairs, ctx->d_small, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (base + n_seg_pairs >= 0xFFFFFFFFull) return IMSAME_ELIMIT;
+    if ((rc = ensure_pairs(ctx, base + n_seg_pairs))) return rc;
+    b.pairs = ctx->pairs;
+    {
+        PhaseScope ps(ctx, PH_K2B);
+        bin_kernel<1><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
+        ctx->launches++;
+    }
+    ctx->seg_pair_base[seg] = base;
+    ctx->seg_pair_count[seg] = n_seg_pairs;
     CK(cudaGetLastError());
+    if (n_seg_pairs && (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE)) {
+        // a hit passed the e-value test while some read exceeds MAX_READ_SIZE: the reference would
+        // abort as soon as such a read reaches NW (src/alignmentFunctions.c:155)
+        ctx->run_active = false;
+        return IMSAME_EREADSIZE;
+    }
     return IMSAME_OK;
 }
 
@@ -691,7 +742,8 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
         return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     const imsame_params *p = &ctx->run_params;
-    uint32_t *bin_work = ctx->d_bins + 3 * NW_NBINS + 4, *launch_range = ctx->d_bins + 4 * NW_NBINS + 4;
+    uint32_t *bins = ctx->d_bins + (size_t)seg * BINS_STRIDE;
+    uint32_t *bin_work = bins + 3 * NW_NBINS + 4, *launch_range = bins + 4 * NW_NBINS + 4;
     PhaseScope ps(ctx, PH_K3);
     NwArgs a;
     a.db = seg_map(ctx->segs[seg]); a.q = query_map(ctx); a.pairs = ctx->pairs; a.res = ctx->res;
@@ -714,7 +766,9 @@ extern "C" int imsame_gpu_run_select(imsame_ctx *ctx, int seg) {
     if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     PhaseScope ps(ctx, PH_SELECT);
-    select_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->pairs, ctx->res, ctx->d_small, ctx->run_keys,
+    select_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->pairs + ctx->seg_pair_base[seg],
+                                                        ctx->res + ctx->seg_pair_base[seg],
+                                                        (uint32_t)ctx->seg_pair_count[seg], ctx->run_keys,
                                                         ctx->run_payload, ctx->pkey,
                                                         ctx->run_params.db_seq_base + ctx->segs[seg].seq_base,
                                                         ctx->d_counters + 5);
@@ -748,13 +802,15 @@ static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, u
                     imsame_stats *st) {
     int rc;
     if ((rc = imsame_gpu_run_begin(ctx, p, d_keys, d_payload))) return rc;
-    for (int seg = 0; seg < (int)ctx->segs.size(); seg++) {
+    const int nseg = (int)ctx->segs.size();
+    for (int seg = 0; seg < nseg; seg++)
         if ((rc = imsame_gpu_run_scan(ctx, seg))) return rc;
-        // ascending bands: an accepted early candidate prunes the read's later ones
-        for (int band = 0; band < NW_BANDS; band++)
+    // ascending bands over ALL segments: an accepted early candidate prunes the read's later ones
+    for (int band = 0; band < NW_BANDS; band++)
+        for (int seg = 0; seg < nseg; seg++)
             if ((rc = imsame_gpu_run_band(ctx, seg, band))) return rc;
+    for (int seg = 0; seg < nseg; seg++)
         if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
-    }
     return imsame_gpu_run_end(ctx, st);
 }
 

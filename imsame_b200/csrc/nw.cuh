@@ -91,6 +91,11 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
         }
         const uint32_t xs = read_start(a.db, pr.s);
         const uint32_t xlen = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs);
+        if (xlen > (uint32_t)MAX_READ || ylen > (uint32_t)MAX_READ) {
+            // the reference aborts here (src/alignmentFunctions.c:155); the host reports IMSAME_EREADSIZE
+            if (lane == 0) { PairRes z; z.score = 0; z.bx = z.by = 0; z.stats = 0; a.res[idx] = z; }
+            continue;
+        }
         const int X1 = (int)xlen - 1, Y1 = (int)ylen - 1;
         uint16_t *tb_pair = nullptr;
         uint32_t tb_str = 0;

@@ -292,17 +292,17 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_kernel(BinArgs a) {
 // work range of every (class, launch) : bands are merged into fewer launches when there are too
 // few candidates to fill the GPU per band (min_per_launch), later launches of a class stay empty.
 __global__ void bin_offsets_kernel(const uint32_t *bin_count, uint32_t *bin_off, uint32_t *launch_range,
-                                   uint32_t *n_pairs, uint32_t min_per_launch) {
+                                   uint32_t *n_pairs, uint32_t min_per_launch, uint32_t base) {
     if (threadIdx.x == 0) {
-        uint32_t acc = 0;
+        uint32_t acc = base;  // this segment's candidates follow those of the earlier segments
         for (int i = 0; i < NW_NBINS; i++) {
             bin_off[i] = acc;
             bin_off[NW_NBINS + 1 + i] = acc;
             acc += bin_count[i];
         }
         bin_off[NW_NBINS] = acc;
-        *n_pairs = acc;
-        uint32_t launches = acc / (min_per_launch ? min_per_launch : 1u);
+        *n_pairs = acc - base;
+        uint32_t launches = (acc - base) / (min_per_launch ? min_per_launch : 1u);
         launches = launches < 1u ? 1u : (launches > (uint32_t)NW_BANDS ? (uint32_t)NW_BANDS : launches);
         const uint32_t merge = ((uint32_t)NW_BANDS + launches - 1) / launches;  // bands per launch
         for (int c = 0; c < 9; c++)
@@ -317,10 +317,9 @@ __global__ void bin_offsets_kernel(const uint32_t *bin_count, uint32_t *bin_off,
 }
 
 // after NW: the pair whose key equals the read's final key owns the record
-__global__ void select_kernel(const PairRec *pairs, const PairRes *res, const uint32_t *n_pairs,
+__global__ void select_kernel(const PairRec *pairs, const PairRes *res, uint32_t n,
                               const unsigned long long *best, unsigned long long *payload,
                               unsigned long long *pkey, uint64_t seg_seq_base, unsigned long long *pairs_total) {
-    const uint32_t n = *n_pairs;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pairs_total, (unsigned long long)n);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const PairRec pr = pairs[i];

@@ -126,9 +126,10 @@ int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *params, uint64_t *d_key
  * it early prunes this shard's later candidates exactly like the reference's early exit,
  * src/alignmentFunctions.c:172,189):
  *     run_begin(params, d_keys, d_payload)
- *     for seg in [0, n_segments):   run_scan(seg)
- *         for band in [0, n_bands): run_band(seg, band)    [caller: all-reduce(d_keys, MIN)]
- *         run_select(seg)
+ *     for seg in [0, n_segments):   run_scan(seg)           (all scans first: candidates are kept)
+ *     for band in [0, n_bands):
+ *         for seg in [0, n_segments): run_band(seg, band)   [caller: all-reduce(d_keys, MIN)]
+ *     for seg in [0, n_segments):   run_select(seg)
  *     run_end(stats)                                        [caller: all-reduce(d_payload, MAX)]
  * Bands order a read's candidates by the position of their k-mer inside the read; run_end zeroes
  * every payload whose key is no longer the read's key, so the owner's payload survives a MAX. */
