@@ -18,6 +18,10 @@ __device__ __forceinline__ void step(int &a, int b, int c) {
     if (OP == 4) asm volatile("{ .reg .pred p; setp.gt.s32 p, %0, %1; selp.s32 %0, %2, %0, p; }" : "+r"(a) : "r"(b), "r"(c));
     if (OP == 5) a = __viaddmax_s32(a, b, c);
     if (OP == 6) a = __vimax3_s32(a, b, c);
+    // float forms of the same recurrence pieces (scores are small integers, exact in fp32)
+    if (OP == 7) asm volatile("{ .reg .pred p; setp.gt.f32 p, %0, %1; selp.f32 %0, %2, %0, p; }" : "+f"(*(float *)&a) : "f"(*(float *)&b), "f"(*(float *)&c));
+    if (OP == 8) asm volatile("max.f32 %0, %0, %1;" : "+f"(*(float *)&a) : "f"(*(float *)&b));
+    if (OP == 9) asm volatile("add.f32 %0, %0, %1;" : "+f"(*(float *)&a) : "f"(*(float *)&b));
 }
 
 template <int OP, int OP2>
@@ -74,6 +78,10 @@ int main() {
     run<4, 4>("setp+selp", 2, d, p.multiProcessorCount);
     run<5, 5>("viaddmax", 1, d, p.multiProcessorCount);
     run<6, 6>("vimax3", 1, d, p.multiProcessorCount);
+    run<7, 7>("fsetp+fsel", 2, d, p.multiProcessorCount);
+    run<8, 8>("fmnmx", 1, d, p.multiProcessorCount);
+    run<9, 9>("fadd", 1, d, p.multiProcessorCount);
+    run<7, 4>("fsetp+fsel | isetp+sel 1:1", 2, d, p.multiProcessorCount);
     run<0, 2>("iadd+imad 1:1", 1, d, p.multiProcessorCount);
     run<1, 2>("imnmx+imad 1:1", 1, d, p.multiProcessorCount);
     run<0, 1>("iadd+imnmx 1:1", 1, d, p.multiProcessorCount);
