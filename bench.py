@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; <1 is not a valid bench)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nw-mode", type=int, default=0, help="0: packed-word K3 where eligible (default); 1: generic K3 (A/B only)")
     ap.add_argument("--cpu-sample-queries", type=int, default=2000)
     ap.add_argument("--cpu-sample-db", type=int, default=200000)
     return ap.parse_args()
@@ -240,6 +241,7 @@ def run_ours(args):
                              db_seq_base=rank * nd)
 
     ctx = api.Imsame(local)
+    ctx.set_nw_mode(args.nw_mode)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")

@@ -61,7 +61,7 @@ SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "im
            "imsame_gpu_set_stream", "imsame_gpu_align", "imsame_gpu_set_query", "imsame_gpu_set_db",
            "imsame_gpu_run", "imsame_gpu_n_segments", "imsame_gpu_n_bands", "imsame_gpu_run_begin",
            "imsame_gpu_run_scan", "imsame_gpu_run_band", "imsame_gpu_run_select", "imsame_gpu_run_end",
-           "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch",
+           "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode",
            "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
 _lib = None
@@ -107,6 +107,7 @@ def lib():
                                           C.POINTER(C.c_float)]
         l.imsame_gpu_traceback.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(SeqInfo), C.POINTER(Params), vp, vp,
                                            C.POINTER(C.POINTER(C.c_uint32)), vp]
+        l.imsame_gpu_set_nw_mode.argtypes = [vp, C.c_int]
         l.imsame_gpu_free.argtypes = [vp]
         l.imsame_gpu_free.restype = None
         l.imsame_gpu_host_alloc.argtypes = [u64]
@@ -212,6 +213,10 @@ class Imsame:
         self._check(lib().imsame_gpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
 
     # -- one call: index + scan + NW + selection (src/IMSAME.c:232-281 + :409-467)
+    def set_nw_mode(self, mode):
+        """0 = packed-word K3 where eligible (default), 1 = generic K3 only"""
+        self._check(lib().imsame_gpu_set_nw_mode(self._h, int(mode)))
+
     def align(self, db, query, params=None, db_breaks=None):
         """db, query: (seq uint8 ASCII, start uint64[n+1]). Returns (records ndarray BEST_DTYPE, stats dict)."""
         params = params or make_params()

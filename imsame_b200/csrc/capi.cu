@@ -13,6 +13,7 @@
 #include "../../include/imsame_gpu.h"
 #include "../host/imsame_host.h"
 #include "nw.cuh"
+#include "nwp.cuh"
 #include "qtable.cuh"
 #include "scan.cuh"
 
@@ -83,6 +84,8 @@ struct imsame_ctx {
     uint64_t carry_warps = 0;
     uint8_t *stage = nullptr;
     int nw_grid[9] = {0};
+    int nwp_grid[9] = {0};
+    int nw_mode = 0;  // 0: packed-word kernel where pw_eligible() holds, 1: generic kernel only
     int scan_grid = 0;
 
     // phase timing
@@ -273,22 +276,56 @@ int launch_nw_class(imsame_ctx *ctx, const NwArgs &a, int c) {
     return rc;
 }
 
+// packed-word kernel (nwp.cuh) of NW class c: 16 lanes x 2c columns
+template <int C>
+int launch_nwp(imsame_ctx *ctx, NwArgs a) {
+    if (!ctx->nwp_grid[C]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nwp_kernel<2 * C>, NWP_THREADS, 0));
+        ctx->nwp_grid[C] = std::max(1, per_sm) * ctx->n_sm;
+    }
+    a.s_class = C;
+    nwp_kernel<2 * C><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    ctx->k3_launches++;
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+int launch_nwp_class(imsame_ctx *ctx, const NwArgs &a, int c) {
+    switch (c) {
+        case 1: return launch_nwp<1>(ctx, a);
+        case 2: return launch_nwp<2>(ctx, a);
+        case 3: return launch_nwp<3>(ctx, a);
+        case 4: return launch_nwp<4>(ctx, a);
+        case 5: return launch_nwp<5>(ctx, a);
+        case 6: return launch_nwp<6>(ctx, a);
+        case 7: return launch_nwp<7>(ctx, a);
+        default: return launch_nwp<8>(ctx, a);
+    }
+}
+
+bool use_packed(const imsame_ctx *ctx, uint32_t xmax, uint32_t ymax, int igap, int egap) {
+    return ctx->nw_mode != 1 && pw_eligible(xmax, ymax, igap, egap);
+}
+
 // unsorted explicit pairs: every class kernel walks the whole list and skips the other classes
 template <bool TB>
-int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 9 zeroed */) {
+int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 9 zeroed */,
+                      bool packed = false) {
     int rc = IMSAME_OK;
     a.check_class = 1;
     for (int c = 1; c <= 8 && !rc; c++) {
         if (!(class_mask & (1u << c))) continue;
         a.work = work_heads + c;
-        rc = launch_nw_class<TB>(ctx, a, c);
+        rc = (packed && !TB) ? launch_nwp_class(ctx, a, c) : launch_nw_class<TB>(ctx, a, c);
     }
     return rc;
 }
 
 int max_nw_grid(imsame_ctx *ctx) {
     int g = 0;
-    for (int c = 1; c <= 8; c++) g = std::max(g, ctx->nw_grid[c]);
+    for (int c = 1; c <= 8; c++) g = std::max(g, std::max(ctx->nw_grid[c], 2 * ctx->nwp_grid[c]));
     return g ? g : ctx->n_sm * 8;
 }
 
@@ -751,12 +788,13 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
     a.best = ctx->run_keys; a.cells = ctx->d_counters + 4; a.carry = ctx->carry; a.s_class = 0;
     a.tb = nullptr; a.tb_off = nullptr; a.check_class = 0;
     int rc;
+    const bool packed = use_packed(ctx, ctx->db_maxlen, ctx->q_maxlen, p->igap, p->egap);
     for (int c = 1; c <= 8; c++) {
         if (!(ctx->class_mask & (1u << c))) continue;
         const int bin = c * NW_BANDS + band;
         a.range = launch_range + 2 * bin;
         a.work = bin_work + bin;
-        if ((rc = launch_nw_class<false>(ctx, a, c))) return rc;
+        if ((rc = packed ? launch_nwp_class(ctx, a, c) : launch_nw_class<false>(ctx, a, c))) return rc;
     }
     return IMSAME_OK;
 }
@@ -821,6 +859,12 @@ int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, ui
     if (!ctx || !p) return IMSAME_EARG;
     reset_timing(ctx);
     return run_impl(ctx, p, d_keys, d_payload, st);
+}
+
+int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 1) return IMSAME_EARG;
+    ctx->nw_mode = mode;
+    return IMSAME_OK;
 }
 
 int imsame_gpu_mask_payload(imsame_ctx *ctx, const uint64_t *reduced, const uint64_t *local, uint64_t *payload) {
@@ -896,7 +940,7 @@ namespace {
 
 struct PairBatch {
     imsame_ctx *ctx;
-    uint32_t n = 0, class_mask = 0, ymax = 0;
+    uint32_t n = 0, class_mask = 0, ymax = 0, xmax = 0;
     uint32_t *xpk = nullptr, *ypk = nullptr, *dxs = nullptr, *dys = nullptr, *dsmall = nullptr;
     PairRec *dp = nullptr;
     PairRes *dr = nullptr;
@@ -922,6 +966,7 @@ struct PairBatch {
             xt += xlen[i]; yt += ylen[i];
             class_mask |= 1u << nw_class_of(ylen[i]);
             ymax = std::max(ymax, ylen[i]);
+            xmax = std::max(xmax, xlen[i]);
         }
         if (xt >= 0xFFFFFF00ull || yt >= 0xFFFFFF00ull) return IMSAME_ELIMIT;
         xs[n] = (uint32_t)xt; ys[n] = (uint32_t)yt;
@@ -986,7 +1031,7 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
-    rc = launch_nw_classes<false>(ctx, a, pb.class_mask, pb.dsmall + 4);
+    rc = launch_nw_classes<false>(ctx, a, pb.class_mask, pb.dsmall + 4, use_packed(ctx, pb.xmax, pb.ymax, igap, egap));
     cudaEventRecord(e1, ctx->stream);
     std::vector<PairRes> hr(n_pairs);
     if (!rc) {

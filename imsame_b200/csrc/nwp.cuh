@@ -1,0 +1,168 @@
+// nwp.cuh -- K3p: the NW/filter/selection kernel of nw.cuh for short reads, in packed words
+// (nwp_core.cuh).  Half a warp per candidate pair: 16 lanes x S columns cover a query read of
+// up to 257 bases in one pass, two pairs per warp run in lockstep.  One 3-input maximum, two
+// compares and four selects per cell on the ALU pipe, the rest adds/logic ops that the FMA
+// pipe co-issues; the two per-cell constants (diagonal statistics, match score) come from a
+// shared-memory table indexed by the step's mismatch bits, four cells per 2 x 128-bit load.
+// Same inputs, outputs, pruning and epilogue as nw_kernel<S, false>; used whenever
+// pw_eligible() holds for the run (capi.cu), bit-identical results otherwise impossible.
+#pragma once
+#include "nw.cuh"
+#include "nwp_core.cuh"
+
+namespace imsame {
+
+constexpr int NWP_WARPS = 8;
+constexpr int NWP_THREADS = NWP_WARPS * 32;
+constexpr int NWP_TBL = 0x56;  // table index = mismatch bits of 4 cells at bits 0,2,4,6
+
+#if defined(__CUDACC__)
+
+struct PwDevEW {
+    const int *tbl;
+    uint32_t mm;
+    __device__ __forceinline__ PwE4 operator()(int g) const {
+        const uint32_t idx = (mm >> (8 * g)) & 0x55u;
+        const int4 *p = reinterpret_cast<const int4 *>(tbl + idx * 8);
+        const int4 d = p[0], s = p[1];
+        PwE4 e;
+        e.ds[0] = d.x; e.ds[1] = d.y; e.ds[2] = d.z; e.ds[3] = d.w;
+        e.sb[0] = s.x; e.sb[1] = s.y; e.sb[2] = s.z; e.sb[3] = s.w;
+        return e;
+    }
+};
+
+template <int S>
+__global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
+    __shared__ __align__(16) int tbl[NWP_TBL * 8];
+    __shared__ uint8_t sx_all[NWP_WARPS * 2][PW_MAX_X];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hl = lane & 15, half = lane >> 4;
+    const unsigned hmask = 0xFFFFu << (16 * half);
+    uint8_t *sx = sx_all[warp * 2 + half];
+    const uint32_t r_begin = a.range[0], r_end = a.range[1];
+    const PwK k = pw_consts(a.igap, a.egap);
+    for (int e = threadIdx.x; e < NWP_TBL; e += NWP_THREADS) {
+        const PwE4 v = pw_e4(k, (uint32_t)e);
+#pragma unroll
+        for (int c = 0; c < 4; c++) { tbl[e * 8 + c] = v.ds[c]; tbl[e * 8 + 4 + c] = v.sb[c]; }
+    }
+    __syncthreads();
+    unsigned long long my_cells = 0, my_pairs = 0;
+
+    for (;;) {
+        // each half warp takes the next pair that still has to be aligned
+        bool have = false;
+        uint32_t idx = 0, xs = 0, ys = 0, xlen = 0, ylen = 0, rd = 0;
+        unsigned long long key = 0;
+        for (;;) {
+            if (hl == 0) idx = atomicAdd(a.work, 1u);
+            idx = __shfl_sync(hmask, idx, 16 * half) + r_begin;
+            if (idx >= r_end) break;
+            const PairRec pr = a.pairs[idx];
+            ys = read_start(a.q, pr.r);
+            ylen = (a.q.fixed_len ? a.q.fixed_len : a.q.start[pr.r + 1] - ys);
+            if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
+            xs = read_start(a.db, pr.s);
+            xlen = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs);
+            const bool pruned = a.best && pr.key >= a.best[pr.r];  // an earlier hit of this read is accepted
+            if (pruned || xlen < 2 || ylen < 2 || xlen > (uint32_t)PW_MAX_X || ylen > (uint32_t)PW_MAX_Y) {
+                if (hl == 0) {
+                    PairRes z; z.score = pruned ? 0 : NW_NEG * 2; z.bx = z.by = 0; z.stats = 0;
+                    a.res[idx] = z;
+                    if (!pruned) { my_pairs++; }
+                }
+                continue;
+            }
+            rd = pr.r; key = pr.key; have = true;
+            break;
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, have)) break;
+        const int X1 = have ? (int)xlen - 1 : 0, Y1 = have ? (int)ylen - 1 : 0;
+        if (have)
+            for (uint32_t i = hl; i < xlen; i += 16) sx[i] = (uint8_t)base_at(a.db.pk, (uint64_t)xs + i);
+        __syncwarp();
+        const int nl = (Y1 + S - 1) / S;
+        const int j0 = hl * S + 1;
+        uint32_t x0 = 0, y0 = 0, ycols = 0;
+        PwLane<S> L;
+        {
+            uint64_t halo = 0;
+            if (have) {
+                const int64_t g = (int64_t)ys + j0 - 2;
+                halo = g >= 0 ? fetch32(a.q.pk, (uint64_t)g) : (fetch32(a.q.pk, 0) << 2);
+                x0 = sx[0];
+                y0 = base_at(a.q.pk, ys);
+            }
+            ycols = (uint32_t)(halo >> 4);  // codes of Y[j0 .. j0+15]
+            pw_lane_init<S>(L, k, x0, halo, hl == 0, hl);
+        }
+        const int cl = Y1 > 0 ? (Y1 - 1) % S : 0;
+        const bool owns_last = (Y1 >= j0) && (Y1 < j0 + S);
+        int steps = have ? X1 + nl - 1 : 0;
+        {
+            const int o = __shfl_xor_sync(0xffffffffu, steps, 16);
+            steps = steps > o ? steps : o;
+        }
+        PwLink out;
+        out.a = out.b = out.mfz = out.lw = 0;
+        // lane l of a half works on row t - l + 1; the two row histories swap roles with the step parity
+#define IMS_PW_STEP(T_, PREV1, PREV2)                                                              \
+    {                                                                                              \
+        const int i = (T_) - hl + 1;                                                               \
+        PwLink in;                                                                                 \
+        in.a = __shfl_up_sync(0xffffffffu, out.a, 1, 16);                                          \
+        in.b = __shfl_up_sync(0xffffffffu, out.b, 1, 16);                                          \
+        in.mfz = __shfl_up_sync(0xffffffffu, out.mfz, 1, 16);                                      \
+        in.lw = __shfl_up_sync(0xffffffffu, out.lw, 1, 16);                                        \
+        const bool act = have && (hl < nl) && (i >= 1) && (i <= X1);                               \
+        if (act) {                                                                                 \
+            const uint32_t xi = sx[i];                                                             \
+            if (hl == 0) in = pw_first_link(k, xi, y0);                                            \
+            const uint32_t d_ = ycols ^ (xi * 0x55555555u);                                        \
+            PwDevEW ew;                                                                            \
+            ew.tbl = tbl;                                                                          \
+            ew.mm = (d_ | (d_ >> 1));                                                              \
+            pw_row<S>(L, PREV1, PREV2, in, out, i, j0, ew, k, X1, Y1, cl, owns_last);              \
+        }                                                                                          \
+    }
+        for (int t = 0; t < steps; t += 2) {
+            IMS_PW_STEP(t, L.r0, L.r1)
+            if (t + 1 < steps) IMS_PW_STEP(t + 1, L.r1, L.r0)
+        }
+#undef IMS_PW_STEP
+        // reduction of the best border cell over the half warp ("last in row-major order" on ties)
+        int bz = (have && hl < nl) ? L.bz : (int)0x80000000, bw = L.bw, bi = L.bi, bj = L.bj;
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1) {
+            const int cz = __shfl_xor_sync(0xffffffffu, bz, o);
+            const int cw = __shfl_xor_sync(0xffffffffu, bw, o);
+            const int ci = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int cj = __shfl_xor_sync(0xffffffffu, bj, o);
+            const bool better = cz > bz || (cz == bz && (ci > bi || (ci == bi && cj > bj)));
+            if (better) { bz = cz; bw = cw; bi = ci; bj = cj; }
+        }
+        if (hl == 0 && have) {
+            const uint32_t len = pw_len(k, bw), id = pw_ids(k, bw);
+            // src/alignmentFunctions.c:163 through the host-built exact tables
+            const bool ok = len > 0 && len >= a.lmin[ylen] && id >= a.imin[len];
+            PairRes z;
+            z.score = pw_score(k, bw); z.bx = (uint32_t)bi; z.by = (uint32_t)bj;
+            z.stats = (len << 16) | id | (ok ? 0x80000000u : 0u);
+            a.res[idx] = z;
+            if (ok && a.best) atomicMin(&a.best[rd], key);
+            my_cells += (unsigned long long)X1 * (unsigned long long)Y1;
+            my_pairs++;
+        }
+        __syncwarp();
+    }
+    if (hl == 0 && my_pairs) {
+        atomicAdd(a.cells, my_cells);
+        atomicAdd(a.cells + 2, my_pairs);  // counters[6]: pairs run through NW
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace imsame

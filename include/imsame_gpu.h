@@ -156,6 +156,12 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
                         const uint32_t *xlen, const unsigned char *const *Y, const uint32_t *ylen,
                         int igap, int egap, int32_t *out5, float *ms_kernel);
 
+/* Which K3 kernel evaluates the pairs: 0 (default) = the packed-word kernel whenever every read
+ * of the run is short enough for it (<= 257 query / 512 database bases, non-positive gap scores;
+ * nwp_core.cuh: pw_eligible), the generic kernel otherwise; 1 = always the generic kernel.  Both
+ * give identical results; the switch exists so tests and benchmarks can compare them. */
+int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode);
+
 /* ---- winners-only traceback (src/alignmentFunctions.c:493-546) ---------- */
 /* For each accepted read of `best`, NW is recomputed on the device with one
  * back-pointer code per cell and walked back from the best border cell.  The

@@ -1,0 +1,129 @@
+// CPU emulation of the 16-lane packed-word wavefront (nwp_core.cuh, kernel nwp.cuh): lanes
+// stepped in lockstep, neighbour hand-over = value of the previous step.  Checks
+// imsame::pw_row / pw_lane_init against the oracle's forward NW, bit for bit, on every pair
+// that pw_eligible admits (and checks that the eligibility bound is what keeps it exact by
+// also running pairs at the edge of the admitted range).
+//   usage: nwp_emul <n_cases> <seed>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../imsame_b200/csrc/nwp_core.cuh"
+extern "C" {
+#include "../../oracle/imsame_oracle.h"
+}
+using namespace imsame;
+
+static uint64_t rng_state;
+static uint64_t rnd() { uint64_t z = (rng_state += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+static inline uint32_t code(unsigned char c) { return (c >> 1) & 3; }
+
+struct Res { int s, i, j; uint32_t len, id; };
+
+struct HostEW {
+    const PwK *k; uint32_t mm;
+    PwE4 operator()(int g) const { return pw_e4(*k, (mm >> (8 * g)) & 0xFFu); }
+};
+
+template <int S>
+static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
+    const int X1 = xlen - 1, Y1 = ylen - 1;
+    const PwK k = pw_consts(igap, egap);
+    Res best; best.s = NW_NEG * 2; best.i = best.j = 0; best.len = best.id = 0;
+    if (X1 < 1 || Y1 < 1) return best;
+    const int nl = (Y1 + S - 1) / S;
+    if (nl > PW_LANES) { fprintf(stderr, "bad S\n"); exit(2); }
+    PwLane<S> lanes[PW_LANES]; PwLink outs[PW_LANES];
+    for (int l = 0; l < nl; l++) {
+        int j0 = l * S + 1;
+        uint64_t halo = 0;
+        for (int c = 0; c < S + 2; c++) { int j = j0 - 2 + c; uint64_t cd = (j >= 0 && j < ylen) ? code(Y[j]) : (rnd() & 3); halo |= cd << (2 * c); }
+        pw_lane_init<S>(lanes[l], k, code(X[0]), halo, l == 0, l);
+    }
+    for (int t = 0; t <= X1 + nl - 2; t++) {
+        for (int l = nl - 1; l >= 0; l--) {
+            int i = t - l + 1;
+            if (i < 1 || i > X1) continue;
+            int j0 = l * S + 1;
+            PwLink in = (l == 0) ? pw_first_link(k, code(X[i]), code(Y[0])) : outs[l - 1];
+            uint32_t mm = 0;
+            for (int c = 0; c < S; c++) { int j = j0 + c; uint32_t y = j < ylen ? code(Y[j]) : (uint32_t)(rnd() & 3); if (y != code(X[i])) mm |= 1u << (2 * c); }
+            HostEW ew{&k, mm};
+            PwLink out;
+            const int cl = (Y1 - 1) % S; const bool owns = Y1 >= j0 && Y1 < j0 + S;
+            if (t & 1) pw_row<S>(lanes[l], lanes[l].r1, lanes[l].r0, in, out, i, j0, ew, k, X1, Y1, cl, owns);
+            else pw_row<S>(lanes[l], lanes[l].r0, lanes[l].r1, in, out, i, j0, ew, k, X1, Y1, cl, owns);
+            outs[l] = out;
+        }
+    }
+    bool have = false; int bz = 0, bw = 0, bi = 0, bj = 0;
+    for (int l = 0; l < nl; l++) {
+        const PwLane<S> &L = lanes[l];
+        if (L.bw == (int)0x80000000) continue;
+        bool better = !have || L.bz > bz || (L.bz == bz && (L.bi > bi || (L.bi == bi && L.bj > bj)));
+        if (better) { have = true; bz = L.bz; bw = L.bw; bi = L.bi; bj = L.bj; }
+    }
+    if (have) { best.s = pw_score(k, bw); best.i = bi; best.j = bj; best.len = pw_len(k, bw); best.id = pw_ids(k, bw); }
+    return best;
+}
+
+template <int S>
+static Res dispatch(int s, const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
+    if (s == S) return run_pair<S>(X, xlen, Y, ylen, igap, egap);
+    if constexpr (S < 16) return dispatch<S + 1>(s, X, xlen, Y, ylen, igap, egap);
+    fprintf(stderr, "bad S\n"); exit(2);
+}
+
+int main(int argc, char **argv) {
+    int n = argc > 1 ? atoi(argv[1]) : 200; rng_state = argc > 2 ? strtoull(argv[2], 0, 10) : 1;
+    const char B[4] = {'A', 'C', 'G', 'T'};
+    int bad = 0, skipped = 0;
+    for (int it = 0; it < n; it++) {
+        int xlen = 2 + rnd() % (it % 7 == 0 ? 510 : 255), ylen = 2 + rnd() % 256;
+        if (it % 11 == 0) { xlen = 250; ylen = 250; }
+        if (it % 19 == 0) { xlen = 256; ylen = 257; }
+        if (it % 23 == 0) { xlen = 512; ylen = 256; }
+        if (it % 13 == 0) { xlen = 2 + rnd() % 6; }
+        if (it % 17 == 0) { ylen = 2 + rnd() % 6; }
+        std::vector<unsigned char> X(xlen), Y(ylen);
+        int alpha = (it % 29 == 0) ? 1 : 3;  // low-complexity reads: many equal scores (tie rules)
+        for (auto &c : X) c = B[rnd() & alpha];
+        int mode = rnd() % 4;
+        if (mode == 0) for (auto &c : Y) c = B[rnd() & alpha];
+        else {
+            int off = (int)(rnd() % (xlen)) - xlen / 3; double pe = (mode == 1) ? 0.03 : (mode == 2 ? 0.15 : 0.30);
+            if (it % 5 == 0) off = 0;
+            int src = off;
+            for (int j = 0; j < ylen; j++) {
+                double u = (rnd() >> 11) * (1.0 / 9007199254740992.0);
+                if (u < pe / 6) { src += 1 + rnd() % 4; }
+                if (u > 1 - pe / 6) { Y[j] = B[rnd() & 3]; continue; }
+                unsigned char c = (src >= 0 && src < xlen) ? X[src] : B[rnd() & alpha];
+                if (u > 0.5 && u < 0.5 + pe) c = B[rnd() & 3];
+                Y[j] = c; src++;
+            }
+        }
+        int igap = -(int)(rnd() % 8), egap = -(int)(rnd() % 4);
+        if (it % 3 == 0) { igap = -5; egap = -2; }
+        if (it % 31 == 0) { igap = 0; egap = 0; }
+        if (it % 37 == 0) { igap = -(int)(rnd() % 40); egap = -(int)(rnd() % 7); }
+        if (!pw_eligible(xlen, ylen, igap, egap)) { skipped++; continue; }
+        int32_t os; uint32_t obx, oby, olen, oid;
+        orc_nw_forward(X.data(), xlen, Y.data(), ylen, igap, egap, &os, &obx, &oby, &olen, &oid);
+        const int smin = (ylen - 1 + PW_LANES - 1) / PW_LANES;
+        int s = smin < 1 ? 1 : smin;
+        if (it % 2 == 0) { s = 2 * ((ylen - 1 + 31) / 32); if (s < 2) s = 2; }  // what the kernel uses: 2 * class
+        else if (s < 16 && (it % 4 == 1)) s += rnd() % (17 - s);
+        Res b = dispatch<1>(s, X.data(), xlen, Y.data(), ylen, igap, egap);
+        bool ok;
+        if (xlen < 2 || ylen < 2) ok = true;
+        else ok = b.s == os && (uint32_t)b.i == obx && (uint32_t)b.j == oby && b.len == olen && b.id == oid;
+        if (!ok) {
+            bad++;
+            if (bad < 10) printf("MISMATCH it=%d xlen=%d ylen=%d S=%d gaps=%d,%d: emul (%d,%d,%d,%u,%u) oracle (%d,%u,%u,%u,%u)\n", it, xlen, ylen, s, igap, egap,
+                                 b.s, b.i, b.j, b.len, b.id, os, obx, oby, olen, oid);
+        }
+    }
+    printf("%d cases, %d skipped (not eligible), %d mismatches\n", n, skipped, bad);
+    return bad != 0;
+}

@@ -41,6 +41,53 @@ def test_nw_batch_matches_oracle(gpu):
             assert tuple(int(v) for v in got[i]) == want, (i, len(x), len(y), igap, egap)
 
 
+def _oracle_nw(lib, x, y, igap, egap):
+    s = C.c_int32(); bx = C.c_uint32(); by = C.c_uint32(); ln = C.c_uint32(); idn = C.c_uint32()
+    u8p = C.POINTER(C.c_ubyte)
+    lib.orc_nw_forward(x.ctypes.data_as(u8p), len(x), y.ctypes.data_as(u8p), len(y), -igap, -egap,
+                       C.byref(s), C.byref(bx), C.byref(by), C.byref(ln), C.byref(idn))
+    return (s.value, bx.value, by.value, ln.value, idn.value)
+
+
+def test_nw_batch_packed_kernel_matches_oracle_and_generic(gpu):
+    """short reads run through the packed-word kernel (nwp.cuh); it must agree bit for bit with the
+    oracle and with the generic kernel, incl. the largest admitted sizes, low-complexity reads (ties)
+    and the gap settings at the edge of pw_eligible"""
+    lib = hp.oracle()
+    rng = np.random.default_rng(77)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    xs, ys = sc.random_pairs(15, 1800, max_len=257)
+    for xl, yl in ((256, 257), (250, 250), (256, 256), (2, 257), (256, 2), (2, 2), (255, 33), (33, 255), (200, 17)):
+        for rep in range(6):
+            x = B[rng.integers(0, 4 if rep < 4 else 2, size=xl)]
+            y = x[:yl].copy() if (rep % 2 and yl <= xl) else B[rng.integers(0, 4 if rep < 4 else 2, size=yl)]
+            xs.append(np.ascontiguousarray(x)); ys.append(np.ascontiguousarray(y))
+    for igap, egap in ((5, 2), (0, 0), (7, 3), (40, 3), (1, 0)):
+        gpu.set_nw_mode(0)
+        got, _ = gpu.nw_batch(xs, ys, igap=igap, egap=egap)
+        gpu.set_nw_mode(1)
+        gen, _ = gpu.nw_batch(xs, ys, igap=igap, egap=egap)
+        gpu.set_nw_mode(0)
+        assert np.array_equal(np.asarray(got), np.asarray(gen)), (igap, egap)
+        for i in range(0, len(xs), 1 if (igap, egap) == (5, 2) else 7):
+            if len(xs[i]) < 2 or len(ys[i]) < 2:
+                continue
+            assert tuple(int(v) for v in got[i]) == _oracle_nw(lib, xs[i], ys[i], igap, egap), (i, len(xs[i]), len(ys[i]), igap, egap)
+
+
+def test_packed_and_generic_kernels_give_the_same_records(gpu):
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(41, 4, 100000, 250, 30000, 1500, 0.08)
+    p = api.make_params(n_threads=4)
+    gpu.set_nw_mode(1)
+    gen, _ = gpu.align((db, ds), (q, qs), p)
+    gpu.set_nw_mode(0)
+    pk, _ = gpu.align((db, ds), (q, qs), p)
+    assert gpu_records(pk) == gpu_records(gen)
+    want, _ = oracle_records(db, ds, q, qs, 4)
+    assert gpu_records(pk) == want and len(want) > 300
+
+
 @pytest.mark.parametrize("n_threads", [1, 4])
 def test_align_fixed_length_matches_oracle(gpu, n_threads):
     from imsame_b200 import api

@@ -53,9 +53,10 @@ def test_threshold_tables_are_exact(built):
         assert imin[0] == 65535
 
 
-@pytest.mark.parametrize("prog,args", [("nw_emul", ["400", "3"]), ("extend_emul", ["5"]), ("tb_emul", ["300", "4"])])
+@pytest.mark.parametrize("prog,args", [("nw_emul", ["400", "3"]), ("nwp_emul", ["3000", "5"]), ("extend_emul", ["5"]),
+                                       ("tb_emul", ["300", "4"])])
 def test_device_functions_on_cpu(built, prog, args, tmp_path):
-    """the HD functions the kernels are made of (nw_core.cuh, extend.cuh, traceback.cuh) + render.c,
+    """the HD functions the kernels are made of (nw_core.cuh, nwp_core.cuh, extend.cuh, traceback.cuh) + render.c,
     compiled for the host and stepped as a 32-lane warp, against the oracle"""
     exe = str(tmp_path / prog)
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"

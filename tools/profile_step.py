@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scale", type=float, default=0.02)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--L", type=int, default=250)
+ap.add_argument("--nw-mode", type=int, default=0)
 a = ap.parse_args()
 nd, nq, g = int(10_000_000 * a.scale), int(1_000_000 * a.scale), max(2, int(1000 * a.scale))
 pool = H.SynthPool(2001, g, 1_000_000)
@@ -24,6 +25,7 @@ pool.close()
 ds = np.arange(nd + 1, dtype=np.uint64) * a.L
 qs = np.arange(nq + 1, dtype=np.uint64) * a.L
 ctx = api.Imsame(0)
+ctx.set_nw_mode(a.nw_mode)
 for _ in range(a.reps):
     out, st = ctx.align((db, ds), (q, qs), api.make_params(n_threads=4))
 print(json.dumps({k: st[k] for k in ("n_hits", "n_evalue_pass", "n_pairs", "n_pairs_dp", "n_cells", "ms_k1", "ms_k2",
