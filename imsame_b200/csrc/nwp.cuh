@@ -18,13 +18,20 @@ constexpr int NWP_TBL = 0x56;  // table index = mismatch bits of 4 cells at bits
 
 #if defined(__CUDACC__)
 
+// Table layout: row idx = 8 copies of the same 16-byte entry (128 bytes = all 32 banks), one table
+// for the diagonal constants and one for the match scores.  A 128-bit shared load is served in
+// four phases of 8 consecutive lanes; lane l reads copy l & 7, so the 8 lanes of a phase always
+// hit 8 different bank groups whatever their indices are: no bank conflicts (the first version,
+// one 32-byte entry per index, ran at 96 % of the shared-memory pipe with 70 % conflict wavefronts).
 struct PwDevEW {
     const int *tbl;
-    uint32_t mm;
+    uint32_t mm;    // mismatch bits of the step at even positions
+    uint32_t copy;  // (lane & 7) * 4: this lane's copy inside a row (in ints)
     __device__ __forceinline__ PwE4 operator()(int g) const {
-        const uint32_t idx = (mm >> (8 * g)) & 0x55u;
-        const int4 *p = reinterpret_cast<const int4 *>(tbl + idx * 8);
-        const int4 d = p[0], s = p[1];
+        // row * 32 ints | copy: one shift + one 3-input logic op
+        const uint32_t at = (g == 0 ? ((mm << 5) & (0x55u << 5)) : ((mm >> (8 * g - 5)) & (0x55u << 5))) | copy;
+        const int4 d = *reinterpret_cast<const int4 *>(tbl + at);
+        const int4 s = *reinterpret_cast<const int4 *>(tbl + NWP_TBL * 32 + at);
         PwE4 e;
         e.ds[0] = d.x; e.ds[1] = d.y; e.ds[2] = d.z; e.ds[3] = d.w;
         e.sb[0] = s.x; e.sb[1] = s.y; e.sb[2] = s.z; e.sb[3] = s.w;
@@ -34,7 +41,7 @@ struct PwDevEW {
 
 template <int S>
 __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
-    __shared__ __align__(16) int tbl[NWP_TBL * 8];
+    __shared__ __align__(128) int tbl[2 * NWP_TBL * 32];
     __shared__ uint8_t sx_all[NWP_WARPS * 2][PW_MAX_X];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int hl = lane & 15, half = lane >> 4;
@@ -42,10 +49,10 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
     uint8_t *sx = sx_all[warp * 2 + half];
     const uint32_t r_begin = a.range[0], r_end = a.range[1];
     const PwK k = pw_consts(a.igap, a.egap);
-    for (int e = threadIdx.x; e < NWP_TBL; e += NWP_THREADS) {
-        const PwE4 v = pw_e4(k, (uint32_t)e);
+    for (int e = threadIdx.x; e < NWP_TBL * 8; e += NWP_THREADS) {
+        const PwE4 v = pw_e4(k, (uint32_t)(e >> 3));
 #pragma unroll
-        for (int c = 0; c < 4; c++) { tbl[e * 8 + c] = v.ds[c]; tbl[e * 8 + 4 + c] = v.sb[c]; }
+        for (int c = 0; c < 4; c++) { tbl[e * 4 + c] = v.ds[c]; tbl[NWP_TBL * 32 + e * 4 + c] = v.sb[c]; }
     }
     __syncthreads();
     unsigned long long my_cells = 0, my_pairs = 0;
@@ -123,13 +130,16 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
             const uint32_t d_ = ycols ^ (xi * 0x55555555u);                                        \
             PwDevEW ew;                                                                            \
             ew.tbl = tbl;                                                                          \
+            ew.copy = (uint32_t)(lane & 7) * 4u;                                                   \
             ew.mm = (d_ | (d_ >> 1));                                                              \
             pw_row<S>(L, PREV1, PREV2, in, out, i, j0, ew, k, X1, Y1, cl, owns_last);              \
         }                                                                                          \
     }
+        // always an even number of steps (a surplus step has no active lane): the register roles of the
+        // two row histories are then the same at every loop head and no row is ever copied
         for (int t = 0; t < steps; t += 2) {
             IMS_PW_STEP(t, L.r0, L.r1)
-            if (t + 1 < steps) IMS_PW_STEP(t + 1, L.r1, L.r0)
+            IMS_PW_STEP(t + 1, L.r1, L.r0)
         }
 #undef IMS_PW_STEP
         // reduction of the best border cell over the half warp ("last in row-major order" on ties)
