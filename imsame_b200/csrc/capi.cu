@@ -60,7 +60,8 @@ struct imsame_ctx {
     bool have_db = false;
 
     // tables + work buffers
-    uint16_t *d_nmin = nullptr, *d_lmin = nullptr, *d_imin = nullptr, *d_lut = nullptr;
+    uint16_t *d_nmin = nullptr, *d_lmin = nullptr, *d_imin = nullptr;
+    uint32_t *d_lut = nullptr;
     unsigned long long *hkeys = nullptr, *hvals = nullptr;
     uint32_t hcap = 0;
     PairRec *pairs = nullptr;
@@ -208,10 +209,10 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
         if ((rc = dev_alloc(ctx, &ctx->d_nmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_lmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_imin, 2 * IMSAME_MAX_READ_SIZE + 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_lut, EXT_LUT_SIZE))) return rc;
-        std::vector<uint16_t> lut(EXT_LUT_SIZE);
-        build_ext_lut(lut.data());
-        CK(cudaMemcpy(ctx->d_lut, lut.data(), EXT_LUT_SIZE * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        if ((rc = dev_alloc(ctx, &ctx->d_lut, 2 * EXT_LUT3_SIZE))) return rc;
+        std::vector<uint32_t> lut(2 * EXT_LUT3_SIZE);
+        build_ext_lut3(lut.data());
+        CK(cudaMemcpy(ctx->d_lut, lut.data(), 2 * EXT_LUT3_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     if (want_cap > ctx->hcap) {
         dev_free(ctx->hkeys); dev_free(ctx->hvals);
@@ -484,6 +485,7 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
     ctx->q_total = total;
     ctx->q_fixed = uniform_len(q->start_pos, nq, q->total_len);
     ctx->class_mask = class_mask_of(q->start_pos, nq, q->total_len, &ctx->q_maxlen);
+    if (ctx->q_maxlen > EXT_MAX_READ) return IMSAME_ELIMIT;  // walk state packs (score, step) in 15 + 16 bits
     ctx->q_start_host.resize((size_t)nq + 1);
     for (uint32_t r = 0; r < nq; r++) ctx->q_start_host[r] = (uint32_t)q->start_pos[r];
     ctx->q_start_host[nq] = total;
@@ -556,6 +558,7 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
     uint32_t mx = 0;
     (void)class_mask_of(db->start_pos, db->n_seqs, db->total_len, &mx);
     ctx->db_maxlen = mx;
+    if (mx > EXT_MAX_READ) return IMSAME_ELIMIT;
     std::vector<uint32_t> tmp;
     uint64_t r0 = 0, bi = 0;
     while (r0 < db->n_seqs) {

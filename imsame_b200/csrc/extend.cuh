@@ -159,15 +159,92 @@ IMS_HD int extend_hit_lut(const uint16_t *lut, const uint32_t *dpk, const uint32
 // that consumes one 32-base window (forward or backward) per call, four table steps with
 // no data-dependent branch, so that the 32 hits of a warp stay converged: every lane
 // executes the same window body until all walks of the warp are finished.
+//
+// Everything is 32-bit: a window is two 16-base halves cut out of three packed words with
+// funnel shifts, the 2-bit differences are reduced to one mismatch bit per base per half
+// (8 shift/logic pairs) and the walk table carries the score change of its 8 steps, so no
+// 64-bit arithmetic and no population count is left in the loop (the first version spent
+// 240 instructions per window, two thirds of them on 64-bit address/shift/compress work).
 namespace imsame {
 
+// Walk table of the scan kernel: one 64-bit entry per (entry score row, 8 mismatch bits).
+// The walk state is ONE word  run = (score << 15) | steps_done  and the running maximum of
+// the reference's `if (high <= score) { pos = cur; high = score; }` (:324,347) is ONE word
+// best = (high << 15) | (1-based step of its last occurrence): later steps have larger step
+// numbers, so "replace when >=" is a plain integer maximum of such keys.  Per 8 steps:
+//     best = max(best, run + entry.x);   run += entry.y;
+//   entry.x = (max prefix score relative to the entry score << 15) + step of its last occurrence
+//   entry.y = (score change << 15) + steps executed
+// When the score reaches 0 inside the 8 steps the walk ends (:318,340): entry.y then sets the
+// score to exactly 0 and counts only the executed steps, and row 0 is absorbing (entry.x very
+// negative, entry.y = 0), so a finished walk needs no predicate.  Row 9 = "9 or more".
+// Matches are not counted: every step is +-1, so matches = (steps + score_end - score_start) / 2.
+constexpr int EXT_ROWS3 = 10;
+constexpr int EXT_LUT3_SIZE = EXT_ROWS3 * 256;  // entries of two uint32
+constexpr int EXT_SC_SHIFT = 15;                // reads of up to 32767 bases
+constexpr uint32_t EXT_POS_MASK = (1u << EXT_SC_SHIFT) - 1u;
+constexpr uint32_t EXT_MAX_READ = EXT_POS_MASK;
+
+inline void build_ext_lut3(uint32_t *lut /* 2 * EXT_LUT3_SIZE */) {
+    for (int row = 0; row < EXT_ROWS3; row++)
+        for (uint32_t m = 0; m < 256; m++) {
+            int32_t x, y;
+            if (row == 0) {
+                x = -(1 << 30);
+                y = 0;
+            } else {
+                int run = 0, rmax = -100, amax = 0, steps = 0;
+                bool term = false;
+                for (int t = 0; t < 8; t++) {
+                    run += ((m >> t) & 1) ? -1 : 1;
+                    steps = t + 1;
+                    if (run >= rmax) { rmax = run; amax = t + 1; }
+                    if (row < 9 && row + run <= 0) { term = true; break; }
+                }
+                x = rmax * (1 << EXT_SC_SHIFT) + amax;
+                y = (term ? -row : run) * (1 << EXT_SC_SHIFT) + steps;
+            }
+            lut[2 * (row * 256 + m)] = (uint32_t)x;
+            lut[2 * (row * 256 + m) + 1] = (uint32_t)y;
+        }
+}
+
+IMS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+
+// even bits of x -> low 16 bits
+IMS_HD uint32_t compress_even16(uint32_t x) {
+    x = (x | (x >> 1)) & 0x33333333u;
+    x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0x0000FFFFu;
+}
+
+// mismatch bits (bit t <=> bases differ) of the 32-base windows starting at base i of a and j of b
+IMS_HD uint32_t window_mismatch(const uint32_t *apk, uint32_t i, const uint32_t *bpk, uint32_t j) {
+    const uint32_t wa = i >> 4, wb = j >> 4;
+    const unsigned sa = (i & 15u) * 2u, sb = (j & 15u) * 2u;
+    const uint32_t a0 = apk[wa], a1 = apk[wa + 1], a2 = apk[wa + 2];
+    const uint32_t b0 = bpk[wb], b1 = bpk[wb + 1], b2 = bpk[wb + 2];
+    uint32_t d0 = funnel_r(a0, a1, sa) ^ funnel_r(b0, b1, sb);
+    uint32_t d1 = funnel_r(a1, a2, sa) ^ funnel_r(b1, b2, sb);
+    d0 = (d0 | (d0 >> 1)) & 0x55555555u;
+    d1 = (d1 | (d1 >> 1)) & 0x55555555u;
+    return compress_even16(d0) | (compress_even16(d1) << 16);
+}
+
 struct ExtState {
-    int phase;  // 0 forward, 1 backward, 2 done
-    int t;      // steps already taken in this phase
-    int sc;     // current score (units of POINT)
-    int hr, fe; // forward: high_right, last step that reached it (-1: none)   (:324-327)
-    int hl, be; // backward: high_left, last step that reached it (-1: none)   (:347-351)
-    int idn;    // idents
+    int phase;       // 0 forward, 1 backward, 2 done
+    int t;           // steps already taken in this phase (multiple of 32)
+    int run;         // (score << 15) | steps done in this phase          (units of POINT)
+    int best;        // (high << 15) | 1-based step that last reached it  (:324-327, :347-351)
+    int pos_f;       // forward result: 1-based step of high_right (fe + 1)
+    int idn2;        // 2 * matches walked so far (both phases, without the seed)
     int fmax, bmax;  // steps available inside both reads
 };
 
@@ -177,51 +254,153 @@ IMS_HD void ext_init(ExtState &s, uint32_t p, uint32_t e, uint32_t xs, uint32_t 
     s.fmax = fq < fd ? fq : fd;
     s.bmax = bq < bd ? bq : bd;
     s.t = 0;
-    s.sc = K; s.hr = K; s.fe = -1; s.hl = K; s.be = -1; s.idn = K;
+    s.run = K << EXT_SC_SHIFT;   // score = 12 (48 / POINT), :300
+    s.best = K << EXT_SC_SHIFT;  // high_right = 12, no step yet
+    s.pos_f = 0;
+    s.idn2 = 0;
     s.phase = s.fmax > 0 ? 0 : (s.bmax > 0 ? 1 : 2);
 }
 
-IMS_HD void ext_window(ExtState &s, const uint16_t *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
+#if defined(__CUDA_ARCH__)
+#define IMS_LUT3(lut, i) (reinterpret_cast<const uint2 *>(lut)[i])
+#else
+struct ExtPair { uint32_t x, y; };
+#define IMS_LUT3(lut, i) (ExtPair{(lut)[2 * (i)], (lut)[2 * (i) + 1]})
+#endif
+
+IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
                        uint32_t e) {
     const bool bwd = s.phase == 1;
     const int maxs = bwd ? s.bmax : s.fmax;
     const int rem = maxs - s.t;
-    const int64_t sd = bwd ? (int64_t)p - (K + 1) - s.t - 31 : (int64_t)p + s.t;
-    const int64_t sq = bwd ? (int64_t)e - K - s.t - 31 : (int64_t)e + 1 + s.t;
-    const uint64_t a = sd >= 0 ? fetch32(dpk, (uint64_t)sd) : (fetch32(dpk, 0) << (2 * (int)(-sd)));
-    const uint64_t b = sq >= 0 ? fetch32(qpk, (uint64_t)sq) : (fetch32(qpk, 0) << (2 * (int)(-sq)));
-    uint32_t mm = mismatch32(a, b);
+    // first base of the window in both sequences
+    const int sd = bwd ? (int)p - (K + 1) - s.t - 31 : (int)p + s.t;
+    const int sq = bwd ? (int)e - K - s.t - 31 : (int)e + 1 + s.t;
+    uint32_t mm;
+    if (sd >= 0 && sq >= 0) {
+        mm = window_mismatch(dpk, (uint32_t)sd, qpk, (uint32_t)sq);
+    } else {
+        // a backward window that starts before base 0 of an array (first read only)
+        const uint64_t a = sd >= 0 ? fetch32(dpk, (uint64_t)sd) : (fetch32(dpk, 0) << (2 * (-sd)));
+        const uint64_t b = sq >= 0 ? fetch32(qpk, (uint64_t)sq) : (fetch32(qpk, 0) << (2 * (-sq)));
+        mm = mismatch32(a, b);
+    }
     if (bwd) mm = brev32(mm);                    // step u <-> bit u in both directions
-    if (rem < 32) mm |= 0xFFFFFFFFu << rem;      // steps past the read end: mismatches (never counted)
-    int sc = s.sc, hi = bwd ? s.hl : s.hr, last = bwd ? s.be : s.fe, idn = s.idn;
-    bool term = false;
+    if (rem < 32) mm |= 0xFFFFFFFFu << rem;      // steps past the read end: mismatches (change neither maximum nor matches)
+    int run = s.run, best = s.best;
+    const int sc0 = run >> EXT_SC_SHIFT;
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
         const uint32_t m = (mm >> c) & 0xFFu;
-        int row = sc < EXT_LUT_ROWS ? sc : EXT_LUT_ROWS;
-        row = row < 1 ? 1 : row;
-        const uint32_t ent = lut[(row - 1) * 256 + m];
-        if (!term) {
-            idn += (int)(ent & 15u);
-            const int cand = sc + (int)((ent >> 5) & 15u) - 1;
-            if (cand >= hi) { hi = cand; last = s.t + c + (int)((ent >> 9) & 15u) - 1; }
-            sc += 8 - 2 * popc32(m);
-            term = (ent & 16u) != 0;
-        }
+        uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
+        row = row < 9u ? row : 9u;
+        const auto ent = IMS_LUT3(lut, row * 256u + m);
+        const int key = run + (int)ent.x;
+        best = key > best ? key : best;
+        run += (int)ent.y;
     }
-    s.idn = idn;
-    const bool phase_over = term || rem <= 32;
-    if (!bwd) {
-        s.hr = hi; s.fe = last;
-        if (phase_over) { s.phase = s.bmax > 0 ? 1 : 2; s.t = 0; s.sc = hi; }  // backward restarts from high_right (:339)
-        else { s.t += 32; s.sc = sc; }
+    const int sc1 = run >> EXT_SC_SHIFT;
+    // +-1 per step: 2 * matches = steps + score change (also true for the padded steps)
+    s.idn2 += ((run - s.run) & (int)EXT_POS_MASK) + sc1 - sc0;
+    const bool phase_over = sc1 == 0 || rem <= 32;
+    if (!phase_over) {
+        s.t += 32; s.run = run; s.best = best;
+    } else if (!bwd) {
+        s.pos_f = best & (int)EXT_POS_MASK;
+        s.phase = s.bmax > 0 ? 1 : 2;
+        s.t = 0;
+        s.run = best & ~(int)EXT_POS_MASK;  // backward restarts from high_right (:339), step count 0
+        s.best = K << EXT_SC_SHIFT;         // high_left = 12 (:303)
     } else {
-        s.hl = hi; s.be = last;
-        if (phase_over) s.phase = 2;
-        else { s.t += 32; s.sc = sc; }
+        s.best = best;
+        s.phase = 2;
     }
 }
 
-IMS_HD int ext_result(const ExtState &s) { return 2 * s.idn - (s.fe + K + s.be + 1); }
+// one table step (8 bases) of a walk
+IMS_HD void ext_step(const uint32_t *lut, uint32_t m8, int &run, int &best) {
+    uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
+    row = row < 9u ? row : 9u;
+    const auto ent = IMS_LUT3(lut, row * 256u + m8);
+    const int key = run + (int)ent.x;
+    best = key > best ? key : best;
+    run += (int)ent.y;
+}
+
+// Mismatch bits of the first forward and the first backward window of a hit (step u <-> bit u in
+// both); steps past the read ends are mismatches.  A phase with no room at all (fmax or bmax <= 0)
+// is an all-mismatch window: walking it changes no match count, and no maximum either in the forward
+// phase (the first step already scores below high_right = the start score); the backward phase starts
+// ABOVE high_left = 12 (:303,339), so there a walk without room is discarded instead (ext_first2).
+IMS_HD void ext_first_masks(const ExtState &s, const uint32_t *dpk, const uint32_t *qpk, uint32_t p, uint32_t e,
+                            uint32_t &mf, uint32_t &mb) {
+    mf = window_mismatch(dpk, p, qpk, e + 1);
+    const int sd = (int)p - (K + 1) - 31, sq = (int)e - K - 31;
+    if (sd >= 0 && sq >= 0) {
+        mb = window_mismatch(dpk, (uint32_t)sd, qpk, (uint32_t)sq);
+    } else {  // the window starts before base 0 of an array (first read only)
+        const uint64_t a = sd >= 0 ? fetch32(dpk, (uint64_t)sd) : (fetch32(dpk, 0) << (2 * (-sd)));
+        const uint64_t b = sq >= 0 ? fetch32(qpk, (uint64_t)sq) : (fetch32(qpk, 0) << (2 * (-sq)));
+        mb = mismatch32(a, b);
+    }
+    mb = brev32(mb);
+    const int fm = s.fmax < 0 ? 0 : s.fmax, bm = s.bmax < 0 ? 0 : s.bmax;
+    if (fm < 32) mf |= 0xFFFFFFFFu << fm;
+    if (bm < 32) mb |= 0xFFFFFFFFu << bm;
+}
+
+// First forward and first backward window of TWO independent hits, the two dependent chains of
+// table lookups interleaved (the scan kernel is bound by the latency of those chains, not by
+// instruction issue).  On return each state is done (phase 2) or parked-ready: phase 0 / 1 with
+// t = 32, to be continued by ext_window.
+IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t mfa, uint32_t mba, uint32_t mfb,
+                       uint32_t mbb) {
+    const int k0 = K << EXT_SC_SHIFT;
+    int ra = k0, ba = k0, rb = k0, bb = k0;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+        ext_step(lut, (mfa >> c) & 0xFFu, ra, ba);
+        ext_step(lut, (mfb >> c) & 0xFFu, rb, bb);
+    }
+    const int sca = ra >> EXT_SC_SHIFT, scb = rb >> EXT_SC_SHIFT;
+    const bool fa_over = sca == 0 || sa.fmax <= 32, fb_over = scb == 0 || sb.fmax <= 32;
+    // backward restarts from high_right (:339) with high_left = 12 (:303)
+    int ra2 = ba & ~(int)EXT_POS_MASK, ba2 = k0, rb2 = bb & ~(int)EXT_POS_MASK, bb2 = k0;
+    const int hra = ra2 >> EXT_SC_SHIFT, hrb = rb2 >> EXT_SC_SHIFT;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+        ext_step(lut, (mba >> c) & 0xFFu, ra2, ba2);
+        ext_step(lut, (mbb >> c) & 0xFFu, rb2, bb2);
+    }
+    if (sa.bmax <= 0) { ra2 = hra << EXT_SC_SHIFT; ba2 = k0; }  // no room: no backward step at all
+    if (sb.bmax <= 0) { rb2 = hrb << EXT_SC_SHIFT; bb2 = k0; }
+    const int sca2 = ra2 >> EXT_SC_SHIFT, scb2 = rb2 >> EXT_SC_SHIFT;
+    // +-1 per step: 2 * matches = steps + score change
+    sa.idn2 = (ra & (int)EXT_POS_MASK) + sca - K;
+    sb.idn2 = (rb & (int)EXT_POS_MASK) + scb - K;
+    if (fa_over) {
+        sa.pos_f = ba & (int)EXT_POS_MASK;
+        sa.idn2 += (ra2 & (int)EXT_POS_MASK) + sca2 - hra;
+        sa.run = ra2; sa.best = ba2; sa.t = 32;
+        sa.phase = (sca2 == 0 || sa.bmax <= 32) ? 2 : 1;
+    } else {
+        sa.run = ra; sa.best = ba; sa.t = 32; sa.phase = 0;
+    }
+    if (fb_over) {
+        sb.pos_f = bb & (int)EXT_POS_MASK;
+        sb.idn2 += (rb2 & (int)EXT_POS_MASK) + scb2 - hrb;
+        sb.run = rb2; sb.best = bb2; sb.t = 32;
+        sb.phase = (scb2 == 0 || sb.bmax <= 32) ? 2 : 1;
+    } else {
+        sb.run = rb; sb.best = bb; sb.t = 32; sb.phase = 0;
+    }
+}
+
+// n = 2 * idents - t_len, t_len = fe + K + be + 1 (:359) with fe = pos_f - 1, be = pos_b - 1
+// (after the last window `best` is the backward maximum, or still "no step" when there was no backward walk)
+IMS_HD int ext_result(const ExtState &s) {
+    const int pos_b = s.best & (int)EXT_POS_MASK;
+    return 2 * K + s.idn2 - (s.pos_f + K + pos_b - 1);
+}
 
 }  // namespace imsame

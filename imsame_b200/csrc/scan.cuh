@@ -27,7 +27,7 @@ struct ScanArgs {
     const uint32_t *brk;   // database word breaks (segment-local), ascending
     uint32_t n_brk;
     const uint16_t *nmin;  // e-value threshold table by ylen
-    const uint16_t *lut;   // extension walk table (extend.cuh), EXT_LUT_SIZE entries
+    const uint32_t *lut;   // extension walk table (extend.cuh: build_ext_lut3), 2 * EXT_LUT3_SIZE words
     uint64_t seg_pos_base; // global index of the segment's first base
     unsigned long long *hkeys, *hvals;  // pair table (open addressing)
     uint32_t hmask;
@@ -76,25 +76,40 @@ __device__ __forceinline__ bool word_broken(const ScanArgs &a, uint32_t q) {
     return lo < a.n_brk && a.brk[lo] <= q;
 }
 
-// A walk that is still running after SCAN_FAST_WINDOWS windows (a true overlap: up to a whole
-// read in both directions) is parked in a per-warp queue; parked walks are finished 32 at a time,
+// pos / fixed_len without a division: q = mulhi(pos, floor(2^32 / L)) is the quotient or one less
+// (pos < 2^32), one conditional increment makes it exact.  inv = 0: ragged reads, block lookup.
+__device__ __forceinline__ uint32_t find_read_inv(const SeqMap &m, uint32_t inv, uint32_t pos) {
+    if (!inv) return find_read(m, pos);
+    uint32_t q = __umulhi(pos, inv);
+    if (pos - q * m.fixed_len >= m.fixed_len) q++;
+    return q;
+}
+__device__ __forceinline__ uint32_t inv_of(uint32_t fixed_len) {
+    return fixed_len >= 2 ? (uint32_t)((1ull << 32) / fixed_len) : 0u;
+}
+
+// A walk that is still running after its first window in either direction (a true overlap: up to
+// a whole read both ways) is parked in a per-warp queue; parked walks are finished 32 at a time,
 // so the many short walks of random hits never wait for the few long ones.
-constexpr int SCAN_FAST_WINDOWS = 3;
 constexpr int SCAN_QCAP = 64;
 
 struct ParkedWalk {
-    uint32_t p, e, ys, yend;
+    uint32_t p, e;
     ExtState st;
 };
 
-__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t p, uint32_t e, uint32_t ys, uint32_t yend,
+__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, uint32_t p, uint32_t e,
                                            const ExtState &st, unsigned long long &c_pass,
                                            unsigned long long &c_anom) {
     const int n = ext_result(st);
     if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
+    // fixed-length queries: one threshold; otherwise the read has to be looked up first
+    if (n >= 0 && a.q.fixed_len && n < (int)a.nmin[a.q.fixed_len]) return;
+    const uint32_t r = find_read_inv(a.q, q_inv, e);
+    const uint32_t ys = read_start(a.q, r);
+    const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
     if (n < 0 || n >= (int)a.nmin[yend - ys]) {
         c_pass++;
-        const uint32_t r = find_read(a.q, e);
         const uint64_t key = make_key(e - ys + 1, a.seg_pos_base + p);
         if (key < a.best[r]) {
             const uint32_t s = find_read(a.db, p - 1);
@@ -104,15 +119,16 @@ __device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t p, uint32
 }
 
 // finish `count` (<= 32) parked walks, one per lane
-__device__ __forceinline__ void drain_parked(const ScanArgs &a, const uint16_t *s_lut, const ParkedWalk *q, int count,
-                                             int lane, unsigned long long &c_pass, unsigned long long &c_anom) {
+__device__ __forceinline__ void drain_parked(const ScanArgs &a, uint32_t q_inv, const uint32_t *s_lut,
+                                             const ParkedWalk *q, int count, int lane, unsigned long long &c_pass,
+                                             unsigned long long &c_anom) {
     ParkedWalk w;
     w.st.phase = 2;
-    w.p = w.e = w.ys = w.yend = 0;
+    w.p = w.e = 0;
     if (lane < count) w = q[lane];
     while (__any_sync(0xffffffffu, w.st.phase < 2))
         if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e);
-    if (lane < count) finish_hit(a, w.p, w.e, w.ys, w.yend, w.st, c_pass, c_anom);
+    if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.st, c_pass, c_anom);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
@@ -121,10 +137,11 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
     __shared__ uint32_t s_xs[SCAN_WARPS][32];
     __shared__ uint32_t s_xe[SCAN_WARPS][32];
-    __shared__ uint16_t s_lut[EXT_LUT_SIZE];
-    for (int i = threadIdx.x; i < EXT_LUT_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
+    __shared__ __align__(8) uint32_t s_lut[2 * EXT_LUT3_SIZE];
+    for (int i = threadIdx.x; i < 2 * EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t q_inv = inv_of(a.q.fixed_len), db_inv = inv_of(a.db.fixed_len);
     const uint32_t n_tiles = (a.db.total + 31) / 32;
     const uint32_t gw = blockIdx.x * SCAN_WARPS + warp, nw = gridDim.x * SCAN_WARPS;
     unsigned long long c_words = 0, c_hits = 0, c_pass = 0, c_anom = 0;
@@ -135,7 +152,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
         const uint32_t q = tile * 32 + lane;  // index of the word's last base
         uint32_t cnt = 0, b0 = 0, xs = 0, xe = 0;
         if (q < a.db.total) {
-            const uint32_t s = find_read(a.db, q);
+            const uint32_t s = find_read_inv(a.db, db_inv, q);
             xs = read_start(a.db, s);
             xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
             if (q >= xs + (K - 1) && !word_broken(a, q)) {
@@ -158,48 +175,60 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
         s_xs[warp][lane] = xs;
         s_xe[warp][lane] = xe;
         __syncwarp();
-        for (uint32_t h0 = 0; h0 < total; h0 += 32) {
-            const uint32_t h = h0 + lane;
-            const bool live = h < total;
-            uint32_t e = 0, p = 0, r = 0, ys = 0, yend = 0;
-            ExtState st;
-            st.phase = 2;
-            if (live) {
-                // owner = last lane whose exclusive prefix is <= h
-                int o = 0;
+        // 64 hits per iteration, two per lane: their loads are issued together and their two chains of
+        // table lookups interleave (ext_first2); what is not finished after one window each way
+        // (long walks = true overlaps, ~1 in 4) is parked and continued 32 at a time
+        for (uint32_t h0 = 0; h0 < total; h0 += 64) {
+            const uint32_t ha = h0 + lane, hb = h0 + 32 + lane;
+            const bool la = ha < total, lb = hb < total;
+            // owner = last lane whose exclusive prefix is <= h (dead slots search for the last hit)
+            const uint32_t sa_h = la ? ha : total - 1, sb_h = lb ? hb : total - 1;
+            int oa = 0, ob = 0;
 #pragma unroll
-                for (int step = 16; step >= 1; step >>= 1)
-                    if (s_excl[warp][o + step] <= h) o += step;
-                e = a.qpos[s_b0[warp][o] + (h - s_excl[warp][o])];
-                p = tile * 32 + o + 1;  // llpos.pos: index after the word
-                r = find_read(a.q, e);
-                ys = read_start(a.q, r);
-                yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
-                ext_init(st, p, e, s_xs[warp][o], s_xe[warp][o], ys, yend);
-                c_hits++;
+            for (int step = 16; step >= 1; step >>= 1) {
+                if (s_excl[warp][oa + step] <= sa_h) oa += step;
+                if (s_excl[warp][ob + step] <= sb_h) ob += step;
             }
-            // all walks of the warp advance one 32-base window per iteration (extend.cuh)
-            for (int it = 0; it < SCAN_FAST_WINDOWS && __any_sync(0xffffffffu, st.phase < 2); it++)
-                if (st.phase < 2) ext_window(st, s_lut, a.db.pk, a.q.pk, p, e);
-            const bool unfinished = st.phase < 2;
-            if (live && !unfinished) finish_hit(a, p, e, ys, yend, st, c_pass, c_anom);
-            const unsigned park = __ballot_sync(0xffffffffu, unfinished);
-            if (park) {
-                if (unfinished) {
-                    ParkedWalk &w = s_park[warp][n_parked + __popc(park & ((1u << lane) - 1u))];
-                    w.p = p; w.e = e; w.ys = ys; w.yend = yend; w.st = st;
-                }
-                n_parked += __popc(park);
-                __syncwarp();
-                if (n_parked >= 32) {
-                    n_parked -= 32;
-                    drain_parked(a, s_lut, &s_park[warp][n_parked], 32, lane, c_pass, c_anom);
+            const uint32_t ea = a.qpos[s_b0[warp][oa] + (sa_h - s_excl[warp][oa])];
+            const uint32_t eb = a.qpos[s_b0[warp][ob] + (sb_h - s_excl[warp][ob])];
+            const uint32_t pa = tile * 32 + oa + 1, pb = tile * 32 + ob + 1;  // llpos.pos: index after the word
+            ExtState sta, stb;
+            {
+                const uint32_t ra = find_read_inv(a.q, q_inv, ea), rb = find_read_inv(a.q, q_inv, eb);
+                const uint32_t ysa = read_start(a.q, ra), ysb = read_start(a.q, rb);
+                const uint32_t yea = a.q.fixed_len ? ysa + a.q.fixed_len : a.q.start[ra + 1];
+                const uint32_t yeb = a.q.fixed_len ? ysb + a.q.fixed_len : a.q.start[rb + 1];
+                ext_init(sta, pa, ea, s_xs[warp][oa], s_xe[warp][oa], ysa, yea);
+                ext_init(stb, pb, eb, s_xs[warp][ob], s_xe[warp][ob], ysb, yeb);
+            }
+            uint32_t mfa, mba, mfb, mbb;
+            ext_first_masks(sta, a.db.pk, a.q.pk, pa, ea, mfa, mba);
+            ext_first_masks(stb, a.db.pk, a.q.pk, pb, eb, mfb, mbb);
+            ext_first2(sta, stb, s_lut, mfa, mba, mfb, mbb);
+            c_hits += (la ? 1 : 0) + (lb ? 1 : 0);
+            if (la && sta.phase == 2) finish_hit(a, q_inv, pa, ea, sta, c_pass, c_anom);
+            if (lb && stb.phase == 2) finish_hit(a, q_inv, pb, eb, stb, c_pass, c_anom);
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const bool unfinished = half ? (lb && stb.phase < 2) : (la && sta.phase < 2);
+                const unsigned park = __ballot_sync(0xffffffffu, unfinished);
+                if (park) {
+                    if (unfinished) {
+                        ParkedWalk &w = s_park[warp][n_parked + __popc(park & ((1u << lane) - 1u))];
+                        w.p = half ? pb : pa; w.e = half ? eb : ea; w.st = half ? stb : sta;
+                    }
+                    n_parked += __popc(park);
                     __syncwarp();
+                    if (n_parked >= 32) {
+                        n_parked -= 32;
+                        drain_parked(a, q_inv, s_lut, &s_park[warp][n_parked], 32, lane, c_pass, c_anom);
+                        __syncwarp();
+                    }
                 }
             }
         }
     }
-    if (n_parked) drain_parked(a, s_lut, &s_park[warp][0], n_parked, lane, c_pass, c_anom);
+    if (n_parked) drain_parked(a, q_inv, s_lut, &s_park[warp][0], n_parked, lane, c_pass, c_anom);
     // counters: warp-reduce then one atomic per warp
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {

@@ -56,6 +56,13 @@ int main(int argc, char **argv) {
     }
     std::vector<uint16_t> lut(EXT_LUT_SIZE);
     build_ext_lut(lut.data());
+    std::vector<uint32_t> lut2(2 * EXT_LUT3_SIZE);
+    build_ext_lut3(lut2.data());
+    // window_mismatch (32-bit halves) against the 64-bit form
+    for (size_t i = 0; i + 40 < D.size() && i + 40 < Q.size(); i += 3) {
+        size_t j = (i * 7 + 5) % (Q.size() - 40);
+        if (window_mismatch(dpk.data(), (uint32_t)i, qpk.data(), (uint32_t)j) != mismatch32(fetch32(dpk.data(), i), fetch32(qpk.data(), j))) { printf("window_mismatch differs\n"); return 1; }
+    }
     long hits = 0, bad = 0;
     for (size_t s = 0; s + 1 < ds.size(); s++)
         for (uint64_t x = ds[s] + 11; x < ds[s + 1]; x++) {
@@ -71,8 +78,25 @@ int main(int argc, char **argv) {
                 int got2 = extend_hit_lut(lut.data(), dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
                 ExtState st;
                 ext_init(st, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
-                while (st.phase < 2) ext_window(st, lut.data(), dpk.data(), qpk.data(), p, e);
+                while (st.phase < 2) ext_window(st, lut2.data(), dpk.data(), qpk.data(), p, e);
                 if (want != ext_result(st)) { if (bad++ < 10) printf("WINDOW MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, ext_result(st)); }
+                {   // the scan kernel's form: first windows of two hits at once, the rest window by window
+                    static ExtState prev; static uint32_t prev_p = 0, prev_e = 0; static long prev_want = 0; static bool have_prev = false;
+                    ExtState cur;
+                    ext_init(cur, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                    if (have_prev) {
+                        uint32_t mfa, mba, mfb, mbb;
+                        ExtState A = prev, Bst = cur;
+                        ext_first_masks(A, dpk.data(), qpk.data(), prev_p, prev_e, mfa, mba);
+                        ext_first_masks(Bst, dpk.data(), qpk.data(), p, e, mfb, mbb);
+                        ext_first2(A, Bst, lut2.data(), mfa, mba, mfb, mbb);
+                        while (A.phase < 2) ext_window(A, lut2.data(), dpk.data(), qpk.data(), prev_p, prev_e);
+                        while (Bst.phase < 2) ext_window(Bst, lut2.data(), dpk.data(), qpk.data(), p, e);
+                        if (prev_want != ext_result(A)) { if (bad++ < 10) printf("FIRST2(A) MISMATCH p=%u e=%u want=%ld got=%d\n", prev_p, prev_e, prev_want, ext_result(A)); }
+                        if (want != ext_result(Bst)) { if (bad++ < 10) printf("FIRST2(B) MISMATCH p=%u e=%u want=%ld got=%d\n", p, e, (long)want, ext_result(Bst)); }
+                    }
+                    prev = cur; prev_p = p; prev_e = e; prev_want = (long)want; have_prev = true;
+                }
                 hits++;
                 if (want != got2) { if (bad++ < 10) printf("LUT MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got2); }
                 if (want != got) { if (bad++ < 10) printf("MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got); }
