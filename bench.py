@@ -28,7 +28,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-OPS_PER_CELL = 24  # INT32 ops per NW cell
+# INT32 lane-operations one NW cell needs:
+#   generic kernel (nw_core.cuh): the SURVEY.md 8(d) accounting, 24 ops per cell
+#   packed-word kernel (nwp_core.cuh): 16 -- 2 compares, 4 selects (2 of them fused with a logic op /
+#   add as predicated instructions), one 3-input maximum (2 instructions), 3 logic ops, 5 adds
+#   (one fused into the maximum); = the instructions per cell in the SASS of the unrolled row body
+OPS_PER_CELL_GENERIC = 24
+OPS_PER_CELL_PACKED = 16
 
 
 def parse():
@@ -321,12 +327,15 @@ def run_ours(args):
             if it > 0:
                 t_e2e.append(dt)
                 h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+                e2e_phases = {k: round(float(st[k]), 2) for k in ("ms_h2d", "ms_pack_query", "ms_k1", "ms_pack_db", "ms_k2",
+                                                                  "ms_k2b", "ms_k3", "ms_select", "ms_d2h", "ms_total")}
         te = torch.tensor([sum(t_e2e) / len(t_e2e)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * nq / float(te.item()), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3,
-               "what": "imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records"}
+               "what": "imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records",
+               "device_phases_ms": e2e_phases}
 
     if rank == 0:
         peaks, which = measured_peaks()
@@ -334,8 +343,13 @@ def run_ours(args):
         ms_step = ms_total / args.steps
         cells_all, ms_k3_max, ms_k2_max = float(agg[0].item()), float(agg_max[1].item()), float(agg_max[2].item())
         gcups = cells_all / world / (ms_k3_max * 1e-3) / 1e9 if ms_k3_max > 0 else 0.0   # per GPU
-        int_peak = ipk.get("imnmx") or ipk.get("iadd") or 0.0
-        achieved = gcups * OPS_PER_CELL
+        packed = all(s.get("k3_packed_launches", 0) == s.get("k3_launches", -1) for s in stats_steps)
+        ops_per_cell = OPS_PER_CELL_PACKED if packed else OPS_PER_CELL_GENERIC
+        # INT32 peak = the measured full-chip rate of independent 32-bit adds (ptxas spreads them over the
+        # ALU and the FMA pipe: 2 x 64 lanes/clk/SM); the ALU pipe alone (compare/select/min/max/logic) is half
+        int_peak = ipk.get("iadd") or 0.0
+        alu_peak = ipk.get("imnmx") or 0.0
+        achieved = gcups * ops_per_cell
         # K2 algorithmic bytes: Nd/4 + 8 per db word + 4 per hit + 16 per passing hit
         k2_bytes = nd * L / 4 + 8 * float(agg[5].item()) / world + 4 * float(agg[3].item()) / world + 16 * float(agg[6].item()) / world
         k2_gbs = k2_bytes / (ms_k2_max * 1e-3) / 1e9 if ms_k2_max > 0 else 0.0
@@ -355,11 +369,21 @@ def run_ours(args):
             "work": {"hits": float(agg[3].item()), "evalue_pass": float(agg[6].item()), "nw_pairs": float(agg[4].item()),
                      "cells": cells_all, "ms_k2": ms_k2_max, "ms_k3": ms_k3_max,
                      "ms_other": max(0.0, ms_step - ms_k2_max - ms_k3_max)},
-            "roofline": {"kernel": "nw_kernel (K3, per-pair NW wavefront)", "bound": "int32-alu",
+            "roofline": {"kernel": ("nwp_kernel (K3p, packed-word NW wavefront, 16 lanes per pair)" if packed
+                                    else "nw_kernel (K3, per-pair NW wavefront)"),
+                         "bound": "int32-issue",
                          "achieved": achieved, "peak": int_peak, "unit": "Gop/s",
-                         "frac": (achieved / int_peak) if int_peak else None, "traffic": None,
-                         "ops_per_cell": OPS_PER_CELL, "gcups": gcups,
-                         "peak_source": "tools/int_peak.cu run on this GPU just now (VIMNMX lane-op rate, ALU pipe)",
+                         "frac": (achieved / int_peak) if int_peak else None,
+                         "traffic": None,
+                         "traffic_note": "register/shared-memory resident: ncu dram bytes per launch are ~1e-4 of the kernel's "
+                                         "integer work (profiles/r01_ncu_nwp_v2_metrics.txt), HBM is not a bound",
+                         "ops_per_cell": ops_per_cell, "gcups": gcups,
+                         "gcups_roofline": (int_peak / ops_per_cell) if ops_per_cell else None,
+                         "frac_survey24": (gcups * OPS_PER_CELL_GENERIC / int_peak) if int_peak else None,
+                         "alu_pipe_peak": alu_peak,
+                         "frac_of_alu_pipe_at_24": (gcups * OPS_PER_CELL_GENERIC / alu_peak) if alu_peak else None,
+                         "peak_source": "tools/int_peak.cu run on this GPU just now: `iadd` = independent 32-bit adds over both "
+                                        "integer pipes (128 lanes/clk/SM); MEASURED_PEAKS.json has no INT32 figure",
                          "int_peak_table": ipk},
             "roofline_k2": {"kernel": "scan_kernel (K2, db scan + extension)", "bound": "hbm", "achieved": k2_gbs,
                             "peak": peaks.get("hbm_gbs"), "unit": "GB/s",

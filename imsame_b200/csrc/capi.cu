@@ -95,7 +95,7 @@ struct imsame_ctx {
     struct Span { int ph; cudaEvent_t a, b; };
     std::vector<Span> spans;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;
-    uint32_t launches = 0, k2_launches = 0, k3_launches = 0;
+    uint32_t launches = 0, k2_launches = 0, k3_launches = 0, k3_packed = 0;
 };
 
 namespace {
@@ -135,7 +135,7 @@ void reset_timing(imsame_ctx *ctx) {
     ctx->ev_used = 0;
     ctx->spans.clear();
     ctx->h2d_bytes = ctx->d2h_bytes = 0;
-    ctx->launches = ctx->k2_launches = ctx->k3_launches = 0;
+    ctx->launches = ctx->k2_launches = ctx->k3_launches = ctx->k3_packed = 0;
 }
 
 template <typename T>
@@ -289,6 +289,7 @@ int launch_nwp(imsame_ctx *ctx, NwArgs a) {
     nwp_kernel<2 * C><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     ctx->k3_launches++;
+    ctx->k3_packed++;
     CK(cudaGetLastError());
     return IMSAME_OK;
 }
@@ -381,6 +382,7 @@ void fill_stats(imsame_ctx *ctx, imsame_stats *st, const unsigned long long *cnt
     st->ms_h2d = acc[PH_H2D]; st->ms_d2h = acc[PH_D2H]; st->ms_total = total;
     st->h2d_bytes = ctx->h2d_bytes; st->d2h_bytes = ctx->d2h_bytes;
     st->k2_launches = ctx->k2_launches; st->k3_launches = ctx->k3_launches; st->total_launches = ctx->launches;
+    st->k3_packed_launches = ctx->k3_packed;
     st->n_query_kmers = ctx->n_qwords;
     if (cnt) {
         st->n_db_kmers = cnt[0]; st->n_hits = cnt[1]; st->n_evalue_pass = cnt[2];

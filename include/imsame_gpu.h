@@ -91,7 +91,7 @@ typedef struct imsame_stats {
     float ms_h2d, ms_d2h, ms_total;
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t k2_launches, k3_launches, total_launches;
-    uint32_t reserved;
+    uint32_t k3_packed_launches; /* of k3_launches: packed-word kernel (imsame_gpu_set_nw_mode) */
 } imsame_stats;
 
 typedef struct imsame_ctx imsame_ctx;
