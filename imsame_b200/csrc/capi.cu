@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -89,6 +90,11 @@ struct imsame_ctx {
     int nw_mode = 0;  // 0: packed-word kernel where pw_eligible() holds, 1: generic kernel only
     int scan_grid = 0;
 
+    // device blocks released by free_query / free_db, reused by the next set_query / set_db
+    // (cudaFree + cudaMalloc of the ~3 GB of a cfg2 call cost several hundred ms per call)
+    struct Block { void *p; size_t bytes; };
+    std::vector<Block> live_blocks, free_blocks;
+
     // phase timing
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
@@ -149,13 +155,62 @@ void dev_free(T *&p) {
     p = nullptr;
 }
 
+// recycled allocation: smallest released block of at least the size (and at most twice it), else cudaMalloc
+template <typename T>
+int pool_alloc(imsame_ctx *ctx, T **p, uint64_t count) {
+    const size_t bytes = (size_t)std::max<uint64_t>(count, 1) * sizeof(T);
+    int best = -1;
+    for (size_t i = 0; i < ctx->free_blocks.size(); i++) {
+        const size_t b = ctx->free_blocks[i].bytes;
+        if (b >= bytes && b <= 2 * bytes + 4096 && (best < 0 || b < ctx->free_blocks[best].bytes)) best = (int)i;
+    }
+    if (best >= 0) {
+        *p = (T *)ctx->free_blocks[best].p;
+        ctx->live_blocks.push_back(ctx->free_blocks[best]);
+        ctx->free_blocks.erase(ctx->free_blocks.begin() + best);
+        return IMSAME_OK;
+    }
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->free_blocks.empty()) {  // give the cached blocks back and retry
+        cudaGetLastError();
+        for (auto &b : ctx->free_blocks) cudaFree(b.p);
+        ctx->free_blocks.clear();
+        e = cudaMalloc((void **)p, bytes);
+    }
+    if (e != cudaSuccess) {
+        ctx->cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? IMSAME_ENOMEM : IMSAME_ECUDA;
+    }
+    ctx->live_blocks.push_back({(void *)*p, bytes});
+    return IMSAME_OK;
+}
+template <typename T>
+void pool_free(imsame_ctx *ctx, T *&p) {
+    if (!p) return;
+    for (size_t i = 0; i < ctx->live_blocks.size(); i++)
+        if (ctx->live_blocks[i].p == (void *)p) {
+            ctx->free_blocks.push_back(ctx->live_blocks[i]);
+            ctx->live_blocks.erase(ctx->live_blocks.begin() + i);
+            p = nullptr;
+            return;
+        }
+    cudaFree(p);
+    p = nullptr;
+}
+void pool_destroy(imsame_ctx *ctx) {
+    for (auto &b : ctx->free_blocks) cudaFree(b.p);
+    for (auto &b : ctx->live_blocks) cudaFree(b.p);
+    ctx->free_blocks.clear();
+    ctx->live_blocks.clear();
+}
+
 void free_query(imsame_ctx *ctx) {
-    dev_free(ctx->q_pk); dev_free(ctx->q_start); dev_free(ctx->q_blk);
-    dev_free(ctx->qpos);
+    pool_free(ctx, ctx->q_pk); pool_free(ctx, ctx->q_start); pool_free(ctx, ctx->q_blk);
+    pool_free(ctx, ctx->qpos);
     ctx->have_query = false;
 }
 void free_db(imsame_ctx *ctx) {
-    for (Seg &s : ctx->segs) { dev_free(s.pk); dev_free(s.start); dev_free(s.blk); dev_free(s.brk); }
+    for (Seg &s : ctx->segs) { pool_free(ctx, s.pk); pool_free(ctx, s.start); pool_free(ctx, s.blk); pool_free(ctx, s.brk); }
     ctx->segs.clear();
     ctx->have_db = false;
 }
@@ -437,6 +492,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_query(ctx);
     free_db(ctx);
+    pool_destroy(ctx);
     dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
     dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
@@ -495,14 +551,14 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
 
     int rc;
     const uint64_t words = ((uint64_t)total + 15) / 16 + PAD_WORDS;
-    if ((rc = dev_alloc(ctx, &ctx->q_pk, words))) return rc;
+    if ((rc = pool_alloc(ctx, &ctx->q_pk, words))) return rc;
     CK(cudaMemsetAsync(ctx->q_pk, 0, words * 4, ctx->stream));
     if ((rc = upload_pack(ctx, q->sequences, total, ctx->q_pk, PH_PACKQ))) return rc;
     if (!ctx->q_fixed) {
-        if ((rc = dev_alloc(ctx, &ctx->q_start, (uint64_t)nq + 1))) return rc;
+        if ((rc = pool_alloc(ctx, &ctx->q_start, (uint64_t)nq + 1))) return rc;
         if ((rc = upload_u32(ctx, ctx->q_start, ctx->q_start_host.data(), (uint64_t)nq + 1))) return rc;
         const uint64_t nblk = ((uint64_t)total + 63) / 64 + 1;
-        if ((rc = dev_alloc(ctx, &ctx->q_blk, nblk))) return rc;
+        if ((rc = pool_alloc(ctx, &ctx->q_blk, nblk))) return rc;
         PhaseScope ps(ctx, PH_K1);
         blk_kernel<<<std::min<uint32_t>((nq + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ctx->q_start, nq, ctx->q_blk);
         ctx->launches++;
@@ -535,7 +591,7 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
     CK(cudaMemcpyAsync(&n_words, ctx->off + NCODES, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_qwords = n_words;
-    if ((rc = dev_alloc(ctx, &ctx->qpos, (uint64_t)n_words + 1))) return rc;
+    if ((rc = pool_alloc(ctx, &ctx->qpos, (uint64_t)n_words + 1))) return rc;
     {
         PhaseScope ps(ctx, PH_K1);
         CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)NCODES + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -585,7 +641,7 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
         s.fixed_len = fixed;
         int rc;
         const uint64_t words = ((uint64_t)s.total + 15) / 16 + PAD_WORDS;
-        if ((rc = dev_alloc(ctx, &s.pk, words))) return rc;
+        if ((rc = pool_alloc(ctx, &s.pk, words))) return rc;
         ctx->segs.push_back(s);
         CK(cudaMemsetAsync(s.pk + words - PAD_WORDS - 1, 0, (PAD_WORDS + 1) * 4, ctx->stream));
         if ((rc = upload_pack(ctx, db->sequences + base, s.total, s.pk, PH_PACKDB))) return rc;
@@ -594,11 +650,11 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
             tmp.resize((size_t)s.n + 1);
             for (uint64_t r = r0; r < r1; r++) tmp[r - r0] = (uint32_t)(db->start_pos[r] - base);
             tmp[s.n] = s.total;
-            if ((rc = dev_alloc(ctx, &ss.start, (uint64_t)s.n + 1))) return rc;
+            if ((rc = pool_alloc(ctx, &ss.start, (uint64_t)s.n + 1))) return rc;
             if ((rc = upload_u32(ctx, ss.start, tmp.data(), (uint64_t)s.n + 1))) return rc;
             CK(cudaStreamSynchronize(ctx->stream));  // tmp is reused
             const uint64_t nblk = ((uint64_t)s.total + 63) / 64 + 1;
-            if ((rc = dev_alloc(ctx, &ss.blk, nblk))) return rc;
+            if ((rc = pool_alloc(ctx, &ss.blk, nblk))) return rc;
             PhaseScope ps(ctx, PH_PACKDB);
             blk_kernel<<<std::min<uint32_t>((s.n + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ss.start, s.n, ss.blk);
             ctx->launches++;
@@ -611,7 +667,7 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
         }
         if (!brk.empty()) {
             ss.n_brk = (uint32_t)brk.size();
-            if ((rc = dev_alloc(ctx, &ss.brk, brk.size()))) return rc;
+            if ((rc = pool_alloc(ctx, &ss.brk, brk.size()))) return rc;
             if ((rc = upload_u32(ctx, ss.brk, brk.data(), brk.size()))) return rc;
             CK(cudaStreamSynchronize(ctx->stream));
         }
@@ -920,12 +976,21 @@ int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seq
     if (!ctx || !db || !query || !p || !out) return IMSAME_EARG;
     reset_timing(ctx);
     int rc;
+    const bool trace = getenv("IMSAME_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if ((rc = imsame_gpu_set_query(ctx, query, p))) return rc;
+    const double t1 = now();
     if ((rc = imsame_gpu_set_db(ctx, db))) return rc;
+    const double t2 = now();
     imsame_stats local;
     memset(&local, 0, sizeof(local));
     if ((rc = run_impl(ctx, p, nullptr, nullptr, &local))) return rc;
+    const double t3 = now();
     if ((rc = imsame_gpu_fetch(ctx, nullptr, nullptr, out))) return rc;
+    if (trace)
+        fprintf(stderr, "[imsame] host wall ms: set_query %.1f  set_db %.1f  run %.1f  fetch %.1f\n", t1 - t0, t2 - t1, t3 - t2,
+                now() - t3);
     uint64_t acc = 0;
     for (uint32_t r = 0; r < ctx->nq; r++) acc += out[r].accepted;
     if (st) {
