@@ -221,7 +221,7 @@ def run_ours(args):
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     # torchrun pins OMP_NUM_THREADS=1; the synthetic generator (host/synth.c) is OpenMP
-    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world)))
+    H.set_synth_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)

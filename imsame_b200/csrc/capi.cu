@@ -87,6 +87,7 @@ struct imsame_ctx {
     uint8_t *stage = nullptr;
     int nw_grid[9] = {0};
     int nwp_grid[9] = {0};
+    bool in_align = false;  // imsame_gpu_align: upload phases belong to the same stats
     int nw_mode = 0;  // 0: packed-word kernel where pw_eligible() holds, 1: generic kernel only
     int scan_grid = 0;
 
@@ -706,6 +707,7 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     if (!ctx || !p) return IMSAME_EARG;
     if (!ctx->have_query || !ctx->have_db) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
+    if (!ctx->in_align) reset_timing(ctx);  // a run of its own: phase times and launch counts start here
     const uint32_t nq = ctx->nq;
     int rc;
     if (ctx->keys_cap < nq) {
@@ -918,7 +920,6 @@ extern "C" {
 int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
                    imsame_stats *st) {
     if (!ctx || !p) return IMSAME_EARG;
-    reset_timing(ctx);
     return run_impl(ctx, p, d_keys, d_payload, st);
 }
 
@@ -985,7 +986,10 @@ int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seq
     const double t2 = now();
     imsame_stats local;
     memset(&local, 0, sizeof(local));
-    if ((rc = run_impl(ctx, p, nullptr, nullptr, &local))) return rc;
+    ctx->in_align = true;
+    rc = run_impl(ctx, p, nullptr, nullptr, &local);
+    ctx->in_align = false;
+    if (rc) return rc;
     const double t3 = now();
     if ((rc = imsame_gpu_fetch(ctx, nullptr, nullptr, out))) return rc;
     if (trace)

@@ -52,6 +52,7 @@ uint64_t imsame_render_alignment(char *dst, const unsigned char *X, uint32_t xle
 
 /* ---- synthetic metagenomes ---------------------------------- */
 typedef struct imsame_synth_pool imsame_synth_pool;
+void imsame_synth_set_threads(int n);
 imsame_synth_pool *imsame_synth_pool_create(uint64_t seed, uint32_t n_genomes, uint64_t genome_len);
 void imsame_synth_pool_destroy(imsame_synth_pool *p);
 void imsame_synth_db_reads(const imsame_synth_pool *p, uint64_t seed, uint64_t first, uint64_t count,

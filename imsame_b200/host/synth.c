@@ -13,6 +13,9 @@
  * ASCII byte per base, reads concatenated without separators.
  */
 #include "imsame_host.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,6 +40,15 @@ struct imsame_synth_pool {
     uint64_t words_per_genome; /* 32 bases per 64-bit word */
     uint64_t *bits;
 };
+
+/* threads of the generator loops (launchers such as torchrun pin OMP_NUM_THREADS=1 in the environment) */
+void imsame_synth_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 
 imsame_synth_pool *imsame_synth_pool_create(uint64_t seed, uint32_t n_genomes, uint64_t genome_len) {
     imsame_synth_pool *p = (imsame_synth_pool *)calloc(1, sizeof(*p));

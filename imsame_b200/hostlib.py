@@ -33,6 +33,7 @@ def lib():
         l.imsame_synth_pool_create.restype = C.c_void_p
         l.imsame_synth_pool_create.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
         l.imsame_synth_pool_destroy.argtypes = [C.c_void_p]
+        l.imsame_synth_set_threads.argtypes = [C.c_int]
         l.imsame_synth_db_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]
         l.imsame_synth_query_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
                                                C.c_double, C.c_uint32, C.c_void_p]
@@ -43,6 +44,11 @@ def lib():
                                               C.c_uint32, C.c_void_p, C.c_uint64]
         _lib = l
     return _lib
+
+
+def set_synth_threads(n):
+    """threads of the synthetic generator (torchrun exports OMP_NUM_THREADS=1)"""
+    lib().imsame_synth_set_threads(int(n))
 
 
 def render_record(read, db_seq, length, identities, x, y, bx, by, ops):
