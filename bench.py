@@ -376,7 +376,7 @@ def run_ours(args):
                          "frac": (achieved / int_peak) if int_peak else None,
                          "traffic": None,
                          "traffic_note": "register/shared-memory resident: ncu dram bytes per launch are ~1e-4 of the kernel's "
-                                         "integer work (profiles/r01_ncu_nwp_v2_metrics.txt), HBM is not a bound",
+                                         "integer work (profiles/r01_ncu_nwp_v4_metrics.txt), HBM is not a bound",
                          "ops_per_cell": ops_per_cell, "gcups": gcups,
                          "gcups_roofline": (int_peak / ops_per_cell) if ops_per_cell else None,
                          "frac_survey24": (gcups * OPS_PER_CELL_GENERIC / int_peak) if int_peak else None,
