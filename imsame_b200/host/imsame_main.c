@@ -167,6 +167,8 @@ int main(int argc, char **av) {
     }
     fflush(stdout);
 
+    const int trace = getenv("IMSAME_TRACE") != NULL; /* phase wall times on stderr (not part of the reference's output) */
+    double tp = now_s();
     uint64_t accepted = 0;
     imsame_best *best = (imsame_best *)calloc(q.n_seqs ? q.n_seqs : 1, sizeof(imsame_best));
     if (!best) terror("Could not allocate arguments for hash table");
@@ -239,6 +241,7 @@ int main(int argc, char **av) {
         free(jobs);
         free(th);
         for (uint64_t r = 0; r < q.n_seqs; r++) accepted += best[r].accepted;
+        if (trace) { fprintf(stderr, "[imsame] align (all shards) %.3f s\n", now_s() - tp); tp = now_s(); }
 
         if (fout != NULL && accepted > 0) {
             imsame_ctx *ctx = NULL;
@@ -248,6 +251,7 @@ int main(int argc, char **av) {
             uint32_t *cell = (uint32_t *)malloc(4 * q.n_seqs * sizeof(uint32_t)), *ops = NULL;
             rc = imsame_gpu_traceback(ctx, &dv, &qv, &p, best, ops_off, &ops, cell);
             if (rc) gpu_fail(ctx, rc);
+            if (trace) { fprintf(stderr, "[imsame] traceback (GPU) %.3f s\n", now_s() - tp); tp = now_s(); }
             char *text = (char *)malloc(6 * (2 * (size_t)IMSAME_MAX_READ_SIZE) + 512), hdr[256];
             for (uint64_t r = 0; r < q.n_seqs; r++) {
                 if (!best[r].accepted) continue;
@@ -261,6 +265,7 @@ int main(int argc, char **av) {
                                                       ops + ops_off[r], ops_off[r + 1] - ops_off[r]);
                 fwrite(text, 1, (size_t)tl, fout);
             }
+            if (trace) { fprintf(stderr, "[imsame] render + write %.3f s\n", now_s() - tp); tp = now_s(); }
             free(text);
             imsame_gpu_free(ops);
             free(ops_off);

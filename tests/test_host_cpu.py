@@ -27,6 +27,39 @@ def test_fasta_loader_matches_oracle_loader(built, name, is_db):
     assert set(np.unique(seq)) <= set(b"ACGT")
 
 
+@pytest.mark.parametrize("is_db", [True, False])
+def test_parallel_fasta_loader_on_a_dirty_multi_megabyte_file(built, is_db, tmp_path):
+    """the loader cuts files > 1 MB into pieces at "\\n>" and parses them on all threads: records that
+    start mid-line, '>' inside headers, N runs, CRLF, lower case, empty records, text before the first
+    header and a missing final newline must come out exactly as in the sequential oracle loader"""
+    from imsame_b200 import hostlib as H
+    rng = np.random.default_rng(5 + int(is_db))
+    alpha = np.frombuffer(b"ACGTACGTACGTacgtNnRY-", dtype=np.uint8)
+    parts = [b"junk before the first header\nACGT\n"]
+    for r in range(9000):
+        hdr = b">r%d desc > with gt" % r if r % 7 else b">r%d" % r
+        parts.append(hdr + (b"\r\n" if r % 5 == 0 else b"\n"))
+        if r % 97 == 0:
+            continue  # empty record
+        for _ in range(int(rng.integers(1, 9))):
+            line = alpha[rng.integers(0, len(alpha), size=int(rng.integers(1, 120)))].tobytes()
+            parts.append(line + (b"\r\n" if r % 5 == 0 else b"\n"))
+        if r % 211 == 0:
+            parts.append(b"ACGTAC>midline record start\nGGGTTTAAACCC")  # '>' not at a line start, no newline after
+            parts.append(b"\n")
+    parts.append(b">last\nACGTNACGT")  # no final newline
+    path = str(tmp_path / "big_dirty.fa")
+    open(path, "wb").write(b"".join(parts))
+    assert os.path.getsize(path) > 2 * (1 << 20)
+    seq, start, brk = H.load_fasta(path, is_db)
+    o = hp.OracleSeqs(path, is_db)
+    oseq, ostart, obrk = o.numpy()
+    assert np.array_equal(start, ostart)
+    assert np.array_equal(seq, oseq)
+    if is_db:
+        assert np.array_equal(brk, obrk) and len(brk) > 1000
+
+
 def test_threshold_tables_are_exact(built):
     from imsame_b200 import api, hostlib as H
     lib = hp.oracle()

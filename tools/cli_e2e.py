@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""End-to-end run of the drop-in CLI (bin/IMSAME) on a synthetic cfg2-shaped FASTA pair:
+FASTA files on disk -> .align file.  usage: python tools/cli_e2e.py --scale 1.0 [--gpus N]"""
+import argparse, os, subprocess, sys, time, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imsame_b200 import hostlib as H  # noqa: E402
+ap = argparse.ArgumentParser()
+ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--gpus", type=int, default=1)
+ap.add_argument("--dir", default=None)
+a = ap.parse_args()
+nd, nq, g, L = int(10_000_000 * a.scale), int(1_000_000 * a.scale), max(2, int(1000 * a.scale)), 250
+d = a.dir or tempfile.mkdtemp(prefix="imsame_cli_")
+t = time.time()
+pool = H.SynthPool(2001, g, 1_000_000)
+db = pool.db_reads(0, nd, L); q = pool.query_reads(0, nq, L, 0.03); pool.close()
+H.write_fasta(os.path.join(d, "db.fa"), db, nd, L, "d"); H.write_fasta(os.path.join(d, "q.fa"), q, nq, L, "q")
+del db, q
+print(f"generated + wrote FASTA in {time.time() - t:.1f}s: db {os.path.getsize(os.path.join(d, 'db.fa')) / 1e9:.2f} GB", flush=True)
+env = dict(os.environ, IMSAME_TRACE="1")
+for rep in range(2):
+    t = time.time()
+    r = subprocess.run([os.path.join(ROOT, "bin", "IMSAME"), "-query", os.path.join(d, "q.fa"), "-db", os.path.join(d, "db.fa"),
+                        "-out", os.path.join(d, "out.align"), "-gpus", str(a.gpus)], capture_output=True, text=True, env=env)
+    wall = time.time() - t
+    info = [l for l in r.stdout.splitlines() if l.startswith("[INFO]")]
+    print(f"run {rep}: rc={r.returncode} wall {wall:.2f}s  -> {nq / wall:.0f} query reads/s end to end, "
+          f"out {os.path.getsize(os.path.join(d, 'out.align')) / 1e6:.0f} MB")
+    print("\n".join(info[-6:])); print(r.stderr[-600:])
