@@ -194,7 +194,7 @@ def run_reference_arm(args):
     w = workload(args.scale)
     r, err = reference_cpu_run(args, w, max(1, args.steps), min(args.warmup, 1))
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": err}))
+        OUT.emit(json.dumps({"impl": "reference", "unavailable": err}))
         return
     v = r["reads_per_s_align_phase"]
     line = {"impl": "reference", "metric": "query reads aligned/sec", "value": v, "unit": "reads/s",
@@ -206,7 +206,7 @@ def run_reference_arm(args):
             "e2e": {"value": r["reads_per_s_index_plus_align"], "unit": "reads/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0,
                     "what": "index build (src/IMSAME.c:196-289) + alignment phase (:409-467), FASTA already parsed is not separable"}}
-    print(json.dumps(line))
+    OUT.emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
@@ -401,7 +401,7 @@ def run_ours(args):
                                         "reads_per_s_index_plus_align": r["reads_per_s_index_plus_align"]}
             else:
                 line["cpu_baseline"] = {"unavailable": err}
-        print(json.dumps(line))
+        OUT.emit(json.dumps(line))
     ctx.close()
     db_pin.free()
     q_pin.free()
@@ -409,8 +409,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+class StdoutToStderr:
+    """stdout carries exactly ONE line (the JSON): everything libraries print on fd 1 meanwhile (NCCL's
+    version banner, torchrun notes) is sent to stderr; `emit` writes to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
+OUT = None
+
+
 if __name__ == "__main__":
     a = parse()
+    OUT = StdoutToStderr()
     if a.impl == "reference":
         run_reference_arm(a)
     else:

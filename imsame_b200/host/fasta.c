@@ -75,39 +75,9 @@ static void parse_piece(const unsigned char *buf, size_t i, size_t end, int is_d
     if (cnt) { cnt->bases = pos - pos0; cnt->recs = n - n0; cnt->brks = nb - nb0; }
 }
 
-int imsame_fasta_load(const char *path, int is_db, imsame_fasta *out) {
+/* parse a FASTA image held in memory (the file, or the output of imsame_revcomp_mem) */
+int imsame_fasta_parse_mem(const unsigned char *buf, size_t flen, int is_db, imsame_fasta *out) {
     memset(out, 0, sizeof(*out));
-    const int fd = open(path, O_RDONLY);
-    if (fd < 0) return IMSAME_EARG;
-    struct stat st;
-    if (fstat(fd, &st)) { close(fd); return IMSAME_EARG; }
-    size_t flen = (size_t)st.st_size;
-    unsigned char *buf = NULL;
-    int mapped = 0;
-    if (S_ISREG(st.st_mode) && flen > 0) {
-        void *m = mmap(NULL, flen, PROT_READ, MAP_PRIVATE, fd, 0);
-        if (m != MAP_FAILED) { buf = (unsigned char *)m; mapped = 1; madvise(m, flen, MADV_SEQUENTIAL | MADV_WILLNEED); }
-    }
-    if (!buf) { /* not mappable (or empty): read it */
-        size_t cap = flen ? flen : (1 << 16), got = 0;
-        buf = (unsigned char *)malloc(cap + 1);
-        if (!buf) { close(fd); return IMSAME_ENOMEM; }
-        for (;;) {
-            if (got == cap) {
-                cap *= 2;
-                unsigned char *nb2 = (unsigned char *)realloc(buf, cap + 1);
-                if (!nb2) { free(buf); close(fd); return IMSAME_ENOMEM; }
-                buf = nb2;
-            }
-            const ssize_t r = read(fd, buf + got, cap - got);
-            if (r < 0) { free(buf); close(fd); return IMSAME_EARG; }
-            if (r == 0) break;
-            got += (size_t)r;
-        }
-        flen = got;
-    }
-    close(fd);
-
     unsigned char cls[256], up[256];
     for (int c = 0; c < 256; c++) { cls[c] = C_OTHER; up[c] = (unsigned char)c; }
     cls['\n'] = C_NL;
@@ -154,22 +124,118 @@ int imsame_fasta_load(const char *path, int is_db, imsame_fasta *out) {
     unsigned char *seq = (unsigned char *)malloc((size_t)pos0[np] + 64);
     uint64_t *start = (uint64_t *)malloc((n0[np] + 2) * sizeof(uint64_t));
     uint64_t *brk = (uint64_t *)malloc((nb0[np] + 1) * sizeof(uint64_t));
-    if (!seq || !start || !brk) {
-        free(seq); free(start); free(brk);
-        if (mapped) munmap(buf, flen); else free(buf);
-        return IMSAME_ENOMEM;
-    }
+    if (!seq || !start || !brk) { free(seq); free(start); free(brk); return IMSAME_ENOMEM; }
 #pragma omp parallel for schedule(static, 1)
     for (int k = 0; k < np; k++)
         parse_piece(buf, cut[k], cut[k + 1], is_db, cls, up, seq, start, brk, pos0[k], n0[k], nb0[k], NULL);
     start[n0[np]] = pos0[np];
-    if (mapped) munmap(buf, flen); else free(buf);
     out->sequences = seq;
     out->start_pos = start;
     out->break_pos = brk;
     out->total_len = pos0[np];
     out->n_seqs = n0[np];
     out->n_breaks = nb0[np];
+    return IMSAME_OK;
+}
+
+/* whole file -> memory image (mapped when possible); release with imsame_file_unmap */
+int imsame_file_map(const char *path, imsame_file_image *img) {
+    memset(img, 0, sizeof(*img));
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return IMSAME_EARG;
+    struct stat st;
+    if (fstat(fd, &st)) { close(fd); return IMSAME_EARG; }
+    size_t flen = (size_t)st.st_size;
+    unsigned char *buf = NULL;
+    if (S_ISREG(st.st_mode) && flen > 0) {
+        void *m = mmap(NULL, flen, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) { buf = (unsigned char *)m; img->mapped = 1; madvise(m, flen, MADV_SEQUENTIAL | MADV_WILLNEED); }
+    }
+    if (!buf) { /* not mappable (or empty): read it */
+        size_t cap = flen ? flen : (1 << 16), got = 0;
+        buf = (unsigned char *)malloc(cap + 1);
+        if (!buf) { close(fd); return IMSAME_ENOMEM; }
+        for (;;) {
+            if (got == cap) {
+                cap *= 2;
+                unsigned char *nb2 = (unsigned char *)realloc(buf, cap + 1);
+                if (!nb2) { free(buf); close(fd); return IMSAME_ENOMEM; }
+                buf = nb2;
+            }
+            const ssize_t r = read(fd, buf + got, cap - got);
+            if (r < 0) { free(buf); close(fd); return IMSAME_EARG; }
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        flen = got;
+    }
+    close(fd);
+    img->data = buf;
+    img->len = flen;
+    return IMSAME_OK;
+}
+
+void imsame_file_unmap(imsame_file_image *img) {
+    if (img->data) {
+        if (img->mapped) munmap(img->data, img->len); else free(img->data);
+    }
+    memset(img, 0, sizeof(*img));
+}
+
+int imsame_fasta_load(const char *path, int is_db, imsame_fasta *out) {
+    memset(out, 0, sizeof(*out));
+    imsame_file_image img;
+    int rc = imsame_file_map(path, &img);
+    if (rc) return rc;
+    rc = imsame_fasta_parse_mem(img.data, img.len, is_db, out);
+    imsame_file_unmap(&img);
+    return rc;
+}
+
+/* The reference's reverse-complement tool on a memory image (src/reverseComplement.c:21-118):
+ * records in REVERSE file order (:56); a record starts at every '>' byte (:47-52); the header line is
+ * copied verbatim (:59-62); only letters are kept from the body (:65-70) and written
+ * reverse-complemented on ONE line (:71-112) with A<->T, C<->G, U->A (case preserved), every other
+ * letter unchanged.  *out is malloc'ed (free it). */
+int imsame_revcomp_mem(const unsigned char *buf, size_t n, unsigned char **out, size_t *out_len) {
+    unsigned char comp[256];
+    for (int c = 0; c < 256; c++) comp[c] = (unsigned char)c;
+    comp['A'] = 'T'; comp['C'] = 'G'; comp['G'] = 'C'; comp['T'] = 'A'; comp['U'] = 'A';
+    comp['a'] = 't'; comp['c'] = 'g'; comp['g'] = 'c'; comp['t'] = 'a'; comp['u'] = 'a';
+    size_t cap = 1024, nrec = 0;
+    size_t *off = (size_t *)malloc(cap * sizeof(size_t));
+    unsigned char *dst = (unsigned char *)malloc(2 * n + 16); /* every record gains at most one '\n' */
+    if (!off || !dst) { free(off); free(dst); return IMSAME_ENOMEM; }
+    for (size_t i = 0; i < n; i++)
+        if (buf[i] == '>') {
+            if (nrec == cap) {
+                cap *= 2;
+                size_t *o2 = (size_t *)realloc(off, cap * sizeof(size_t));
+                if (!o2) { free(off); free(dst); return IMSAME_ENOMEM; }
+                off = o2;
+            }
+            off[nrec++] = i;
+        }
+    size_t w = 0;
+    for (size_t r = nrec; r-- > 0;) {
+        /* header = up to the first newline (fgets, :59), even if it holds another '>';
+           body = up to the next '>' after the header (:65) */
+        size_t i = off[r], h = i;
+        while (h < n && buf[h] != '\n') h++;
+        if (h < n) h++;
+        size_t end = h;
+        while (end < n && buf[end] != '>') end++;
+        memcpy(dst + w, buf + i, h - i);
+        w += h - i;
+        for (size_t k = end; k-- > h;) {
+            const unsigned char c = buf[k];
+            if ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) dst[w++] = comp[c];
+        }
+        dst[w++] = '\n';
+    }
+    free(off);
+    *out = dst;
+    *out_len = w;
     return IMSAME_OK;
 }
 

@@ -7,6 +7,7 @@
  */
 #ifndef IMSAME_HOST_H
 #define IMSAME_HOST_H
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/imsame_gpu.h"
@@ -24,8 +25,18 @@ typedef struct imsame_fasta {
     uint64_t n_breaks;
 } imsame_fasta;
 
-/* pinned != 0: allocate `sequences` with imsame_gpu_host_alloc (needs the GPU library) */
 int imsame_fasta_load(const char *path, int is_db, imsame_fasta *out);
+/* the same parser on a FASTA image in memory */
+int imsame_fasta_parse_mem(const unsigned char *buf, size_t len, int is_db, imsame_fasta *out);
+typedef struct imsame_file_image {
+    unsigned char *data;
+    size_t len;
+    int mapped;
+} imsame_file_image;
+int imsame_file_map(const char *path, imsame_file_image *img);
+void imsame_file_unmap(imsame_file_image *img);
+/* src/reverseComplement.c on a memory image; *out is malloc'ed */
+int imsame_revcomp_mem(const unsigned char *buf, size_t n, unsigned char **out, size_t *out_len);
 void imsame_fasta_free(imsame_fasta *f);
 void imsame_fasta_view(const imsame_fasta *f, imsame_seqinfo *v);
 
