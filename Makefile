@@ -15,7 +15,7 @@ HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/
 GPU_SRC   := imsame_b200/csrc/capi.cu
 GPU_HDR   := $(wildcard imsame_b200/csrc/*.cuh) include/imsame_gpu.h
 
-all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so bin/IMSAME bin/revComp bin/all_vs_all_metagenomes_IMSAME.sh
+all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so bin/IMSAME bin/IMSAME_allvsall bin/revComp bin/all_vs_all_metagenomes_IMSAME.sh
 
 $(OUT)/libimsame_host.so: $(HOST_SRC) imsame_b200/host/imsame_host.h include/imsame_gpu.h
 	@mkdir -p $(OUT)
@@ -27,9 +27,16 @@ $(OUT)/libimsame_gpu.so: $(GPU_SRC) $(GPU_HDR) imsame_b200/host/thresholds.c
 	$(NVCC) $(NVFLAGS) -shared $(GPU_SRC) $(OUT)/thresholds.o -o $@ 2> $(OUT)/ptxas.log || (cat $(OUT)/ptxas.log; false)
 	@grep -E "error|warning|spill" $(OUT)/ptxas.log | grep -v "0 bytes spill" || true
 
-bin/IMSAME: imsame_b200/host/imsame_main.c $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
+JOB_SRC   := imsame_b200/host/imsame_job.c imsame_b200/host/imsame_job.h
+
+bin/IMSAME: imsame_b200/host/imsame_main.c $(JOB_SRC) $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
 	@mkdir -p bin
-	$(CC) $(CFLAGS) -fPIE imsame_b200/host/imsame_main.c -L$(OUT) -limsame_host -limsame_gpu \
+	$(CC) $(CFLAGS) -fPIE imsame_b200/host/imsame_main.c imsame_b200/host/imsame_job.c -L$(OUT) -limsame_host -limsame_gpu \
+	    -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lpthread -lm -o $@
+
+bin/IMSAME_allvsall: imsame_b200/host/imsame_allvsall_main.c $(JOB_SRC) $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so
+	@mkdir -p bin
+	$(CC) $(CFLAGS) -fPIE imsame_b200/host/imsame_allvsall_main.c imsame_b200/host/imsame_job.c -L$(OUT) -limsame_host -limsame_gpu \
 	    -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lpthread -lm -o $@
 
 bin/revComp: imsame_b200/host/revcomp_main.c

@@ -1,0 +1,156 @@
+/*
+ * IMSAME_allvsall -- the reference's all-vs-all workflow (bin/all_vs_all_metagenomes_IMSAME.sh:27-58)
+ * in ONE process: same arguments, same output files (OUT/X-Y.align and OUT/X-Y.r.align, byte for byte
+ * what the script produces with the drop-in IMSAME and revComp), same resume rule (existing outputs
+ * are kept) -- but every sample is parsed once, its reverse complement (src/reverseComplement.c, incl.
+ * the reversed record order that renumbers db_seq) is built in memory instead of a temporary Y.r.EXT
+ * file, and all 2 * n(n-1)/2 comparisons share one CUDA context and its device buffers.  The script
+ * starts 56 IMSAME and 28 revComp processes for 8 samples and re-parses every file 14 times.
+ *
+ * usage: IMSAME_allvsall metagenomes_directory coverage similarity threads file_extension outpath [-device D]
+ */
+#define _GNU_SOURCE
+#include <dirent.h>
+#include <inttypes.h>
+#include <locale.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+
+#include "imsame_host.h"
+#include "imsame_job.h"
+
+static void terror(const char *s) { /* src/commonFunctions.c:10-13 */
+    printf("ERR**** %s ****\n", s);
+    exit(-1);
+}
+
+static double now_s(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+
+typedef struct {
+    char *name;            /* file name without ".EXT" */
+    imsame_fasta fwd, rev; /* parsed forward sample / parsed revComp(sample) */
+    int have_fwd, have_rev;
+} sample;
+
+static int by_name(const void *a, const void *b) { return strcoll(((const sample *)a)->name, ((const sample *)b)->name); }
+
+static int exists(const char *path) {
+    struct stat st;
+    return stat(path, &st) == 0 && S_ISREG(st.st_mode);
+}
+
+static void need_forward(sample *s, const char *dir, const char *ext) {
+    if (s->have_fwd) return;
+    char path[4096];
+    snprintf(path, sizeof path, "%s/%s.%s", dir, s->name, ext);
+    if (imsame_fasta_load(path, 1, &s->fwd)) terror("Could not allocate memory for database vector");
+    s->have_fwd = 1;
+}
+
+static void need_reverse(sample *s, const char *dir, const char *ext) {
+    if (s->have_rev) return;
+    char path[4096];
+    snprintf(path, sizeof path, "%s/%s.%s", dir, s->name, ext);
+    imsame_file_image img;
+    if (imsame_file_map(path, &img)) terror("opening IN sequence FASTA file");
+    unsigned char *rc = NULL;
+    size_t rc_len = 0;
+    if (imsame_revcomp_mem(img.data, img.len, &rc, &rc_len)) terror("memory for Seq");
+    imsame_file_unmap(&img);
+    if (imsame_fasta_parse_mem(rc, rc_len, 1, &s->rev)) terror("Could not allocate memory for database vector");
+    free(rc);
+    s->have_rev = 1;
+}
+
+int main(int argc, char **av) {
+    if (argc < 7) {
+        printf("***ERROR*** Use: %s metagenomes_directory coverage similarity threads file_extension outpath\n", av[0]);
+        return 255;
+    }
+    setlocale(LC_ALL, "");
+    const char *dir = av[1], *ext = av[5], *out = av[6];
+    imsame_job_opts jo;
+    memset(&jo, 0, sizeof jo);
+    /* the script passes -coverage / -identity / -n_threads; everything else keeps IMSAME's defaults (src/IMSAME.c:44-49) */
+    jo.mincoverage = (long double)atof(av[2]);
+    jo.minidentity = (long double)atof(av[3]);
+    jo.n_threads = (uint64_t)atoi(av[4]);
+    jo.minevalue = 1 / powl(10, 20);
+    jo.igap = -5;
+    jo.egap = -2;
+    jo.gpus = 1;
+    jo.trace = getenv("IMSAME_TRACE") != NULL;
+    for (int i = 7; i + 1 < argc; i++)
+        if (strcmp(av[i], "-device") == 0) jo.device = atoi(av[i + 1]);
+    if (jo.mincoverage <= 0) terror("Min-coverage must be larger than zero");
+    if (jo.minidentity <= 0) terror("Min-identity must be larger than zero");
+
+    /* `ls -d DIR/<name>.EXT`: names ending in ".EXT", in collation order */
+    DIR *d = opendir(dir);
+    if (!d) terror("Could not open the metagenomes directory");
+    size_t n = 0, cap = 16, el = strlen(ext);
+    sample *sm = (sample *)calloc(cap, sizeof(sample));
+    for (struct dirent *e; (e = readdir(d)) != NULL;) {
+        const size_t l = strlen(e->d_name);
+        if (e->d_name[0] == '.' || l < el + 2 || e->d_name[l - el - 1] != '.' || strcmp(e->d_name + l - el, ext) != 0) continue;
+        if (n == cap) {
+            cap *= 2;
+            sm = (sample *)realloc(sm, cap * sizeof(sample));
+            memset(sm + n, 0, (cap - n) * sizeof(sample));
+        }
+        sm[n].name = strndup(e->d_name, l - el - 1);
+        n++;
+    }
+    closedir(d);
+    qsort(sm, n, sizeof(sample), by_name);
+
+    imsame_ctx *ctx = NULL;
+    const double t_all = now_s();
+    uint64_t jobs = 0;
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = i + 1; j < n; j++)
+            for (int rev = 0; rev < 2; rev++) {
+                char path[4096];
+                snprintf(path, sizeof path, "%s/%s-%s%s.align", out, sm[i].name, sm[j].name, rev ? ".r" : "");
+                if (exists(path)) continue; /* resume: bin/...sh:35,45 */
+                need_forward(&sm[i], dir, ext);
+                if (rev) need_reverse(&sm[j], dir, ext); else need_forward(&sm[j], dir, ext);
+                const imsame_fasta *q = &sm[i].fwd, *db = rev ? &sm[j].rev : &sm[j].fwd;
+                FILE *fout = fopen(path, "wt");
+                const double t0 = now_s();
+                uint64_t accepted = 0;
+                char err[300];
+                const int rc = imsame_run_job(q, db, &jo, fout, &ctx, &accepted, err, sizeof err);
+                if (fout) fclose(fout);
+                if (rc == IMSAME_EREADSIZE) terror("Read size reached for gapped alignment.");
+                if (rc) {
+                    char msg[512];
+                    snprintf(msg, sizeof msg, "GPU hot path failed: %s%s%s", imsame_gpu_strerror(rc), err[0] ? " / " : "", err);
+                    terror(msg);
+                }
+                jobs++;
+                fprintf(stdout,
+                        "[INFO] %s vs %s%s: %" PRIu64 " reads (%" PRIu64 ") from the query were found in the database (%" PRIu64
+                        "); Jaccard-index %Le; %.3f s\n",
+                        sm[i].name, sm[j].name, rev ? " (reverse complement)" : "", accepted, q->n_seqs, db->n_seqs,
+                        (long double)accepted / ((db->n_seqs + q->n_seqs) - accepted), now_s() - t0);
+                fflush(stdout);
+            }
+    fprintf(stdout, "[INFO] %" PRIu64 " comparisons of %zu samples in %.3f s\n", jobs, n, now_s() - t_all);
+    if (ctx) imsame_gpu_destroy(ctx);
+    for (size_t i = 0; i < n; i++) {
+        if (sm[i].have_fwd) imsame_fasta_free(&sm[i].fwd);
+        if (sm[i].have_rev) imsame_fasta_free(&sm[i].rev);
+        free(sm[i].name);
+    }
+    free(sm);
+    return 0;
+}

@@ -26,6 +26,7 @@
 #include <time.h>
 
 #include "imsame_host.h"
+#include "imsame_job.h"
 
 static void terror(const char *s) { /* src/commonFunctions.c:10-13: message on STDOUT, exit(-1) */
     printf("ERR**** %s ****\n", s);
@@ -99,37 +100,6 @@ static void parse_args(int argc, char **av, cli_args *a) {
     }
 }
 
-static void gpu_fail(imsame_ctx *ctx, int rc) {
-    char msg[512];
-    if (rc == IMSAME_EREADSIZE) terror("Read size reached for gapped alignment."); /* :155 */
-    snprintf(msg, sizeof msg, "GPU hot path failed: %s%s%s", imsame_gpu_strerror(rc),
-             ctx && imsame_gpu_last_cuda_error(ctx)[0] ? " / " : "", ctx ? imsame_gpu_last_cuda_error(ctx) : "");
-    terror(msg);
-}
-
-/* one database shard on one GPU */
-typedef struct {
-    int device;
-    const imsame_seqinfo *query;
-    imsame_seqinfo db;
-    imsame_params params;
-    imsame_best *best;
-    imsame_stats stats;
-    int rc;
-    char err[256];
-} shard_job;
-
-static void *shard_main(void *arg) {
-    shard_job *j = (shard_job *)arg;
-    imsame_ctx *ctx = NULL;
-    j->rc = imsame_gpu_create(&ctx, j->device);
-    if (j->rc) return NULL;
-    j->rc = imsame_gpu_align(ctx, &j->db, j->query, &j->params, j->best, &j->stats);
-    if (j->rc) snprintf(j->err, sizeof j->err, "%s", imsame_gpu_last_cuda_error(ctx));
-    imsame_gpu_destroy(ctx);
-    return NULL;
-}
-
 int main(int argc, char **av) {
     cli_args a;
     parse_args(argc, av, &a);
@@ -167,111 +137,25 @@ int main(int argc, char **av) {
     }
     fflush(stdout);
 
-    const int trace = getenv("IMSAME_TRACE") != NULL; /* phase wall times on stderr (not part of the reference's output) */
-    double tp = now_s();
     uint64_t accepted = 0;
-    imsame_best *best = (imsame_best *)calloc(q.n_seqs ? q.n_seqs : 1, sizeof(imsame_best));
-    if (!best) terror("Could not allocate arguments for hash table");
-    imsame_seqinfo qv, dv;
-    imsame_fasta_view(&q, &qv);
-    imsame_fasta_view(&db, &dv);
-    imsame_params p;
-    memset(&p, 0, sizeof p);
-    p.min_e_value = a.minevalue;
-    p.min_coverage = a.mincoverage;
-    p.min_identity = a.minidentity;
-    p.igap = a.igap;
-    p.egap = a.egap;
-    p.n_threads = a.n_threads;
-
-    if (a.n_threads > 0 && q.n_seqs > 0 && db.n_seqs > 0) {
-        int ng = a.gpus;
-        if ((uint64_t)ng > db.n_seqs) ng = (int)db.n_seqs;
-        shard_job *jobs = (shard_job *)calloc((size_t)ng, sizeof(shard_job));
-        pthread_t *th = (pthread_t *)calloc((size_t)ng, sizeof(pthread_t));
-        for (int g = 0; g < ng; g++) {
-            /* contiguous read ranges; global coordinates keep keys and the e-value exact */
-            uint64_t r0 = db.n_seqs * (uint64_t)g / (uint64_t)ng, r1 = db.n_seqs * (uint64_t)(g + 1) / (uint64_t)ng;
-            uint64_t b0 = db.start_pos[r0], b1 = db.start_pos[r1];
-            shard_job *j = &jobs[g];
-            j->device = a.device + g;
-            j->query = &qv;
-            j->db.sequences = db.sequences + b0;
-            j->db.total_len = b1 - b0;
-            j->db.n_seqs = r1 - r0;
-            uint64_t *st = (uint64_t *)malloc((r1 - r0 + 1) * sizeof(uint64_t));
-            for (uint64_t r = r0; r <= r1; r++) st[r - r0] = db.start_pos[r] - b0;
-            j->db.start_pos = st;
-            uint64_t nb = 0, *bk = (uint64_t *)malloc((db.n_breaks + 1) * sizeof(uint64_t));
-            for (uint64_t k = 0; k < db.n_breaks; k++)
-                if (db.break_pos[k] >= b0 && db.break_pos[k] < b1) bk[nb++] = db.break_pos[k] - b0;
-            j->db.break_pos = bk;
-            j->db.n_breaks = nb;
-            j->params = p;
-            j->params.db_total_len_global = db.total_len;
-            j->params.db_pos_base = b0;
-            j->params.db_seq_base = r0;
-            j->best = ng == 1 ? best : (imsame_best *)calloc(q.n_seqs, sizeof(imsame_best));
-            if (ng == 1) shard_main(j);
-            else if (pthread_create(&th[g], NULL, shard_main, j)) terror("Could not launch");
-        }
-        for (int g = 0; g < ng; g++) {
-            if (ng > 1) pthread_join(th[g], NULL);
-            if (jobs[g].rc) {
-                if (jobs[g].rc == IMSAME_EREADSIZE) terror("Read size reached for gapped alignment.");
-                char msg[512];
-                snprintf(msg, sizeof msg, "GPU hot path failed on device %d: %s %s", jobs[g].device,
-                         imsame_gpu_strerror(jobs[g].rc), jobs[g].err);
-                terror(msg);
-            }
-        }
-        if (ng > 1) {
-            /* first accepted hit in the reference's scan order: k-mer end ascending, db position descending */
-            for (uint64_t r = 0; r < q.n_seqs; r++)
-                for (int g = 0; g < ng; g++) {
-                    const imsame_best *c = &jobs[g].best[r];
-                    if (!c->accepted) continue;
-                    if (!best[r].accepted || c->qpos_end < best[r].qpos_end ||
-                        (c->qpos_end == best[r].qpos_end && c->db_pos > best[r].db_pos))
-                        best[r] = *c;
-                }
-            for (int g = 0; g < ng; g++) free(jobs[g].best);
-        }
-        for (int g = 0; g < ng; g++) { free((void *)jobs[g].db.start_pos); free((void *)jobs[g].db.break_pos); }
-        free(jobs);
-        free(th);
-        for (uint64_t r = 0; r < q.n_seqs; r++) accepted += best[r].accepted;
-        if (trace) { fprintf(stderr, "[imsame] align (all shards) %.3f s\n", now_s() - tp); tp = now_s(); }
-
-        if (fout != NULL && accepted > 0) {
-            imsame_ctx *ctx = NULL;
-            int rc = imsame_gpu_create(&ctx, a.device);
-            if (rc) gpu_fail(NULL, rc);
-            uint64_t *ops_off = (uint64_t *)malloc((q.n_seqs + 1) * sizeof(uint64_t));
-            uint32_t *cell = (uint32_t *)malloc(4 * q.n_seqs * sizeof(uint32_t)), *ops = NULL;
-            rc = imsame_gpu_traceback(ctx, &dv, &qv, &p, best, ops_off, &ops, cell);
-            if (rc) gpu_fail(ctx, rc);
-            if (trace) { fprintf(stderr, "[imsame] traceback (GPU) %.3f s\n", now_s() - tp); tp = now_s(); }
-            char *text = (char *)malloc(6 * (2 * (size_t)IMSAME_MAX_READ_SIZE) + 512), hdr[256];
-            for (uint64_t r = 0; r < q.n_seqs; r++) {
-                if (!best[r].accepted) continue;
-                const uint64_t s = best[r].db_seq;
-                const uint32_t xlen = (uint32_t)(db.start_pos[s + 1] - db.start_pos[s]);
-                const uint32_t ylen = (uint32_t)(q.start_pos[r + 1] - q.start_pos[r]);
-                int hl = imsame_format_header(hdr, r, s, best[r].length, best[r].identities, ylen);
-                fwrite(hdr, 1, (size_t)hl, fout);
-                uint64_t tl = imsame_render_alignment(text, db.sequences + db.start_pos[s], xlen,
-                                                      q.sequences + q.start_pos[r], ylen, cell[4 * r], cell[4 * r + 1],
-                                                      ops + ops_off[r], ops_off[r + 1] - ops_off[r]);
-                fwrite(text, 1, (size_t)tl, fout);
-            }
-            if (trace) { fprintf(stderr, "[imsame] render + write %.3f s\n", now_s() - tp); tp = now_s(); }
-            free(text);
-            imsame_gpu_free(ops);
-            free(ops_off);
-            free(cell);
-            imsame_gpu_destroy(ctx);
-        }
+    imsame_job_opts jo;
+    memset(&jo, 0, sizeof jo);
+    jo.n_threads = a.n_threads;
+    jo.minevalue = a.minevalue;
+    jo.mincoverage = a.mincoverage;
+    jo.minidentity = a.minidentity;
+    jo.igap = a.igap;
+    jo.egap = a.egap;
+    jo.gpus = a.gpus;
+    jo.device = a.device;
+    jo.trace = getenv("IMSAME_TRACE") != NULL; /* phase wall times on stderr (not part of the reference's output) */
+    char err[300];
+    int rc = imsame_run_job(&q, &db, &jo, fout, NULL, &accepted, err, sizeof err);
+    if (rc == IMSAME_EREADSIZE) terror("Read size reached for gapped alignment."); /* src/alignmentFunctions.c:155 */
+    if (rc) {
+        char msg[512];
+        snprintf(msg, sizeof msg, "GPU hot path failed: %s%s%s", imsame_gpu_strerror(rc), err[0] ? " / " : "", err);
+        terror(msg);
     }
 
     fprintf(stdout, "[INFO] Alignments computed in %e seconds.\n", now_s() - t0);
@@ -283,7 +167,6 @@ int main(int argc, char **av) {
             (long double)accepted / ((db.n_seqs + q.n_seqs) - accepted));
     fprintf(stdout, "[INFO] Deallocating heap memory.\n");
     if (fout != NULL) fclose(fout);
-    free(best);
     imsame_fasta_free(&db);
     imsame_fasta_free(&q);
     return 0;

@@ -93,6 +93,46 @@ def test_all_vs_all_script(gpu, tmp_path):
         assert hp.parse_align_headers(ref) == hp.parse_align_headers(str(o / "s0-s1.align"))
 
 
+def test_in_process_all_vs_all_equals_the_script(gpu, tmp_path):
+    """bin/IMSAME_allvsall (one process, samples parsed once, reverse complements built in memory) writes
+    byte for byte the files the script produces with 2 IMSAME + 1 revComp process per pair, and keeps the
+    script's resume rule.  Sample 2 is "dirty" (lower case, N, multi-line, '>' inside a header) so that
+    revComp's record-order reversal and letter handling matter."""
+    from imsame_b200 import hostlib as H
+    d, o1, o2 = tmp_path / "samples", tmp_path / "out_script", tmp_path / "out_batch"
+    d.mkdir(); o1.mkdir(); o2.mkdir()
+    pool = H.SynthPool(4001, 3, 30000)
+    for i in range(3):
+        H.write_fasta(str(d / f"s{i}.fasta"), pool.db_reads(i * 1000, 500, 150), 500, 150, "r")
+    reads = pool.db_reads(5000, 300, 150)
+    pool.close()
+    with open(d / "s3.fasta", "wb") as f:
+        f.write(b"text before the first header\n")
+        for r in range(300):
+            b = bytes(reads[r * 150:(r + 1) * 150])
+            if r % 3 == 0:
+                b = b[:40].lower() + b"N" + b[40:]
+            f.write(b">x%d with > inside\n" % r + b[:70] + b"\n" + b[70:] + b"\n")
+    args = [str(d), "0.5", "0.5", "4", "fasta"]
+    subprocess.run([os.path.join(hp.ROOT, "bin", "all_vs_all_metagenomes_IMSAME.sh")] + args + [str(o1)],
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    r = subprocess.run([os.path.join(hp.ROOT, "bin", "IMSAME_allvsall")] + args + [str(o2)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    names = sorted(os.listdir(o1))
+    assert names == sorted(os.listdir(o2)) and len(names) == 12
+    for n in names:
+        assert open(o1 / n, "rb").read() == open(o2 / n, "rb").read(), n
+    assert os.path.getsize(o2 / "s0-s1.align") > 10000 and os.path.getsize(o2 / "s0-s3.align") > 1000
+    assert "12 comparisons of 4 samples" in r.stdout
+    # resume: existing outputs are kept, only the missing one is recomputed
+    os.remove(o2 / "s1-s3.r.align")
+    (o2 / "s0-s1.align").write_bytes(b"kept")
+    r = subprocess.run([os.path.join(hp.ROOT, "bin", "IMSAME_allvsall")] + args + [str(o2)], capture_output=True, text=True)
+    assert "1 comparisons of 4 samples" in r.stdout
+    assert (o2 / "s0-s1.align").read_bytes() == b"kept"
+    assert open(o1 / "s1-s3.r.align", "rb").read() == open(o2 / "s1-s3.r.align", "rb").read()
+
+
 def test_traceback_api_matches_oracle_text(gpu):
     from imsame_b200 import api, hostlib as H
     db, ds, q, qs = sc.ragged_case(17, 2, 50000, 3000, 300, 0.08)
