@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""cfg4 (BASELINE.json configs[3]): all-vs-all over 8 synthetic metagenome samples (100 k reads x 150 bp
+each, shared 40-genome pool), through the reference workflow script (84 processes) and through the
+in-process driver bin/IMSAME_allvsall.  Prints wall times and checks that both produce the same files.
+usage: python tools/allvsall_bench.py [--samples 8] [--reads 100000] [--skip-script]"""
+import argparse, filecmp, os, shutil, subprocess, sys, tempfile, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from imsame_b200 import hostlib as H  # noqa: E402
+ap = argparse.ArgumentParser()
+ap.add_argument("--samples", type=int, default=8)
+ap.add_argument("--reads", type=int, default=100000)
+ap.add_argument("--skip-script", action="store_true")
+a = ap.parse_args()
+d = tempfile.mkdtemp(prefix="imsame_avall_")
+sd, o1, o2 = (os.path.join(d, n) for n in ("samples", "out_script", "out_batch"))
+for p in (sd, o1, o2):
+    os.makedirs(p)
+pool = H.SynthPool(4001, 40, 500_000)
+for s in range(a.samples):
+    H.write_fasta(os.path.join(sd, f"m{s}.fasta"), pool.db_reads(s * a.reads, a.reads, 150), a.reads, 150, "r")
+pool.close()
+args = [sd, "0.5", "0.5", "8", "fasta"]
+t = time.time()
+r = subprocess.run([os.path.join(ROOT, "bin", "IMSAME_allvsall")] + args + [o2], capture_output=True, text=True)
+t_batch = time.time() - t
+print(r.stdout.splitlines()[-1] if r.stdout else r.stderr[-300:])
+print(f"in-process driver: {t_batch:.2f} s wall, rc {r.returncode}")
+if not a.skip_script:
+    t = time.time()
+    subprocess.run([os.path.join(ROOT, "bin", "all_vs_all_metagenomes_IMSAME.sh")] + args + [o1], stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL)
+    t_script = time.time() - t
+    names = sorted(os.listdir(o1))
+    same = names == sorted(os.listdir(o2)) and all(filecmp.cmp(os.path.join(o1, n), os.path.join(o2, n), shallow=False) for n in names)
+    print(f"workflow script ({len(names)} outputs, one process per comparison): {t_script:.2f} s wall; identical files: {same}")
+    print(f"speed-up of the in-process driver: {t_script / t_batch:.1f}x")
+shutil.rmtree(d, ignore_errors=True)
