@@ -296,6 +296,18 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     rec = ctx.fetch(keys.data_ptr(), payload.data_ptr())
     n_accepted = int(rec["accepted"].sum())
+    # self-check of the sharded reduction (N > 1): the band-stepped run with key exchanges must give the
+    # same records as independent shard runs followed by one min/max reduction
+    sharded_check = None
+    if world > 1:
+        from imsame_b200 import sharding
+        k2, p2 = torch.empty_like(keys), torch.empty_like(payload)
+        ctx.run(params, k2.data_ptr(), p2.data_ptr())
+        sharding.reduce_best(k2, p2, dist, lambda kr, kl, pl: ctx.mask_payload(kr.data_ptr(), kl.data_ptr(), pl.data_ptr()))
+        same = bool(torch.equal(k2, keys)) and bool(torch.equal(p2, payload))
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_check = "stepped == unstepped" if int(flag.item()) == 1 else "MISMATCH between stepped and unstepped sharded runs"
 
     # per-kernel device times of the timed steps (CUDA events on the launching stream, inside the library)
     def avg(k):
@@ -365,7 +377,7 @@ def run_ours(args):
                        "l2": "inputs (625 MB packed shard + 1 GB query table) exceed the 126 MB L2"},
             "query_reads_per_s": nq / (ms_step * 1e-3),
             "dp_gcups_per_gpu": gcups, "dp_gcups_total": gcups * world,
-            "accepted_reads": n_accepted,
+            "accepted_reads": n_accepted, "sharded_check": sharded_check,
             "work": {"hits": float(agg[3].item()), "evalue_pass": float(agg[6].item()), "nw_pairs": float(agg[4].item()),
                      "cells": cells_all, "ms_k2": ms_k2_max, "ms_k3": ms_k3_max,
                      "ms_other": max(0.0, ms_step - ms_k2_max - ms_k3_max)},

@@ -210,7 +210,10 @@ class Imsame:
             raise ImsameError(rc, lib().imsame_gpu_last_cuda_error(self._h).decode())
 
     def set_stream(self, cuda_stream_ptr):
-        self._check(lib().imsame_gpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+        """run all work of this context on an existing stream.  torch's default stream has the raw handle 0,
+        which the C ABI reads as "use your own stream": it is passed as cudaStreamLegacy (handle 1) instead, so
+        that the library's kernels and torch / NCCL operations issued on the default stream stay ordered."""
+        self._check(lib().imsame_gpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 1)))
 
     # -- one call: index + scan + NW + selection (src/IMSAME.c:232-281 + :409-467)
     def set_nw_mode(self, mode):

@@ -101,7 +101,8 @@ int imsame_gpu_create(imsame_ctx **ctx, int device);
 void imsame_gpu_destroy(imsame_ctx *ctx);
 const char *imsame_gpu_strerror(int code);
 const char *imsame_gpu_last_cuda_error(const imsame_ctx *ctx);
-/* run all work of this context on an existing cudaStream_t (NULL = own stream) */
+/* run all work of this context on an existing cudaStream_t (NULL = own non-blocking stream; pass
+ * cudaStreamLegacy / cudaStreamPerThread to share a default stream with other libraries) */
 int imsame_gpu_set_stream(imsame_ctx *ctx, void *cuda_stream);
 
 /* ---- one call = src/IMSAME.c:232-281 + :409-467 ------------------------ */
