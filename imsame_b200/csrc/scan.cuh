@@ -97,6 +97,23 @@ struct ParkedWalk {
     uint32_t p, e;
     ExtState st;
 };
+// the per-warp queue is stored field by field (10 arrays of SCAN_QCAP words): consecutive lanes touch
+// consecutive banks (as an array of 40-byte structs every access was a 2-way bank conflict)
+constexpr int PARK_FIELDS = 10;
+__device__ __forceinline__ void park_store(uint32_t (*q)[SCAN_QCAP], int slot, const ParkedWalk &w) {
+    q[0][slot] = w.p; q[1][slot] = w.e;
+    q[2][slot] = (uint32_t)w.st.phase; q[3][slot] = (uint32_t)w.st.t; q[4][slot] = (uint32_t)w.st.run;
+    q[5][slot] = (uint32_t)w.st.best; q[6][slot] = (uint32_t)w.st.pos_f; q[7][slot] = (uint32_t)w.st.idn2;
+    q[8][slot] = (uint32_t)w.st.fmax; q[9][slot] = (uint32_t)w.st.bmax;
+}
+__device__ __forceinline__ ParkedWalk park_load(const uint32_t (*q)[SCAN_QCAP], int slot) {
+    ParkedWalk w;
+    w.p = q[0][slot]; w.e = q[1][slot];
+    w.st.phase = (int)q[2][slot]; w.st.t = (int)q[3][slot]; w.st.run = (int)q[4][slot];
+    w.st.best = (int)q[5][slot]; w.st.pos_f = (int)q[6][slot]; w.st.idn2 = (int)q[7][slot];
+    w.st.fmax = (int)q[8][slot]; w.st.bmax = (int)q[9][slot];
+    return w;
+}
 
 __device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, uint32_t p, uint32_t e,
                                            const ExtState &st, unsigned long long &c_pass,
@@ -120,19 +137,19 @@ __device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, ui
 
 // finish `count` (<= 32) parked walks, one per lane
 __device__ __forceinline__ void drain_parked(const ScanArgs &a, uint32_t q_inv, const uint32_t *s_lut,
-                                             const ParkedWalk *q, int count, int lane, unsigned long long &c_pass,
-                                             unsigned long long &c_anom) {
+                                             const uint32_t (*q)[SCAN_QCAP], int first, int count, int lane,
+                                             unsigned long long &c_pass, unsigned long long &c_anom) {
     ParkedWalk w;
     w.st.phase = 2;
     w.p = w.e = 0;
-    if (lane < count) w = q[lane];
+    if (lane < count) w = park_load(q, first + lane);
     while (__any_sync(0xffffffffu, w.st.phase < 2))
         if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e);
     if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.st, c_pass, c_anom);
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
-    __shared__ ParkedWalk s_park[SCAN_WARPS][SCAN_QCAP];
+    __shared__ uint32_t s_park[SCAN_WARPS][PARK_FIELDS][SCAN_QCAP];
     __shared__ uint32_t s_excl[SCAN_WARPS][33];
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
     __shared__ uint32_t s_xs[SCAN_WARPS][32];
@@ -214,21 +231,22 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                 const unsigned park = __ballot_sync(0xffffffffu, unfinished);
                 if (park) {
                     if (unfinished) {
-                        ParkedWalk &w = s_park[warp][n_parked + __popc(park & ((1u << lane) - 1u))];
+                        ParkedWalk w;
                         w.p = half ? pb : pa; w.e = half ? eb : ea; w.st = half ? stb : sta;
+                        park_store(s_park[warp], n_parked + __popc(park & ((1u << lane) - 1u)), w);
                     }
                     n_parked += __popc(park);
                     __syncwarp();
                     if (n_parked >= 32) {
                         n_parked -= 32;
-                        drain_parked(a, q_inv, s_lut, &s_park[warp][n_parked], 32, lane, c_pass, c_anom);
+                        drain_parked(a, q_inv, s_lut, s_park[warp], n_parked, 32, lane, c_pass, c_anom);
                         __syncwarp();
                     }
                 }
             }
         }
     }
-    if (n_parked) drain_parked(a, q_inv, s_lut, &s_park[warp][0], n_parked, lane, c_pass, c_anom);
+    if (n_parked) drain_parked(a, q_inv, s_lut, s_park[warp], 0, n_parked, lane, c_pass, c_anom);
     // counters: warp-reduce then one atomic per warp
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
