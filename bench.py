@@ -248,7 +248,10 @@ def run_ours(args):
 
     ctx = api.Imsame(local)
     ctx.set_nw_mode(args.nw_mode)
-    stream = torch.cuda.current_stream()
+    # one real (non-default) stream for everything: the library's kernels, torch ops and the NCCL reductions
+    # issued through torch are ordered on it, and stream attributes (the scan's L2 window) can be set on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")
     payload = torch.empty(nq, dtype=torch.int64, device="cuda")
