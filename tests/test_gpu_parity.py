@@ -57,7 +57,8 @@ def test_nw_batch_packed_kernel_matches_oracle_and_generic(gpu):
     rng = np.random.default_rng(77)
     B = np.frombuffer(b"ACGT", dtype=np.uint8)
     xs, ys = sc.random_pairs(15, 1800, max_len=257)
-    for xl, yl in ((256, 257), (250, 250), (256, 256), (2, 257), (256, 2), (2, 2), (255, 33), (33, 255), (200, 17)):
+    for xl, yl in ((256, 257), (250, 250), (256, 256), (2, 257), (256, 2), (2, 2), (255, 33), (33, 255), (200, 17),
+                   (512, 200), (400, 257), (511, 150)):
         for rep in range(6):
             x = B[rng.integers(0, 4 if rep < 4 else 2, size=xl)]
             y = x[:yl].copy() if (rep % 2 and yl <= xl) else B[rng.integers(0, 4 if rep < 4 else 2, size=yl)]
@@ -73,6 +74,23 @@ def test_nw_batch_packed_kernel_matches_oracle_and_generic(gpu):
             if len(xs[i]) < 2 or len(ys[i]) < 2:
                 continue
             assert tuple(int(v) for v in got[i]) == _oracle_nw(lib, xs[i], ys[i], igap, egap), (i, len(xs[i]), len(ys[i]), igap, egap)
+
+
+def test_read_longer_than_the_scan_limit_is_refused(gpu):
+    """documented implementation limit: a read of more than 32 767 bases -> IMSAME_ELIMIT, not a wrong answer"""
+    from imsame_b200 import api
+    rng = np.random.default_rng(9)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    long_read = B[rng.integers(0, 4, size=40000)]
+    short = B[rng.integers(0, 4, size=300)]
+    seq = np.concatenate([long_read, short])
+    start = np.array([0, 40000, 40300], dtype=np.uint64)
+    with pytest.raises(api.ImsameError) as e:
+        gpu.align((seq, start), (short, np.array([0, 300], dtype=np.uint64)), api.make_params(n_threads=1))
+    assert e.value.code == -7
+    out, _ = gpu.align((short, np.array([0, 300], dtype=np.uint64)), (short, np.array([0, 300], dtype=np.uint64)),
+                       api.make_params(n_threads=1))
+    assert int(out["accepted"].sum()) == 1  # the context is still usable
 
 
 def test_packed_and_generic_kernels_give_the_same_records(gpu):
