@@ -334,9 +334,18 @@ def run_ours(args):
         for it in range(args.e2e_steps + 1):
             barrier()
             t0 = time.perf_counter()
-            out, st = ctx2.align((db_pin.array, ds), (q_pin.array, qs), params)
-            if world > 1:
-                pass  # the sharded e2e figure is reported per rank: reductions are timed in `value`
+            if world == 1:
+                out, st = ctx2.align((db_pin.array, ds), (q_pin.array, qs), params)
+            else:
+                # the same public calls a sharded caller makes: upload + pack + query table, upload + pack
+                # of the shard, band-stepped run with the key exchange, owner's payload, records to the host
+                ctx2.set_query((q_pin.array, qs), params)
+                ctx2.set_db((db_pin.array, ds))
+                st = ctx2.run_stepped(params, keys.data_ptr(), payload.data_ptr(), exchange=exchange, exchange_every=2)
+                dist.all_reduce(payload, op=dist.ReduceOp.MAX)
+                out = ctx2.fetch(keys.data_ptr(), payload.data_ptr())
+                st["h2d_bytes"] = int(nd * L + nq * L)
+                st["d2h_bytes"] = int(16 * nq)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if it > 0:
@@ -349,7 +358,10 @@ def run_ours(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * nq / float(te.item()), "unit": "reads/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3,
-               "what": "imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records",
+               "what": ("imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records"
+                        if world == 1 else
+                        "per rank: set_query + set_db (pinned host ASCII reads -> H2D -> pack -> query table) -> band-stepped run "
+                        "with NCCL key exchange -> owner payload reduction -> D2H records"),
                "device_phases_ms": e2e_phases}
 
     if rank == 0:
