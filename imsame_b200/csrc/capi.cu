@@ -344,6 +344,7 @@ int launch_nwp(imsame_ctx *ctx, NwArgs a) {
         ctx->nwp_grid[C] = std::max(1, per_sm) * ctx->n_sm;
     }
     a.s_class = C;
+    a.one = 1;
     nwp_kernel<2 * C><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     ctx->k3_launches++;

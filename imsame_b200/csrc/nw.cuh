@@ -43,6 +43,7 @@ struct NwArgs {
     // read, all its later candidates are pruned by the key comparison below instead of aligned.
     const uint32_t *range;
     int check_class;  // 1: unsorted explicit pairs (nw_batch / traceback): skip other classes here
+    int one;          // 1, as a run-time value (nwp_core.cuh: pw_row)
     // TB = true only (K4, winners-only traceback): back-pointer codes per cell
     uint16_t *tb;              // codes of pair idx start at tb + tb_off[idx]
     const uint64_t *tb_off;

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
     const unsigned hmask = 0xFFFFu << (16 * half);
     uint8_t *sx = sx_all[warp * 2 + half];
     const uint32_t r_begin = a.range[0], r_end = a.range[1];
-    const PwK k = pw_consts(a.igap, a.egap);
+    const PwK k = pw_consts(a.igap, a.egap, a.one);
     for (int e = threadIdx.x; e < NWP_TBL * 8; e += NWP_THREADS) {
         const PwE4 v = pw_e4(k, (uint32_t)(e >> 3));
 #pragma unroll
@@ -142,6 +142,11 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
             IMS_PW_STEP(t + 1, L.r1, L.r0)
         }
 #undef IMS_PW_STEP
+        // the last row: lane hl wrote it at step X1 - 1 + hl
+        if (have && hl < nl) {
+            if ((X1 - 1 + hl) & 1) pw_last_row<S>(L, L.r0, j0, X1, Y1);
+            else pw_last_row<S>(L, L.r1, j0, X1, Y1);
+        }
         // reduction of the best border cell over the half warp ("last in row-major order" on ties)
         int bz = (have && hl < nl) ? L.bz : (int)0x80000000, bw = L.bw, bi = L.bi, bj = L.bj;
 #pragma unroll

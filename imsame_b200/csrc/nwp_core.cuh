@@ -63,10 +63,12 @@ struct PwK {
     int negl;     // "-inf" L candidate at j = 1 (:446)
     int ds_mis;   // diagonal constant on mismatch: D0 = T'[i-1][j-1] + ds  (ds_match = ds_mis + 1)
     int sb_mis;   // after the maximum: T'[i][j] = (m & ~prio) + sb            (sb_match = sb_mis + 8 * SC1)
+    int one;      // 1, opaque to the compiler on the device (pw_row: diagonal add as IMAD)
 };
 
-IMS_HD PwK pw_consts(int igap, int egap) {
+IMS_HD PwK pw_consts(int igap, int egap, int one = 1) {
     PwK k;
+    k.one = one;
     k.B = (igap + egap) * PW_SC1 + 2 * PW_LEN1 + PW_PR1;
     k.step = egap * PW_SC1 + PW_LEN1;
     k.negz = -2046 * PW_SC1;
@@ -191,7 +193,16 @@ IMS_HD void pw_row(PwLane<S> &L, const PwRow<S> &P1, PwRow<S> &P2, const PwLink 
         mfz = up ? (r2 & PW_SMASK) : mfz;
         lw = up ? r2 : lw;
         const int d = P1.h[c];
-        const int m = max3i(d + e.ds[c & 3], lw, L.rw[c]);
+#if defined(__CUDA_ARCH__)
+        // diagonal candidate as a multiply-add with a run-time 1 (FMA pipe): ptxas then keeps the 3-input
+        // maximum as ONE VIMNMX3 instead of fusing the add into a VIADDMNMX + VIMNMX pair (two ALU-pipe
+        // instructions; the ALU pipe is what limits this kernel)
+        int d0;
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d0) : "r"(d), "r"(k.one), "r"(e.ds[c & 3]));
+#else
+        const int d0 = d + e.ds[c & 3];
+#endif
+        const int m = max3i(d0, lw, L.rw[c]);
         lw += k.step;
         // column maximum of column j-1 absorbs T[i-2][j-1], strictly greater only (:476-480)
         const bool uc = o2 > L.mck[c];
@@ -207,14 +218,9 @@ IMS_HD void pw_row(PwLane<S> &L, const PwRow<S> &P1, PwRow<S> &P2, const PwLink 
     out.b = t2;
     out.mfz = mfz;
     out.lw = lw;
-    // best border cell (:481-484, >= : last in row-major order wins)
-    if (i == X1) {
-#pragma unroll
-        for (int c = 0; c < S; c++)
-            if (j0 + c <= Y1 && P2.h[c + 1] >= L.bz) {
-                L.bw = P2.h[c + 1]; L.bz = P2.h[c + 1] & PW_SMASK; L.bi = i; L.bj = j0 + c;
-            }
-    } else if (owns_last) {
+    // best border cell (:481-484, >= : last in row-major order wins): the last column of every row but
+    // the last one here; the last row is scanned once per pair from the row history (pw_last_row)
+    if (owns_last && i != X1) {
         int lt = P2.h[S];
         switch (cl) {
 #define IMS_CASE(C) case C: if (C < S) lt = P2.h[(C < S ? C : 0) + 1]; break;
@@ -225,6 +231,18 @@ IMS_HD void pw_row(PwLane<S> &L, const PwRow<S> &P1, PwRow<S> &P2, const PwLink 
         }
         if (lt >= L.bz) { L.bw = lt; L.bz = lt & PW_SMASK; L.bi = i; L.bj = Y1; }
     }
+}
+
+// After the lane's last step its row history still holds row X1 (in the history that was written last:
+// r1 when that step was even, r0 when odd).  All lanes scan their part of the last row at once, after
+// the step loop, instead of one lane per step inside it.
+template <int S>
+IMS_HD void pw_last_row(PwLane<S> &L, const PwRow<S> &row, int j0, int X1, int Y1) {
+#pragma unroll
+    for (int c = 0; c < S; c++)
+        if (j0 + c <= Y1 && row.h[c + 1] >= L.bz) {
+            L.bw = row.h[c + 1]; L.bz = row.h[c + 1] & PW_SMASK; L.bi = X1; L.bj = j0 + c;
+        }
 }
 
 // stored word -> score / statistics

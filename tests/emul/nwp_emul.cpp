@@ -56,6 +56,10 @@ static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, in
             outs[l] = out;
         }
     }
+    for (int l = 0; l < nl; l++) {
+        if ((X1 - 1 + l) & 1) pw_last_row<S>(lanes[l], lanes[l].r0, l * S + 1, X1, Y1);
+        else pw_last_row<S>(lanes[l], lanes[l].r1, l * S + 1, X1, Y1);
+    }
     bool have = false; int bz = 0, bw = 0, bi = 0, bj = 0;
     for (int l = 0; l < nl; l++) {
         const PwLane<S> &L = lanes[l];
