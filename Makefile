@@ -39,9 +39,9 @@ bin/IMSAME_allvsall: imsame_b200/host/imsame_allvsall_main.c $(JOB_SRC) $(OUT)/l
 	$(CC) $(CFLAGS) -fPIE imsame_b200/host/imsame_allvsall_main.c imsame_b200/host/imsame_job.c -L$(OUT) -limsame_host -limsame_gpu \
 	    -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lpthread -lm -o $@
 
-bin/revComp: imsame_b200/host/revcomp_main.c
+bin/revComp: imsame_b200/host/revcomp_main.c $(OUT)/libimsame_host.so
 	@mkdir -p bin
-	$(CC) $(CFLAGS) -fPIE imsame_b200/host/revcomp_main.c -o $@
+	$(CC) $(CFLAGS) -fPIE imsame_b200/host/revcomp_main.c -L$(OUT) -limsame_host -Wl,-rpath,'$$ORIGIN/../$(OUT)' -lm -o $@
 
 tools: tools/int_peak
 tools/int_peak: tools/int_peak.cu

@@ -184,6 +184,18 @@ def test_sharded_database_equals_whole(gpu):
     assert merged == gpu_records(whole)
 
 
+@pytest.mark.parametrize("divergence,identity", [(0.05, 0.95), (0.15, 0.80), (0.25, 0.70), (0.30, 0.70)])
+def test_cfg5_low_identity_sweep(gpu, divergence, identity):
+    """BASELINE.json configs[4] at k = 12 (the only k the reference has): divergent queries, identity
+    thresholds 70-95 % -- dense candidate load, many near-threshold alignments with gaps"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(5005, 4, 100000, 150, 20000, 1500, divergence)
+    want, _ = oracle_records(db, ds, q, qs, 4, identity=identity, coverage=0.5)
+    out, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4, min_identity=identity, min_coverage=0.5))
+    assert gpu_records(out) == want
+    assert len(want) > (20 if divergence >= 0.25 else 300)
+
+
 def test_cfg1_full_size(gpu):
     """BASELINE.json configs[0]: 10k x 150bp reads vs 100k-read metagenome, defaults"""
     from imsame_b200 import api
