@@ -193,7 +193,7 @@ def test_cfg5_low_identity_sweep(gpu, divergence, identity):
     want, _ = oracle_records(db, ds, q, qs, 4, identity=identity, coverage=0.5)
     out, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4, min_identity=identity, min_coverage=0.5))
     assert gpu_records(out) == want
-    assert len(want) > (20 if divergence >= 0.25 else 300)
+    assert len(want) > (10 if divergence >= 0.25 else 300)
 
 
 def test_cfg1_full_size(gpu):
