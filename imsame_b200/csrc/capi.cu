@@ -1060,9 +1060,9 @@ struct PairBatch {
     unsigned long long *dcells = nullptr;
     std::vector<uint32_t> xs, ys;
     explicit PairBatch(imsame_ctx *c) : ctx(c) {}
-    ~PairBatch() {
-        dev_free(xpk); dev_free(ypk); dev_free(dxs); dev_free(dys); dev_free(dsmall); dev_free(dp); dev_free(dr);
-        dev_free(dz); dev_free(dcells);
+    ~PairBatch() {  // blocks go back to the context's pool: the next batch / call reuses them
+        pool_free(ctx, xpk); pool_free(ctx, ypk); pool_free(ctx, dxs); pool_free(ctx, dys); pool_free(ctx, dsmall);
+        pool_free(ctx, dp); pool_free(ctx, dr); pool_free(ctx, dz); pool_free(ctx, dcells);
     }
     // X[i]/Y[i] ASCII reads -> packed device arrays + pair list (r = s = i)
     int upload(uint32_t n_pairs, const unsigned char *const *X, const uint32_t *xlen, const unsigned char *const *Y,
@@ -1089,10 +1089,10 @@ struct PairBatch {
         }
         int rc;
         const uint64_t xw = (xt + 15) / 16 + PAD_WORDS, yw = (yt + 15) / 16 + PAD_WORDS;
-        if ((rc = dev_alloc(ctx, &xpk, xw)) || (rc = dev_alloc(ctx, &ypk, yw)) ||
-            (rc = dev_alloc(ctx, &dxs, (uint64_t)n + 1)) || (rc = dev_alloc(ctx, &dys, (uint64_t)n + 1)) ||
-            (rc = dev_alloc(ctx, &dsmall, 16)) || (rc = dev_alloc(ctx, &dp, n)) || (rc = dev_alloc(ctx, &dr, n)) ||
-            (rc = dev_alloc(ctx, &dz, 2 * IMSAME_MAX_READ_SIZE + 1)) || (rc = dev_alloc(ctx, &dcells, 4)))
+        if ((rc = pool_alloc(ctx, &xpk, xw)) || (rc = pool_alloc(ctx, &ypk, yw)) ||
+            (rc = pool_alloc(ctx, &dxs, (uint64_t)n + 1)) || (rc = pool_alloc(ctx, &dys, (uint64_t)n + 1)) ||
+            (rc = pool_alloc(ctx, &dsmall, 16)) || (rc = pool_alloc(ctx, &dp, n)) || (rc = pool_alloc(ctx, &dr, n)) ||
+            (rc = pool_alloc(ctx, &dz, 2 * IMSAME_MAX_READ_SIZE + 1)) || (rc = pool_alloc(ctx, &dcells, 4)))
             return rc;
         CK(cudaMemsetAsync(xpk, 0, xw * 4, ctx->stream));
         CK(cudaMemsetAsync(ypk, 0, yw * 4, ctx->stream));
@@ -1216,10 +1216,14 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
         uint16_t *d_tb = nullptr;
         uint64_t *d_tboff = nullptr, *d_opoff = nullptr;
         uint32_t *d_str = nullptr, *d_ops = nullptr, *d_nops = nullptr, *d_end = nullptr;
-        auto cleanup = [&]() { dev_free(d_tb); dev_free(d_tboff); dev_free(d_opoff); dev_free(d_str); dev_free(d_ops); dev_free(d_nops); dev_free(d_end); };
-        if ((rc = dev_alloc(ctx, &d_tb, tb_elems)) || (rc = dev_alloc(ctx, &d_tboff, nb)) || (rc = dev_alloc(ctx, &d_opoff, nb)) ||
-            (rc = dev_alloc(ctx, &d_str, nb)) || (rc = dev_alloc(ctx, &d_ops, op_elems)) || (rc = dev_alloc(ctx, &d_nops, nb)) ||
-            (rc = dev_alloc(ctx, &d_end, 2ull * nb))) { cleanup(); return rc; }
+        // recycled blocks (pool): a cudaMalloc + cudaFree of the 3 GB table per batch cost 0.1 - 3 s each
+        auto cleanup = [&]() {
+            pool_free(ctx, d_tb); pool_free(ctx, d_tboff); pool_free(ctx, d_opoff); pool_free(ctx, d_str); pool_free(ctx, d_ops);
+            pool_free(ctx, d_nops); pool_free(ctx, d_end);
+        };
+        if ((rc = pool_alloc(ctx, &d_tb, tb_elems)) || (rc = pool_alloc(ctx, &d_tboff, nb)) || (rc = pool_alloc(ctx, &d_opoff, nb)) ||
+            (rc = pool_alloc(ctx, &d_str, nb)) || (rc = pool_alloc(ctx, &d_ops, op_elems)) || (rc = pool_alloc(ctx, &d_nops, nb)) ||
+            (rc = pool_alloc(ctx, &d_end, 2ull * nb))) { cleanup(); return rc; }
         cudaMemcpyAsync(d_tboff, tb_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(d_opoff, op_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
         cudaMemcpyAsync(d_str, strides.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream);

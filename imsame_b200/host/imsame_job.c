@@ -7,6 +7,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 static double now_s(void) {
     struct timespec t;
@@ -138,21 +141,54 @@ int imsame_run_job(const imsame_fasta *qf, const imsame_fasta *dbf, const imsame
             if (err && errlen) snprintf(err, errlen, "%s", imsame_gpu_last_cuda_error(ctx));
         } else {
             if (o->trace) { fprintf(stderr, "[imsame] traceback (GPU) %.3f s\n", now_s() - tp); tp = now_s(); }
-            char *text = (char *)malloc(6 * (2 * (size_t)IMSAME_MAX_READ_SIZE) + 512), hdr[256];
-            for (uint64_t r = 0; r < q.n_seqs; r++) {
-                if (!best[r].accepted) continue;
-                const uint64_t s = best[r].db_seq;
-                const uint32_t xlen = (uint32_t)(db.start_pos[s + 1] - db.start_pos[s]);
-                const uint32_t ylen = (uint32_t)(q.start_pos[r + 1] - q.start_pos[r]);
-                int hl = imsame_format_header(hdr, r, s, best[r].length, best[r].identities, ylen);
-                fwrite(hdr, 1, (size_t)hl, fout);
-                uint64_t tl = imsame_render_alignment(text, db.sequences + db.start_pos[s], xlen,
-                                                      q.sequences + q.start_pos[r], ylen, cell[4 * r], cell[4 * r + 1],
-                                                      ops + ops_off[r], ops_off[r + 1] - ops_off[r]);
-                fwrite(text, 1, (size_t)tl, fout);
+            /* records are rendered by all host threads, each into its own buffer for a contiguous range of
+               reads, and written in ascending read order (the reference's order with -n_threads 1) */
+            int nt = 1;
+#ifdef _OPENMP
+            nt = omp_get_max_threads();
+#endif
+            if (nt > 64) nt = 64;
+            if ((uint64_t)nt > q.n_seqs) nt = (int)q.n_seqs;
+            char *bufs[64];
+            size_t lens[64];
+            int failed = 0;
+            memset(bufs, 0, sizeof bufs);
+            memset(lens, 0, sizeof lens);
+#pragma omp parallel for schedule(static, 1) num_threads(nt)
+            for (int t = 0; t < nt; t++) {
+                const uint64_t r0 = q.n_seqs * (uint64_t)t / (uint64_t)nt, r1 = q.n_seqs * (uint64_t)(t + 1) / (uint64_t)nt;
+                const size_t rec_max = 6 * (2 * (size_t)IMSAME_MAX_READ_SIZE) + 768;
+                size_t cap = 1 << 20, len = 0;
+                char *buf = (char *)malloc(cap);
+                for (uint64_t r = r0; r < r1 && buf; r++) {
+                    if (!best[r].accepted) continue;
+                    if (cap - len < rec_max) {
+                        cap = cap * 2 + rec_max;
+                        char *nb2 = (char *)realloc(buf, cap);
+                        if (!nb2) { free(buf); buf = NULL; break; }
+                        buf = nb2;
+                    }
+                    const uint64_t s = best[r].db_seq;
+                    const uint32_t xlen = (uint32_t)(db.start_pos[s + 1] - db.start_pos[s]);
+                    const uint32_t ylen = (uint32_t)(q.start_pos[r + 1] - q.start_pos[r]);
+                    len += (size_t)imsame_format_header(buf + len, r, s, best[r].length, best[r].identities, ylen);
+                    len += (size_t)imsame_render_alignment(buf + len, db.sequences + db.start_pos[s], xlen,
+                                                           q.sequences + q.start_pos[r], ylen, cell[4 * r], cell[4 * r + 1],
+                                                           ops + ops_off[r], ops_off[r + 1] - ops_off[r]);
+                }
+                if (!buf) {
+#pragma omp atomic write
+                    failed = 1;
+                }
+                bufs[t] = buf;
+                lens[t] = len;
             }
+            for (int t = 0; t < nt; t++) {
+                if (!failed && bufs[t]) fwrite(bufs[t], 1, lens[t], fout);
+                free(bufs[t]);
+            }
+            if (failed) rc = IMSAME_ENOMEM;
             if (o->trace) { fprintf(stderr, "[imsame] render + write %.3f s\n", now_s() - tp); tp = now_s(); }
-            free(text);
         }
         imsame_gpu_free(ops);
         free(ops_off);
