@@ -149,7 +149,18 @@ void reset_timing(imsame_ctx *ctx) {
 
 template <typename T>
 int dev_alloc(imsame_ctx *ctx, T **p, uint64_t count) {
-    CK(cudaMalloc((void **)p, std::max<uint64_t>(count, 1) * sizeof(T)));
+    const size_t bytes = (size_t)std::max<uint64_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void **)p, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->free_blocks.empty()) {  // give the recycled blocks back and retry
+        cudaGetLastError();
+        for (auto &b : ctx->free_blocks) cudaFree(b.p);
+        ctx->free_blocks.clear();
+        e = cudaMalloc((void **)p, bytes);
+    }
+    if (e != cudaSuccess) {
+        ctx->cuda_err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? IMSAME_ENOMEM : IMSAME_ECUDA;
+    }
     return IMSAME_OK;
 }
 template <typename T>
@@ -488,6 +499,7 @@ int imsame_gpu_create(imsame_ctx **out, int device) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMSAME_ECUDA; }
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, SCAN_THREADS_K2, 0);
+    if (const char *e = getenv("IMSAME_SCAN_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
     ctx->scan_grid = std::max(1, per_sm) * ctx->n_sm;
     *out = ctx;
     return IMSAME_OK;
