@@ -100,6 +100,17 @@ static void parse_args(int argc, char **av, cli_args *a) {
     }
 }
 
+/* the CUDA context (0.8 s to create) comes up on its own thread while the FASTA files are parsed */
+typedef struct {
+    int device, rc;
+    imsame_ctx *ctx;
+} ctx_boot;
+static void *ctx_boot_main(void *arg) {
+    ctx_boot *b = (ctx_boot *)arg;
+    b->rc = imsame_gpu_create(&b->ctx, b->device);
+    return NULL;
+}
+
 int main(int argc, char **av) {
     cli_args a;
     parse_args(argc, av, &a);
@@ -113,6 +124,12 @@ int main(int argc, char **av) {
     double t0 = now_s();
     fprintf(stdout, "[INFO] Init. quick table\n");
     if (a.gpus < 1) a.gpus = 1;
+    ctx_boot boot;
+    pthread_t boot_thread;
+    int booting = 0;
+    memset(&boot, 0, sizeof boot);
+    boot.device = a.device;
+    if (a.gpus == 1 && a.n_threads > 0) booting = pthread_create(&boot_thread, NULL, ctx_boot_main, &boot) == 0;
     fprintf(stdout, "[INFO] Initialization took %e seconds \n", now_s() - t0);
 
     fprintf(stdout, "[INFO] Loading database\n");
@@ -150,7 +167,13 @@ int main(int argc, char **av) {
     jo.device = a.device;
     jo.trace = getenv("IMSAME_TRACE") != NULL; /* phase wall times on stderr (not part of the reference's output) */
     char err[300];
-    int rc = imsame_run_job(&q, &db, &jo, fout, NULL, &accepted, err, sizeof err);
+    imsame_ctx *ctx = NULL;
+    if (booting) {
+        pthread_join(boot_thread, NULL);
+        ctx = boot.rc == IMSAME_OK ? boot.ctx : NULL; /* on failure run_job tries again and reports */
+    }
+    int rc = imsame_run_job(&q, &db, &jo, fout, ctx ? &ctx : NULL, &accepted, err, sizeof err);
+    if (ctx) imsame_gpu_destroy(ctx);
     if (rc == IMSAME_EREADSIZE) terror("Read size reached for gapped alignment."); /* src/alignmentFunctions.c:155 */
     if (rc) {
         char msg[512];
