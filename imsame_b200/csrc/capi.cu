@@ -278,10 +278,10 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
         if ((rc = dev_alloc(ctx, &ctx->d_nmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_lmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_imin, 2 * IMSAME_MAX_READ_SIZE + 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_lut, 2 * EXT_LUT3_SIZE))) return rc;
-        std::vector<uint32_t> lut(2 * EXT_LUT3_SIZE);
+        if ((rc = dev_alloc(ctx, &ctx->d_lut, EXT_LUT3_SIZE))) return rc;
+        std::vector<uint32_t> lut(EXT_LUT3_SIZE);
         build_ext_lut3(lut.data());
-        CK(cudaMemcpy(ctx->d_lut, lut.data(), 2 * EXT_LUT3_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_lut, lut.data(), EXT_LUT3_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     if (want_cap > ctx->hcap) {
         dev_free(ctx->hkeys); dev_free(ctx->hvals);

@@ -167,33 +167,36 @@ IMS_HD int extend_hit_lut(const uint16_t *lut, const uint32_t *dpk, const uint32
 // 240 instructions per window, two thirds of them on 64-bit address/shift/compress work).
 namespace imsame {
 
-// Walk table of the scan kernel: one 64-bit entry per (entry score row, 8 mismatch bits).
+// Walk table of the scan kernel: one 32-bit entry per (entry score row, 8 mismatch bits).
 // The walk state is ONE word  run = (score << 15) | steps_done  and the running maximum of
 // the reference's `if (high <= score) { pos = cur; high = score; }` (:324,347) is ONE word
-// best = (high << 15) | (1-based step of its last occurrence): later steps have larger step
+// best = ((high + 1) << 15) | (1-based step of its last occurrence): later steps have larger step
 // numbers, so "replace when >=" is a plain integer maximum of such keys.  Per 8 steps:
-//     best = max(best, run + entry.x);   run += entry.y;
-//   entry.x = (max prefix score relative to the entry score << 15) + step of its last occurrence
-//   entry.y = (score change << 15) + steps executed
-// When the score reaches 0 inside the 8 steps the walk ends (:318,340): entry.y then sets the
-// score to exactly 0 and counts only the executed steps, and row 0 is absorbing (entry.x very
-// negative, entry.y = 0), so a finished walk needs no predicate.  Row 9 = "9 or more".
+//     best = max(best, run + X(entry));   run += Y(entry) - (8 << 15);
+//   X = ((max prefix score relative to the entry score + 1) << 15) + step of its last occurrence
+//   Y = ((score change + 8) << 15) + steps executed
+// Both come out of the entry with one rotate + two masks (fields: steps bits 0-3, step of the
+// maximum bits 8-11, change + 8 bits 15-19, maximum + 1 bits 23-26).  The first version kept X and Y
+// as a 64-bit pair: 32 lanes reading random 8-byte entries cost 6.4 shared-memory wavefronts per
+// lookup against 3.5 for 4-byte entries, and the scan kernel runs at 92 % of the L1 data pipe.
+// When the score reaches 0 inside the 8 steps the walk ends (:318,340): the entry then sets the
+// score to exactly 0 and counts only the executed steps, and row 0 is absorbing (X never wins,
+// Y changes nothing), so a finished walk needs no predicate.  Row 9 = "9 or more".
 // Matches are not counted: every step is +-1, so matches = (steps + score_end - score_start) / 2.
 constexpr int EXT_ROWS3 = 10;
-constexpr int EXT_LUT3_SIZE = EXT_ROWS3 * 256;  // entries of two uint32
+constexpr int EXT_LUT3_SIZE = EXT_ROWS3 * 256;  // uint32 entries
 constexpr int EXT_SC_SHIFT = 15;                // reads of up to 32767 bases
 constexpr uint32_t EXT_POS_MASK = (1u << EXT_SC_SHIFT) - 1u;
 constexpr uint32_t EXT_MAX_READ = EXT_POS_MASK;
+constexpr int EXT_BEST_BIAS = 1 << EXT_SC_SHIFT;  // `best` words carry high + 1
+constexpr uint32_t EXT_X_MASK = 0x0007800Fu, EXT_Y_MASK = 0x000F800Fu;
 
-inline void build_ext_lut3(uint32_t *lut /* 2 * EXT_LUT3_SIZE */) {
+inline void build_ext_lut3(uint32_t *lut /* EXT_LUT3_SIZE */) {
     for (int row = 0; row < EXT_ROWS3; row++)
         for (uint32_t m = 0; m < 256; m++) {
-            int32_t x, y;
-            if (row == 0) {
-                x = -(1 << 30);
-                y = 0;
-            } else {
-                int run = 0, rmax = -100, amax = 0, steps = 0;
+            int rmax1 = 0, amax = 0, delta8 = 8, steps = 0;  // row 0: absorbing
+            if (row > 0) {
+                int run = 0, rmax = -100;
                 bool term = false;
                 for (int t = 0; t < 8; t++) {
                     run += ((m >> t) & 1) ? -1 : 1;
@@ -201,11 +204,10 @@ inline void build_ext_lut3(uint32_t *lut /* 2 * EXT_LUT3_SIZE */) {
                     if (run >= rmax) { rmax = run; amax = t + 1; }
                     if (row < 9 && row + run <= 0) { term = true; break; }
                 }
-                x = rmax * (1 << EXT_SC_SHIFT) + amax;
-                y = (term ? -row : run) * (1 << EXT_SC_SHIFT) + steps;
+                rmax1 = rmax + 1;
+                delta8 = (term ? -row : run) + 8;
             }
-            lut[2 * (row * 256 + m)] = (uint32_t)x;
-            lut[2 * (row * 256 + m) + 1] = (uint32_t)y;
+            lut[row * 256 + m] = (uint32_t)steps | ((uint32_t)amax << 8) | ((uint32_t)delta8 << 15) | ((uint32_t)rmax1 << 23);
         }
 }
 
@@ -272,18 +274,21 @@ IMS_HD void ext_init(ExtState &s, uint32_t p, uint32_t e, uint32_t xs, uint32_t 
     s.bmax = bq < bd ? bq : bd;
     s.t = 0;
     s.run = K << EXT_SC_SHIFT;   // score = 12 (48 / POINT), :300
-    s.best = K << EXT_SC_SHIFT;  // high_right = 12, no step yet
+    s.best = (K << EXT_SC_SHIFT) + EXT_BEST_BIAS;  // high_right = 12, no step yet
     s.pos_f = 0;
     s.idn2 = 0;
     s.phase = s.fmax > 0 ? 0 : (s.bmax > 0 ? 1 : 2);
 }
 
-#if defined(__CUDA_ARCH__)
-#define IMS_LUT3(lut, i) (reinterpret_cast<const uint2 *>(lut)[i])
-#else
-struct ExtPair { uint32_t x, y; };
-#define IMS_LUT3(lut, i) (ExtPair{(lut)[2 * (i)], (lut)[2 * (i) + 1]})
-#endif
+// one table step (8 bases) of a walk
+IMS_HD void ext_step(const uint32_t *lut, uint32_t m8, int &run, int &best) {
+    uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
+    row = row < 9u ? row : 9u;
+    const uint32_t e = lut[row * 256u + m8];
+    const int key = run + (int)(funnel_r(e, e, 8) & EXT_X_MASK);
+    best = key > best ? key : best;
+    run += (int)(e & EXT_Y_MASK) - (8 << EXT_SC_SHIFT);
+}
 
 IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
                        uint32_t e) {
@@ -307,15 +312,7 @@ IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, co
     int run = s.run, best = s.best;
     const int sc0 = run >> EXT_SC_SHIFT;
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) {
-        const uint32_t m = (mm >> c) & 0xFFu;
-        uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
-        row = row < 9u ? row : 9u;
-        const auto ent = IMS_LUT3(lut, row * 256u + m);
-        const int key = run + (int)ent.x;
-        best = key > best ? key : best;
-        run += (int)ent.y;
-    }
+    for (int c = 0; c < 32; c += 8) ext_step(lut, (mm >> c) & 0xFFu, run, best);
     const int sc1 = run >> EXT_SC_SHIFT;
     // +-1 per step: 2 * matches = steps + score change (also true for the padded steps)
     s.idn2 += ((run - s.run) & (int)EXT_POS_MASK) + sc1 - sc0;
@@ -326,22 +323,12 @@ IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, co
         s.pos_f = best & (int)EXT_POS_MASK;
         s.phase = s.bmax > 0 ? 1 : 2;
         s.t = 0;
-        s.run = best & ~(int)EXT_POS_MASK;  // backward restarts from high_right (:339), step count 0
-        s.best = K << EXT_SC_SHIFT;         // high_left = 12 (:303)
+        s.run = (best & ~(int)EXT_POS_MASK) - EXT_BEST_BIAS;  // backward restarts from high_right (:339), step count 0
+        s.best = (K << EXT_SC_SHIFT) + EXT_BEST_BIAS;         // high_left = 12 (:303)
     } else {
         s.best = best;
         s.phase = 2;
     }
-}
-
-// one table step (8 bases) of a walk
-IMS_HD void ext_step(const uint32_t *lut, uint32_t m8, int &run, int &best) {
-    uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
-    row = row < 9u ? row : 9u;
-    const auto ent = IMS_LUT3(lut, row * 256u + m8);
-    const int key = run + (int)ent.x;
-    best = key > best ? key : best;
-    run += (int)ent.y;
 }
 
 // Mismatch bits of the first forward and the first backward window of a hit (step u <-> bit u in
@@ -372,8 +359,8 @@ IMS_HD void ext_first_masks(const ExtState &s, const uint32_t *dpk, const uint32
 // t = 32, to be continued by ext_window.
 IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t mfa, uint32_t mba, uint32_t mfb,
                        uint32_t mbb) {
-    const int k0 = K << EXT_SC_SHIFT;
-    int ra = k0, ba = k0, rb = k0, bb = k0;
+    const int k0 = K << EXT_SC_SHIFT, kb = k0 + EXT_BEST_BIAS;
+    int ra = k0, ba = kb, rb = k0, bb = kb;
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
         ext_step(lut, (mfa >> c) & 0xFFu, ra, ba);
@@ -382,15 +369,15 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t
     const int sca = ra >> EXT_SC_SHIFT, scb = rb >> EXT_SC_SHIFT;
     const bool fa_over = sca == 0 || sa.fmax <= 32, fb_over = scb == 0 || sb.fmax <= 32;
     // backward restarts from high_right (:339) with high_left = 12 (:303)
-    int ra2 = ba & ~(int)EXT_POS_MASK, ba2 = k0, rb2 = bb & ~(int)EXT_POS_MASK, bb2 = k0;
+    int ra2 = (ba & ~(int)EXT_POS_MASK) - EXT_BEST_BIAS, ba2 = kb, rb2 = (bb & ~(int)EXT_POS_MASK) - EXT_BEST_BIAS, bb2 = kb;
     const int hra = ra2 >> EXT_SC_SHIFT, hrb = rb2 >> EXT_SC_SHIFT;
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
         ext_step(lut, (mba >> c) & 0xFFu, ra2, ba2);
         ext_step(lut, (mbb >> c) & 0xFFu, rb2, bb2);
     }
-    if (sa.bmax <= 0) { ra2 = hra << EXT_SC_SHIFT; ba2 = k0; }  // no room: no backward step at all
-    if (sb.bmax <= 0) { rb2 = hrb << EXT_SC_SHIFT; bb2 = k0; }
+    if (sa.bmax <= 0) { ra2 = hra << EXT_SC_SHIFT; ba2 = kb; }  // no room: no backward step at all
+    if (sb.bmax <= 0) { rb2 = hrb << EXT_SC_SHIFT; bb2 = kb; }
     const int sca2 = ra2 >> EXT_SC_SHIFT, scb2 = rb2 >> EXT_SC_SHIFT;
     // +-1 per step: 2 * matches = steps + score change
     sa.idn2 = (ra & (int)EXT_POS_MASK) + sca - K;

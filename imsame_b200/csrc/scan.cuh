@@ -27,7 +27,7 @@ struct ScanArgs {
     const uint32_t *brk;   // database word breaks (segment-local), ascending
     uint32_t n_brk;
     const uint16_t *nmin;  // e-value threshold table by ylen
-    const uint32_t *lut;   // extension walk table (extend.cuh: build_ext_lut3), 2 * EXT_LUT3_SIZE words
+    const uint32_t *lut;   // extension walk table (extend.cuh: build_ext_lut3), EXT_LUT3_SIZE words
     uint64_t seg_pos_base; // global index of the segment's first base
     unsigned long long *hkeys, *hvals;  // pair table (open addressing)
     uint32_t hmask;
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
     __shared__ uint32_t s_xs[SCAN_WARPS][32];
     __shared__ uint32_t s_xe[SCAN_WARPS][32];
-    __shared__ __align__(8) uint32_t s_lut[2 * EXT_LUT3_SIZE];
-    for (int i = threadIdx.x; i < 2 * EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
+    __shared__ uint32_t s_lut[EXT_LUT3_SIZE];
+    for (int i = threadIdx.x; i < EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t q_inv = inv_of(a.q.fixed_len), db_inv = inv_of(a.db.fixed_len);

@@ -56,7 +56,7 @@ int main(int argc, char **argv) {
     }
     std::vector<uint16_t> lut(EXT_LUT_SIZE);
     build_ext_lut(lut.data());
-    std::vector<uint32_t> lut2(2 * EXT_LUT3_SIZE);
+    std::vector<uint32_t> lut2(EXT_LUT3_SIZE);
     build_ext_lut3(lut2.data());
     // window_mismatch (32-bit halves) against the 64-bit form
     for (size_t i = 0; i + 40 < D.size() && i + 40 < Q.size(); i += 3) {
