@@ -204,3 +204,49 @@ def test_cfg1_full_size(gpu):
     out, stats = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
     assert gpu_records(out) == want
     assert len(want) > 3000
+
+
+def test_cfg2_shaped_properties_at_scale(gpu):
+    """BASELINE.json configs[1] at 0.3 scale (300 k x 250 bp reads vs 3 M reads: two database segments,
+    ~30 M candidate pairs) -- too large for the CPU oracle, so size-independent properties are checked:
+    the packed-word and the generic NW kernel give identical records; three uneven database shards
+    merged by the scan-order key equal the whole database; about half of the reads (those drawn from
+    the genome pool) find a hit and every record satisfies the filter it was accepted by."""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(2001, 300, 1000000, 250, 3000000, 300000, 0.03)
+    p = api.make_params(n_threads=4)
+    whole, st = gpu.align((db, ds), (q, qs), p)
+    assert st["k3_packed_launches"] == st["k3_launches"] > 0
+    gpu.set_nw_mode(1)
+    generic, st1 = gpu.align((db, ds), (q, qs), p)
+    gpu.set_nw_mode(0)
+    assert st1["k3_packed_launches"] == 0
+    for f in ("accepted", "db_seq", "qpos_end", "db_pos", "length", "identities"):
+        assert np.array_equal(whole[f], generic[f]), f
+    acc = whole["accepted"] == 1
+    assert 0.45 < acc.mean() < 0.60
+    assert np.all(whole["length"][acc] * 2 >= 250) and np.all(whole["identities"][acc] * 2 >= whole["length"][acc])
+    assert np.all((whole["db_pos"][acc] - 1) // 250 == whole["db_seq"][acc])  # the seed lies inside the reported read
+    # three uneven shards, merged on the host by (k-mer end ascending, database position descending)
+    nd = len(ds) - 1
+    cuts = [0, nd // 7, nd // 2 + 12345, nd]
+    recs = []
+    ctx = api.Imsame(0)
+    try:
+        ctx.set_query((q, qs), p)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            b0, b1 = int(ds[lo]), int(ds[hi])
+            ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
+            ctx.run(api.make_params(n_threads=4, db_total_len_global=len(db), db_pos_base=b0, db_seq_base=lo))
+            recs.append(ctx.fetch())
+    finally:
+        ctx.close()
+    key = np.stack([np.where(r["accepted"] == 1, r["qpos_end"].astype(np.int64) * (1 << 40) + ((1 << 40) - 1 - r["db_pos"].astype(np.int64)),
+                             np.iinfo(np.int64).max) for r in recs])
+    owner = key.argmin(axis=0)
+    m_acc = key.min(axis=0) != np.iinfo(np.int64).max
+    assert np.array_equal(m_acc, acc)
+    for f in ("db_seq", "qpos_end", "db_pos", "length", "identities"):
+        stacked = np.stack([r[f] for r in recs])
+        merged = stacked[owner, np.arange(stacked.shape[1])]
+        assert np.array_equal(np.where(m_acc, merged, 0), np.where(acc, whole[f], 0)), f
