@@ -54,8 +54,6 @@ int main(int argc, char **argv) {
         int64_t lo = r == 0 ? (int64_t)qs[r] : (int64_t)qs[r] - 1;
         for (int64_t e = lo + 11; e < (int64_t)qs[r + 1]; e++) qwords.emplace(fetch16(qpk.data(), e - 11) & KMASK, (uint32_t)e);
     }
-    std::vector<uint16_t> lut(EXT_LUT_SIZE);
-    build_ext_lut(lut.data());
     std::vector<uint32_t> lut2(EXT_LUT3_SIZE);
     build_ext_lut3(lut2.data());
     // window_mismatch (32-bit halves) against the 64-bit form
@@ -75,7 +73,6 @@ int main(int argc, char **argv) {
                 while (qs[r + 1] <= e) r++;
                 int64_t want = orc_extend(&db, &q, p, (uint64_t)e + 1, r, s);
                 int got = extend_hit(dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
-                int got2 = extend_hit_lut(lut.data(), dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
                 ExtState st;
                 ext_init(st, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
                 while (st.phase < 2) ext_window(st, lut2.data(), dpk.data(), qpk.data(), p, e);
@@ -98,7 +95,6 @@ int main(int argc, char **argv) {
                     prev = cur; prev_p = p; prev_e = e; prev_want = (long)want; have_prev = true;
                 }
                 hits++;
-                if (want != got2) { if (bad++ < 10) printf("LUT MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got2); }
                 if (want != got) { if (bad++ < 10) printf("MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, got); }
             }
         }
