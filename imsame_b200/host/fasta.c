@@ -52,6 +52,23 @@ static void parse_piece(const unsigned char *buf, size_t i, size_t end, int is_d
         i = (size_t)(nl - buf) + 1;
         int pending = 0;
         while (i < end) {
+            /* fast path: a whole line of nothing but A/C/G/T (any case) is classified with one pass and
+               copied with another, without the per-character state machine below */
+            if (!pending) {
+                const unsigned char *le = (const unsigned char *)memchr(buf + i, '\n', end - i);
+                const size_t ll = (le ? (size_t)(le - buf) : end) - i;
+                unsigned bad = 0, lower = 0;
+                for (size_t k = 0; k < ll; k++) { bad |= cls[buf[i + k]]; lower |= buf[i + k]; }
+                if (!bad && ll) {
+                    if (seq) {
+                        if (lower & 0x20) for (size_t k = 0; k < ll; k++) seq[pos + k] = up[buf[i + k]];
+                        else memcpy(seq + pos, buf + i, ll);
+                    }
+                    pos += ll;
+                    i += ll + (le ? 1 : 0);
+                    continue;
+                }
+            }
             const unsigned char c = buf[i];
             const unsigned k = cls[c];
             if (k == C_BASE) {
