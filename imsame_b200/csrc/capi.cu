@@ -346,17 +346,31 @@ int launch_nw_class(imsame_ctx *ctx, const NwArgs &a, int c) {
     return rc;
 }
 
-// packed-word kernel (nwp.cuh) of NW class c: 16 lanes x 2c columns
+// packed-word kernel (nwp.cuh) of NW class C: 16 lanes x 2C columns.  cl >= 0 (every query read has the
+// same length): the variant with the last column's slot compiled in.
+template <int C, int CL>
+void launch_nwp_variant(imsame_ctx *ctx, const NwArgs &a, int cl) {
+    if (cl == CL) {
+        nwp_kernel<2 * C, CL><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
+        return;
+    }
+    if constexpr (CL + 1 < 2 * C) launch_nwp_variant<C, CL + 1>(ctx, a, cl);
+    else nwp_kernel<2 * C, -1><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
+}
+
 template <int C>
 int launch_nwp(imsame_ctx *ctx, NwArgs a) {
     if (!ctx->nwp_grid[C]) {
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nwp_kernel<2 * C>, NWP_THREADS, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nwp_kernel<2 * C, -1>, NWP_THREADS, 0));
         ctx->nwp_grid[C] = std::max(1, per_sm) * ctx->n_sm;
     }
     a.s_class = C;
     a.one = 1;
-    nwp_kernel<2 * C><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
+    int cl = -1;
+    if (a.q.fixed_len >= 2 && !a.check_class && nw_class_of(a.q.fixed_len) == C) cl = (int)((a.q.fixed_len - 2) % (2 * C));
+    if (cl >= 0) launch_nwp_variant<C, 0>(ctx, a, cl);
+    else nwp_kernel<2 * C, -1><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     ctx->k3_launches++;
     ctx->k3_packed++;

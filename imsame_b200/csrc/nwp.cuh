@@ -39,7 +39,9 @@ struct PwDevEW {
     }
 };
 
-template <int S>
+// CL: slot of the last query column inside a lane's strip when every query read has the same length
+// (a.q.fixed_len; CL = (ylen - 2) % S), -1 otherwise
+template <int S, int CL>
 __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
     __shared__ __align__(128) int tbl[2 * NWP_TBL * 32];
     __shared__ uint8_t sx_all[NWP_WARPS * 2][PW_MAX_X];
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
             ew.tbl = tbl;                                                                          \
             ew.copy = (uint32_t)(lane & 7) * 4u;                                                   \
             ew.mm = (d_ | (d_ >> 1));                                                              \
-            pw_row<S>(L, PREV1, PREV2, in, out, i, j0, ew, k, X1, Y1, cl, owns_last);              \
+            pw_row<S, PwDevEW, CL>(L, PREV1, PREV2, in, out, i, j0, ew, k, X1, Y1, cl, owns_last);  \
         }                                                                                          \
     }
         // always an even number of steps (a surplus step has no active lane): the register roles of the

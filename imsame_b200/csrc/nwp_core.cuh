@@ -175,7 +175,9 @@ IMS_HD PwLink pw_first_link(const PwK &k, uint32_t xi, uint32_t y0) {
 
 // One row of the lane's strip.  P1 = T'[i-1] (read only), P2 = T'[i-2] on entry and T'[i]
 // on exit.  ew(g) returns the constants of cells 4g .. 4g+3.  cl / owns_last as in nw_row.
-template <int S, class EW>
+// CL >= 0: the slot of the last column is a compile-time constant (every query read of the launch has
+// the same length) and is read straight out of its register; CL = -1: run-time slot, a switch per row.
+template <int S, class EW, int CL = -1>
 IMS_HD void pw_row(PwLane<S> &L, const PwRow<S> &P1, PwRow<S> &P2, const PwLink &in, PwLink &out, int i, int j0,
                    const EW &ew, const PwK &k, int X1, int Y1, int cl, bool owns_last) {
     int mfz = in.mfz, lw = in.lw;
@@ -222,7 +224,8 @@ IMS_HD void pw_row(PwLane<S> &L, const PwRow<S> &P1, PwRow<S> &P2, const PwLink 
     // the last one here; the last row is scanned once per pair from the row history (pw_last_row)
     if (owns_last && i != X1) {
         int lt = P2.h[S];
-        switch (cl) {
+        if (CL >= 0) lt = P2.h[(CL >= 0 && CL < S ? CL : 0) + 1];
+        else switch (cl) {
 #define IMS_CASE(C) case C: if (C < S) lt = P2.h[(C < S ? C : 0) + 1]; break;
             IMS_CASE(0) IMS_CASE(1) IMS_CASE(2) IMS_CASE(3) IMS_CASE(4) IMS_CASE(5) IMS_CASE(6) IMS_CASE(7)
             IMS_CASE(8) IMS_CASE(9) IMS_CASE(10) IMS_CASE(11) IMS_CASE(12) IMS_CASE(13) IMS_CASE(14)
