@@ -62,6 +62,7 @@ SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "im
            "imsame_gpu_run", "imsame_gpu_n_segments", "imsame_gpu_n_bands", "imsame_gpu_run_begin",
            "imsame_gpu_run_scan", "imsame_gpu_run_band", "imsame_gpu_run_select", "imsame_gpu_run_end",
            "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode",
+           "imsame_gpu_set_kmer",
            "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
 _lib = None
@@ -108,6 +109,7 @@ def lib():
         l.imsame_gpu_traceback.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(SeqInfo), C.POINTER(Params), vp, vp,
                                            C.POINTER(C.POINTER(C.c_uint32)), vp]
         l.imsame_gpu_set_nw_mode.argtypes = [vp, C.c_int]
+        l.imsame_gpu_set_kmer.argtypes = [vp, C.c_int]
         l.imsame_gpu_free.argtypes = [vp]
         l.imsame_gpu_free.restype = None
         l.imsame_gpu_host_alloc.argtypes = [u64]
@@ -219,6 +221,10 @@ class Imsame:
     def set_nw_mode(self, mode):
         """0 = packed-word K3 where eligible (default), 1 = generic K3 only"""
         self._check(lib().imsame_gpu_set_nw_mode(self._h, int(mode)))
+
+    def set_kmer(self, k):
+        """seed length, 4..15 (default 12 = the reference's FIXED_K); call before set_query / align"""
+        self._check(lib().imsame_gpu_set_kmer(self._h, int(k)))
 
     def align(self, db, query, params=None, db_breaks=None):
         """db, query: (seq uint8 ASCII, start uint64[n+1]). Returns (records ndarray BEST_DTYPE, stats dict)."""

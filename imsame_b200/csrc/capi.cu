@@ -91,6 +91,9 @@ struct imsame_ctx {
     int nwp_grid[9] = {0};
     bool in_align = false;  // imsame_gpu_align: upload phases belong to the same stats
     int nw_mode = 0;  // 0: packed-word kernel where pw_eligible() holds, 1: generic kernel only
+    int k = K;        // seed length (imsame_gpu_set_kmer); k_tables = the length off/cursor/tile_sums are sized for
+    int k_tables = 0;
+    int q_k = K;      // the seed length the resident query table was built with
     int scan_grid = 0;
 
     // device blocks released by free_query / free_db, reused by the next set_query / set_db
@@ -510,9 +513,12 @@ int imsame_gpu_create(imsame_ctx **out, int device) {
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (getenv("IMSAME_NO_L2_PIN")) ctx->l2_pin = 0;
+    if (getenv("IMSAME_TRACE"))
+        fprintf(stderr, "[imsame] L2 %d B, persisting max %zu B, access window max %zu B\n", prop.l2CacheSize,
+                ctx->l2_persist_max, ctx->l2_window_max);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMSAME_ECUDA; }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel, SCAN_THREADS_K2, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<K>, SCAN_THREADS_K2, 0);
     if (const char *e = getenv("IMSAME_SCAN_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
     ctx->scan_grid = std::max(1, per_sm) * ctx->n_sm;
     *out = ctx;
@@ -596,12 +602,19 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
         blk_kernel<<<std::min<uint32_t>((nq + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ctx->q_start, nq, ctx->q_blk);
         ctx->launches++;
     }
-    if (!ctx->off) {
-        if ((rc = dev_alloc(ctx, &ctx->off, (uint64_t)NCODES + 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->cursor, (uint64_t)NCODES + 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->tile_sums, (uint64_t)SCAN_TILE))) return rc;
+    const uint32_t ncodes = ncodes_of(ctx->k);
+    const uint32_t n_tiles = (ncodes + SCAN_TILE - 1) / SCAN_TILE;
+    if (ctx->k_tables != ctx->k) {
+        dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
+        ctx->off = ctx->cursor = ctx->tile_sums = nullptr;
+        ctx->k_tables = 0;
+        if ((rc = dev_alloc(ctx, &ctx->off, (uint64_t)ncodes + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->cursor, (uint64_t)ncodes + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->tile_sums, (uint64_t)n_tiles + 1))) return rc;
+        ctx->k_tables = ctx->k;
     }
     QTableArgs a;
+    a.k = ctx->k;
     a.q.pk = ctx->q_pk; a.q.start = ctx->q_start; a.q.blk = ctx->q_blk; a.q.n = nq; a.q.total = total;
     a.q.fixed_len = ctx->q_fixed;
     a.n_threads = (uint32_t)std::min<uint64_t>(ctx->q_threads, 0xFFFFFFFFull);
@@ -609,30 +622,30 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
     a.cnt = ctx->cursor;
     a.qpos = nullptr;
     const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
-    const uint32_t n_tiles = (NCODES + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t n_words = 0;
     {
         PhaseScope ps(ctx, PH_K1);
-        CK(cudaMemsetAsync(ctx->cursor, 0, ((size_t)NCODES + 1) * 4, ctx->stream));
+        CK(cudaMemsetAsync(ctx->cursor, 0, ((size_t)ncodes + 1) * 4, ctx->stream));
         qtable_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
-        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, NCODES, ctx->tile_sums, ctx->off);
+        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
         scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, n_tiles);
-        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, NCODES, ctx->tile_sums, ctx->off);
+        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
         ctx->launches += 4;
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(&n_words, ctx->off + NCODES, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&n_words, ctx->off + ncodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_qwords = n_words;
     if ((rc = pool_alloc(ctx, &ctx->qpos, (uint64_t)n_words + 1))) return rc;
     {
         PhaseScope ps(ctx, PH_K1);
-        CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)NCODES + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         a.qpos = ctx->qpos;
         qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    ctx->q_k = ctx->k;
     ctx->have_query = true;
     return IMSAME_OK;
 }
@@ -808,7 +821,7 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
     // (956 MB) stream through the same 126 MB L2: keep the query resident (persisting access window),
     // everything else on this stream is marked streaming.  Reset after the scan.
     bool pinned = false;
-    if (ctx->l2_pin && ctx->l2_persist_max && ctx->l2_window_max) {
+    if (ctx->l2_pin && !getenv("IMSAME_NO_L2_PIN") && ctx->l2_persist_max && ctx->l2_window_max) {
         const size_t qbytes = ((size_t)ctx->q_total + 15) / 16 * 4;
         const size_t win = std::min(qbytes, ctx->l2_window_max);
         const size_t carve = std::min(win, ctx->l2_persist_max);
@@ -847,7 +860,9 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
             a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
             a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
             a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;
-            scan_kernel<<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
+            a.k = ctx->q_k;
+            if (ctx->q_k == K) scan_kernel<K><<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
+            else scan_kernel<0><<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
             ctx->launches++; ctx->k2_launches++;
         }
         int overflow = 0;
@@ -985,6 +1000,14 @@ int imsame_gpu_run(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, ui
                    imsame_stats *st) {
     if (!ctx || !p) return IMSAME_EARG;
     return run_impl(ctx, p, d_keys, d_payload, st);
+}
+
+int imsame_gpu_set_kmer(imsame_ctx *ctx, int k) {
+    if (!ctx || k < K_MIN || k > K_MAX) return IMSAME_EARG;
+    if (ctx->run_active) return IMSAME_ESTATE;
+    if (k != ctx->k) ctx->have_query = false;  // the resident word table belongs to the old length
+    ctx->k = k;
+    return IMSAME_OK;
 }
 
 int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode) {

@@ -8,6 +8,8 @@
 //   backward from (p-13, e-12) starting at score = high_right while
 //   high_left stays at its initial 12 (:303,339); `if (high_left <= score) start = cur` (:347);
 //   t_len = end - start (:359);  returns n = 2*idents - t_len  (raw score = 4n, :373).
+// The seed length is a parameter `K` of every function here (default: the reference's FIXED_K = 12,
+// src/structs.h:15); other values are the reference "recompiled with another FIXED_K" (SURVEY 8(f) rank 4).
 // p = database index AFTER the seed's last base (llpos.pos), e = query index of
 // the seed's last base (curr_pos).  [xs, xend) and [ys, yend) are the reads.
 #pragma once
@@ -16,7 +18,7 @@
 namespace imsame {
 
 IMS_HD int extend_hit(const uint32_t *dpk, const uint32_t *qpk, uint32_t p, uint32_t e, uint32_t xs,
-                      uint32_t xend, uint32_t ys, uint32_t yend) {
+                      uint32_t xend, uint32_t ys, uint32_t yend, int K = imsame::K) {
     int fmax = (int)(xend - p);
     {
         const int fq = (int)(yend - (e + 1));
@@ -188,7 +190,8 @@ struct ExtState {
     int fmax, bmax;  // steps available inside both reads
 };
 
-IMS_HD void ext_init(ExtState &s, uint32_t p, uint32_t e, uint32_t xs, uint32_t xend, uint32_t ys, uint32_t yend) {
+IMS_HD void ext_init(ExtState &s, uint32_t p, uint32_t e, uint32_t xs, uint32_t xend, uint32_t ys, uint32_t yend,
+                     int K = imsame::K) {
     const int fd = (int)(xend - p), fq = (int)(yend - (e + 1));
     const int bd = (int)(p - K - xs), bq = (int)e - (K - 1) - (int)ys;  // -1 for the phantom word
     s.fmax = fq < fd ? fq : fd;
@@ -212,7 +215,7 @@ IMS_HD void ext_step(const uint32_t *lut, uint32_t m8, int &run, int &best) {
 }
 
 IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
-                       uint32_t e) {
+                       uint32_t e, int K = imsame::K) {
     const bool bwd = s.phase == 1;
     const int maxs = bwd ? s.bmax : s.fmax;
     const int rem = maxs - s.t;
@@ -258,7 +261,7 @@ IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, co
 // phase (the first step already scores below high_right = the start score); the backward phase starts
 // ABOVE high_left = 12 (:303,339), so there a walk without room is discarded instead (ext_first2).
 IMS_HD void ext_first_masks(const ExtState &s, const uint32_t *dpk, const uint32_t *qpk, uint32_t p, uint32_t e,
-                            uint32_t &mf, uint32_t &mb) {
+                            uint32_t &mf, uint32_t &mb, int K = imsame::K) {
     mf = window_mismatch(dpk, p, qpk, e + 1);
     const int sd = (int)p - (K + 1) - 31, sq = (int)e - K - 31;
     if (sd >= 0 && sq >= 0) {
@@ -279,7 +282,7 @@ IMS_HD void ext_first_masks(const ExtState &s, const uint32_t *dpk, const uint32
 // instruction issue).  On return each state is done (phase 2) or parked-ready: phase 0 / 1 with
 // t = 32, to be continued by ext_window.
 IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t mfa, uint32_t mba, uint32_t mfb,
-                       uint32_t mbb) {
+                       uint32_t mbb, int K = imsame::K) {
     const int k0 = K << EXT_SC_SHIFT, kb = k0 + EXT_BEST_BIAS;
     int ra = k0, ba = kb, rb = k0, bb = kb;
 #pragma unroll
@@ -323,7 +326,7 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t
 
 // n = 2 * idents - t_len, t_len = fe + K + be + 1 (:359) with fe = pos_f - 1, be = pos_b - 1
 // (after the last window `best` is the backward maximum, or still "no step" when there was no backward walk)
-IMS_HD int ext_result(const ExtState &s) {
+IMS_HD int ext_result(const ExtState &s, int K = imsame::K) {
     const int pos_b = s.best & (int)EXT_POS_MASK;
     return 2 * K + s.idn2 - (s.pos_f + K + pos_b - 1);
 }

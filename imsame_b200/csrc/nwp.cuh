@@ -29,9 +29,9 @@ struct PwDevEW {
     uint32_t copy;  // (lane & 7) * 4: this lane's copy inside a row (in ints)
     __device__ __forceinline__ PwE4 operator()(int g) const {
         // row * 32 ints | copy: one shift + one 3-input logic op
-        const uint32_t at = (g == 0 ? ((mm << 5) & (0x55u << 5)) : ((mm >> (8 * g - 5)) & (0x55u << 5))) | copy;
-        const int4 d = *reinterpret_cast<const int4 *>(tbl + at);
-        const int4 s = *reinterpret_cast<const int4 *>(tbl + NWP_TBL * 32 + at);
+        const uint32_t at = (g == 0 ? ((mm << 7) & (0x55u << 7)) : g == 1 ? ((mm >> 1) & (0x55u << 7)) : ((mm >> (8 * g - 7)) & (0x55u << 7))) | copy;
+        const int4 d = *reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(tbl) + at);
+        const int4 s = *reinterpret_cast<const int4 *>(reinterpret_cast<const char *>(tbl) + NWP_TBL * 128 + at);
         PwE4 e;
         e.ds[0] = d.x; e.ds[1] = d.y; e.ds[2] = d.z; e.ds[3] = d.w;
         e.sb[0] = s.x; e.sb[1] = s.y; e.sb[2] = s.z; e.sb[3] = s.w;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
             const uint32_t d_ = ycols ^ (xi * 0x55555555u);                                        \
             PwDevEW ew;                                                                            \
             ew.tbl = tbl;                                                                          \
-            ew.copy = (uint32_t)(lane & 7) * 4u;                                                   \
+            ew.copy = (uint32_t)(lane & 7) * 16u;                                                   \
             ew.mm = (d_ | (d_ >> 1));                                                              \
             pw_row<S, PwDevEW, CL>(L, PREV1, PREV2, in, out, i, j0, ew, k, X1, Y1, cl, owns_last);  \
         }                                                                                          \

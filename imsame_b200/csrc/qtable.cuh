@@ -3,7 +3,8 @@
 // The reference indexes the DATABASE (12-D pointer table of linked lists,
 // src/IMSAME.c:232-281) and streams the query (src/alignmentFunctions.c:91-203).
 // Here the mirror image is built: a CSR table over the QUERY words
-//     off[4^12 + 1], qpos[n_words]   (qpos = index of the word's last base = curr_pos)
+//     off[4^k + 1], qpos[n_words]   (k = 12 unless imsame_gpu_set_kmer says otherwise)
+//       (qpos = index of the word's last base = curr_pos)
 // holding exactly the words the reference's scan would look up, including its
 // cross-read "phantom" word: every read that is not the first of its pthread
 // chunk starts its word stream on the LAST base of the previous read and never
@@ -51,6 +52,7 @@ struct QTableArgs {
     uint32_t per, n_threads;  // chunking of src/IMSAME.c:414,433
     uint32_t *cnt;            // pass 0: histogram ; pass 1: bucket cursors
     uint32_t *qpos;
+    int k;                    // seed length (the reference: FIXED_K = 12, src/structs.h:15)
 };
 
 // does a query word end at base e, and which word?  
@@ -60,8 +62,9 @@ __device__ __forceinline__ bool query_word_at(const QTableArgs &a, uint32_t e, u
     const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
     const uint32_t lo = (ys == 0 || is_chunk_first(r, a.per, a.n_threads)) ? ys : ys - 1;
     const uint32_t hi = (r == a.q.n - 1) ? a.q.total - 1 : yend - 2;
-    if (e < lo + (K - 1) || e > hi || yend < 2 + ys) return false;
-    code = fetch16(a.q.pk, (uint64_t)e - (K - 1)) & KMASK;
+    const uint32_t k1 = (uint32_t)a.k - 1u;
+    if (e < lo + k1 || e > hi || yend < 2 + ys) return false;
+    code = fetch16(a.q.pk, (uint64_t)e - k1) & kmask_of(a.k);
     return true;
 }
 
@@ -134,20 +137,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t
     }
 }
 
-// phase 1: exclusive scan of the tile sums in one block (n_tiles <= SCAN_TILE)
+// phase 1: exclusive scan of the tile sums in one block, SCAN_TILE sums at a time with a running carry
+// (4^12 counters = 4096 tile sums = one round; 4^15 = 64 rounds)
 __global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(uint32_t *tile_sums, uint32_t n_tiles) {
-    const uint32_t base = threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS], s = 0;
+    uint32_t carry = 0;
+    for (uint32_t chunk = 0; chunk < n_tiles; chunk += SCAN_TILE) {
+        const uint32_t base = chunk + threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        v[k] = (base + k < n_tiles) ? tile_sums[base + k] : 0u;
-        s += v[k];
-    }
-    uint32_t ex = block_exclusive_scan(s, nullptr);
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            v[k] = (base + k < n_tiles) ? tile_sums[base + k] : 0u;
+            s += v[k];
+        }
+        uint32_t total;
+        uint32_t ex = carry + block_exclusive_scan(s, &total);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < n_tiles) tile_sums[base + k] = ex;
-        ex += v[k];
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n_tiles) tile_sums[base + k] = ex;
+            ex += v[k];
+        }
+        carry += total;
     }
 }
 

@@ -34,6 +34,7 @@ struct ScanArgs {
     const unsigned long long *best;  // current per-read best key (prunes later segments)
     unsigned long long *counters;    // [0] db words, [1] hits, [2] e-value passes, [3] anomalies
     int *overflow;
+    int k;  // seed length when the kernel is not specialised on it (scan_kernel<0>)
 };
 
 IMS_HD uint64_t pair_hash(uint64_t k) {
@@ -63,12 +64,12 @@ __device__ __forceinline__ void pair_insert(const ScanArgs &a, uint32_t r, uint3
     *a.overflow = 1;
 }
 
-// is there a word break inside the word ending at base q (bases q-11 .. q)?
-__device__ __forceinline__ bool word_broken(const ScanArgs &a, uint32_t q) {
+// is there a word break inside the word ending at base q (bases q-k+1 .. q)?
+__device__ __forceinline__ bool word_broken(const ScanArgs &a, uint32_t q, int k) {
     if (a.n_brk == 0) return false;
-    // first break >= q-10
+    // first break >= q-k+2
     uint32_t lo = 0, hi = a.n_brk;
-    const uint32_t want = q - (K - 2);
+    const uint32_t want = q - (uint32_t)(k - 2);
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if (a.brk[mid] < want) lo = mid + 1; else hi = mid;
@@ -117,8 +118,8 @@ __device__ __forceinline__ ParkedWalk park_load(const uint32_t (*q)[SCAN_QCAP], 
 
 __device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, uint32_t p, uint32_t e,
                                            const ExtState &st, unsigned long long &c_pass,
-                                           unsigned long long &c_anom) {
-    const int n = ext_result(st);
+                                           unsigned long long &c_anom, int k) {
+    const int n = ext_result(st, k);
     if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
     // fixed-length queries: one threshold; otherwise the read has to be looked up first
     if (n >= 0 && a.q.fixed_len && n < (int)a.nmin[a.q.fixed_len]) return;
@@ -138,17 +139,21 @@ __device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, ui
 // finish `count` (<= 32) parked walks, one per lane
 __device__ __forceinline__ void drain_parked(const ScanArgs &a, uint32_t q_inv, const uint32_t *s_lut,
                                              const uint32_t (*q)[SCAN_QCAP], int first, int count, int lane,
-                                             unsigned long long &c_pass, unsigned long long &c_anom) {
+                                             unsigned long long &c_pass, unsigned long long &c_anom, int k) {
     ParkedWalk w;
     w.st.phase = 2;
     w.p = w.e = 0;
     if (lane < count) w = park_load(q, first + lane);
     while (__any_sync(0xffffffffu, w.st.phase < 2))
-        if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e);
-    if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.st, c_pass, c_anom);
+        if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e, k);
+    if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.st, c_pass, c_anom, k);
 }
 
+// KT: the seed length as a compile-time constant (12 = the reference's FIXED_K, the only value it has),
+// or 0 = read it from the arguments (imsame_gpu_set_kmer)
+template <int KT>
 __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
+    const int k = KT ? KT : a.k;
     __shared__ uint32_t s_park[SCAN_WARPS][PARK_FIELDS][SCAN_QCAP];
     __shared__ uint32_t s_excl[SCAN_WARPS][33];
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
@@ -172,8 +177,8 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             const uint32_t s = find_read_inv(a.db, db_inv, q);
             xs = read_start(a.db, s);
             xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
-            if (q >= xs + (K - 1) && !word_broken(a, q)) {
-                const uint32_t code = fetch16(a.db.pk, (uint64_t)q - (K - 1)) & KMASK;
+            if (q >= xs + (uint32_t)(k - 1) && !word_broken(a, q, k)) {
+                const uint32_t code = fetch16(a.db.pk, (uint64_t)q - (uint32_t)(k - 1)) & kmask_of(k);
                 b0 = a.off[code];
                 cnt = a.off[code + 1] - b0;
                 c_words++;
@@ -215,16 +220,16 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                 const uint32_t ysa = read_start(a.q, ra), ysb = read_start(a.q, rb);
                 const uint32_t yea = a.q.fixed_len ? ysa + a.q.fixed_len : a.q.start[ra + 1];
                 const uint32_t yeb = a.q.fixed_len ? ysb + a.q.fixed_len : a.q.start[rb + 1];
-                ext_init(sta, pa, ea, s_xs[warp][oa], s_xe[warp][oa], ysa, yea);
-                ext_init(stb, pb, eb, s_xs[warp][ob], s_xe[warp][ob], ysb, yeb);
+                ext_init(sta, pa, ea, s_xs[warp][oa], s_xe[warp][oa], ysa, yea, k);
+                ext_init(stb, pb, eb, s_xs[warp][ob], s_xe[warp][ob], ysb, yeb, k);
             }
             uint32_t mfa, mba, mfb, mbb;
-            ext_first_masks(sta, a.db.pk, a.q.pk, pa, ea, mfa, mba);
-            ext_first_masks(stb, a.db.pk, a.q.pk, pb, eb, mfb, mbb);
-            ext_first2(sta, stb, s_lut, mfa, mba, mfb, mbb);
+            ext_first_masks(sta, a.db.pk, a.q.pk, pa, ea, mfa, mba, k);
+            ext_first_masks(stb, a.db.pk, a.q.pk, pb, eb, mfb, mbb, k);
+            ext_first2(sta, stb, s_lut, mfa, mba, mfb, mbb, k);
             c_hits += (la ? 1 : 0) + (lb ? 1 : 0);
-            if (la && sta.phase == 2) finish_hit(a, q_inv, pa, ea, sta, c_pass, c_anom);
-            if (lb && stb.phase == 2) finish_hit(a, q_inv, pb, eb, stb, c_pass, c_anom);
+            if (la && sta.phase == 2) finish_hit(a, q_inv, pa, ea, sta, c_pass, c_anom, k);
+            if (lb && stb.phase == 2) finish_hit(a, q_inv, pb, eb, stb, c_pass, c_anom, k);
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const bool unfinished = half ? (lb && stb.phase < 2) : (la && sta.phase < 2);
@@ -239,14 +244,14 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                     __syncwarp();
                     if (n_parked >= 32) {
                         n_parked -= 32;
-                        drain_parked(a, q_inv, s_lut, s_park[warp], n_parked, 32, lane, c_pass, c_anom);
+                        drain_parked(a, q_inv, s_lut, s_park[warp], n_parked, 32, lane, c_pass, c_anom, k);
                         __syncwarp();
                     }
                 }
             }
         }
     }
-    if (n_parked) drain_parked(a, q_inv, s_lut, s_park[warp], 0, n_parked, lane, c_pass, c_anom);
+    if (n_parked) drain_parked(a, q_inv, s_lut, s_park[warp], 0, n_parked, lane, c_pass, c_anom, k);
     // counters: warp-reduce then one atomic per warp
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {

@@ -26,6 +26,7 @@ typedef struct {
     imsame_params params;
     imsame_best *best;
     imsame_stats stats;
+    int kmer;
     int rc;
     char err[256];
 } shard_job;
@@ -37,7 +38,8 @@ static void *shard_main(void *arg) {
         j->rc = imsame_gpu_create(&ctx, j->device);
         if (j->rc) return NULL;
     }
-    j->rc = imsame_gpu_align(ctx, &j->db, j->query, &j->params, j->best, &j->stats);
+    j->rc = imsame_gpu_set_kmer(ctx, j->kmer);
+    if (!j->rc) j->rc = imsame_gpu_align(ctx, &j->db, j->query, &j->params, j->best, &j->stats);
     if (j->rc) snprintf(j->err, sizeof j->err, "%s", imsame_gpu_last_cuda_error(ctx));
     if (!j->ctx) imsame_gpu_destroy(ctx);
     return NULL;
@@ -99,6 +101,7 @@ int imsame_run_job(const imsame_fasta *qf, const imsame_fasta *dbf, const imsame
         j->params.db_total_len_global = db.total_len;
         j->params.db_pos_base = b0;
         j->params.db_seq_base = r0;
+        j->kmer = o->kmer ? o->kmer : 12; /* FIXED_K, src/structs.h:15 */
         j->best = ng == 1 ? best : (imsame_best *)calloc(q.n_seqs, sizeof(imsame_best));
         if (ng == 1) shard_main(j);
         else if (pthread_create(&th[g], NULL, shard_main, j)) { j->rc = IMSAME_ECUDA; snprintf(j->err, sizeof j->err, "pthread_create"); }

@@ -15,6 +15,7 @@ typedef struct imsame_job_opts {
     int igap, egap; /* negated, as stored by the reference (src/IMSAME.c:565,568) */
     int gpus, device;
     int trace; /* phase wall times on stderr */
+    int kmer;  /* seed length, 0 = the reference's FIXED_K (12) */
 } imsame_job_opts;
 
 /* Aligns every read of q against db and writes the records of the accepted reads to fout (may be

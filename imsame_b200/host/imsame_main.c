@@ -14,6 +14,7 @@
  *
  * Opt-in additions that default to reference behaviour:
  *   -gpus N     shard the database by contiguous read ranges over N GPUs (default 1)
+ *   -kmer K     seed length 4..15 (default 12 = the reference's FIXED_K; it has no such flag)
  *   -device D   first CUDA device to use (default 0)
  */
 #define _GNU_SOURCE
@@ -44,7 +45,7 @@ typedef struct {
     uint64_t n_threads;
     long double minevalue, mincoverage, minidentity;
     int igap, egap;
-    int gpus, device;
+    int gpus, device, kmer;
 } cli_args;
 
 static void usage_and_exit(void) { /* src/IMSAME.c:526-538 */
@@ -74,6 +75,7 @@ static void parse_args(int argc, char **av, cli_args *a) {
     a->egap = -2;
     a->gpus = 1;
     a->device = 0;
+    a->kmer = 12; /* FIXED_K, src/structs.h:15 */
     for (int i = 0; i < argc; i++) { /* the reference also scans av[0] and never skips values */
         const char *nxt = (i + 1 < argc) ? av[i + 1] : NULL;
         if (strcmp(av[i], "--help") == 0) usage_and_exit();
@@ -97,6 +99,10 @@ static void parse_args(int argc, char **av, cli_args *a) {
         if (strcmp(av[i], "-n_threads") == 0 && nxt) a->n_threads = (uint64_t)atoi(nxt);
         if (strcmp(av[i], "-gpus") == 0 && nxt) a->gpus = atoi(nxt);
         if (strcmp(av[i], "-device") == 0 && nxt) a->device = atoi(nxt);
+        if (strcmp(av[i], "-kmer") == 0 && nxt) {
+            a->kmer = atoi(nxt);
+            if (a->kmer < 4 || a->kmer > 15) terror("The seed length must be between 4 and 15");
+        }
     }
 }
 
@@ -164,6 +170,7 @@ int main(int argc, char **av) {
     jo.igap = a.igap;
     jo.egap = a.egap;
     jo.gpus = a.gpus;
+    jo.kmer = a.kmer;
     jo.device = a.device;
     jo.trace = getenv("IMSAME_TRACE") != NULL; /* phase wall times on stderr (not part of the reference's output) */
     char err[300];

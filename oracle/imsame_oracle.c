@@ -101,7 +101,7 @@ static inline unsigned base2(unsigned char c) { /* src/IMSAME.c:55-59 */
 }
 
 static int build_index(const orc_seqs *db, int k, orc_index *ix) {
-    if (k < 4 || k > 13) return -1;
+    if (k < 4 || k > 14) return -1; /* 4^14 offsets = 2 GB of host memory */
     ix->k = k;
     ix->n_codes = 1ull << (2 * k);
     ix->off = (uint64_t *)calloc(ix->n_codes + 1, sizeof(uint64_t));
@@ -151,12 +151,18 @@ static void free_index(orc_index *ix) {
 /* ------------------------------------------------------------------------- */
 int64_t orc_extend(const orc_seqs *db, const orc_seqs *q, uint64_t pos_db, uint64_t pos_q,
                    uint64_t read, uint64_t db_seq) {
+    return orc_extend_k(db, q, pos_db, pos_q, read, db_seq, 12); /* FIXED_K, src/structs.h:15 */
+}
+
+/* the same with FIXED_K = k: what the reference would compute if recompiled with another seed length
+ * (it cannot be: its Container is a 12-dimensional array, src/alignmentFunctions.h:4-6) */
+int64_t orc_extend_k(const orc_seqs *db, const orc_seqs *q, uint64_t pos_db, uint64_t pos_q,
+                     uint64_t read, uint64_t db_seq, int k) {
     /* read bounds (:280-294): end = index of the last base, or total_len for the last read */
     int64_t xs = (int64_t)db->start[db_seq];
     int64_t xe = db_seq == db->n_seqs - 1 ? (int64_t)db->total_len : (int64_t)db->start[db_seq + 1] - 1;
     int64_t ys = (int64_t)q->start[read];
     int64_t ye = read == q->n_seqs - 1 ? (int64_t)q->total_len : (int64_t)q->start[read + 1] - 1;
-    int k = 12;
     int64_t cd = (int64_t)pos_db, cq = (int64_t)pos_q;
     int64_t end_x = cd - 1, start_x = end_x - k + 1;
     int64_t sc = (int64_t)k * PT, hi_r = sc, hi_l = sc; /* :301-303 */
@@ -343,7 +349,7 @@ static void emit_record(FILE *out, uint64_t r, uint64_t s, uint32_t len, uint32_
 /* ------------------------------------------------------------------------- */
 int orc_align_sequential(const orc_seqs *db, const orc_seqs *q, const orc_params *p,
                          orc_best *best, FILE *out, orc_stats *st) {
-    if (p->k != 12) return -9; /* the extension hard-codes FIXED_K like the reference */
+    if (p->k < 4 || p->k > 14) return -9; /* k != 12: no reference to compare against (orc_extend_k) */
     orc_index ix;
     if (build_index(db, p->k, &ix)) return -1;
     orc_stats z = {0, 0, 0, 0};
@@ -369,7 +375,7 @@ int orc_align_sequential(const orc_seqs *db, const orc_seqs *q, const orc_params
                 for (uint64_t h = hi; h > lo && !aligned; h--) { /* descending pos */
                     uint64_t pos = ix.pos[h - 1], s = ix.sid[h - 1];
                     z.hits++;
-                    int64_t n = orc_extend(db, q, pos, cp + 1, cr, s);
+                    int64_t n = orc_extend_k(db, q, pos, cp + 1, cr, s, p->k);
                     if (!(orc_evalue(n, ylen, p->db_total_len_global ? p->db_total_len_global : db->total_len) < p->min_e_value)) continue;
                     z.evalue_pass++;
                     uint64_t xlen = db->start[s + 1] - db->start[s];
@@ -407,7 +413,7 @@ int orc_align_sequential(const orc_seqs *db, const orc_seqs *q, const orc_params
 /* ------------------------------------------------------------------------- */
 int orc_align_bulk(const orc_seqs *db, const orc_seqs *q, const orc_params *p, orc_best *best,
                    orc_stats *st) {
-    if (p->k != 12) return -9;
+    if (p->k < 4 || p->k > 14) return -9;
     orc_index ix;
     if (build_index(db, p->k, &ix)) return -1;
     orc_stats z = {0, 0, 0, 0};
@@ -434,7 +440,7 @@ int orc_align_bulk(const orc_seqs *db, const orc_seqs *q, const orc_params *p, o
                 z.hits++;
                 /* key order: e ascending, pos descending; skip anything not better */
                 if (b->accepted && !((uint64_t)e < b->qpos_end || ((uint64_t)e == b->qpos_end && pos > b->db_pos))) continue;
-                int64_t n = orc_extend(db, q, pos, (uint64_t)e + 1, r, s);
+                int64_t n = orc_extend_k(db, q, pos, (uint64_t)e + 1, r, s, p->k);
                 if (!(orc_evalue(n, ylen, p->db_total_len_global ? p->db_total_len_global : db->total_len) < p->min_e_value)) continue;
                 z.evalue_pass++;
                 uint64_t ci;

@@ -43,7 +43,7 @@ typedef struct {
     long double min_e_value, min_coverage, min_identity; /* src/alignmentFunctions.h:17-19 */
     int igap, egap;     /* negated, as stored in HashTableArgs (src/IMSAME.c:565,568) */
     uint64_t n_threads; /* only defines the chunk starts (src/IMSAME.c:414,433) */
-    int k;              /* seed length; the reference has FIXED_K = 12 */
+    int k;              /* seed length; the reference has FIXED_K = 12 (the only pinned value), 4..14 accepted */
     /* database shards (multi-GPU tests): 0 = db is the whole database */
     uint64_t db_total_len_global; /* database->total_len used by the e-value (src/alignmentFunctions.c:384) */
 } orc_params;
@@ -68,6 +68,8 @@ void orc_free_seqs(orc_seqs *s);
 /* ungapped extension; returns n = 2*idents - t_len  (raw score = 4n) */
 int64_t orc_extend(const orc_seqs *db, const orc_seqs *q, uint64_t pos_db, uint64_t pos_q,
                    uint64_t read, uint64_t db_seq);
+int64_t orc_extend_k(const orc_seqs *db, const orc_seqs *q, uint64_t pos_db, uint64_t pos_q,
+                     uint64_t read, uint64_t db_seq, int k);
 long double orc_evalue(int64_t n, uint64_t ylen, uint64_t db_total_len);
 
 /* full NW with back-pointers + traceback + rendering (reference formulation) */

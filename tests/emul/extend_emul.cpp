@@ -1,6 +1,6 @@
 // CPU check of the packed-sequence helpers and the ungapped extension used by the
 // scan kernel (common.cuh / extend.cuh) against the oracle's byte-wise extension.
-//   usage: extend_emul <seed>
+//   usage: extend_emul <seed> [k]     (k = seed length, default 12 = the reference's FIXED_K)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,6 +22,8 @@ static std::vector<uint32_t> pack(const std::vector<unsigned char> &s) {
 
 int main(int argc, char **argv) {
     rng_state = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
+    const int k = argc > 2 ? atoi(argv[2]) : K;
+    const uint32_t kmask = kmask_of(k);
     const char B[4] = {'A', 'C', 'G', 'T'};
     // database: reads of varying length cut from a small genome (so that many words repeat)
     std::vector<unsigned char> genome(3000);
@@ -30,12 +32,12 @@ int main(int argc, char **argv) {
     std::vector<uint64_t> ds, qs;
     for (int r = 0; r < 120; r++) {
         ds.push_back(D.size());
-        int len = 12 + rnd() % 200, at = rnd() % (genome.size() - len);
+        int len = k + rnd() % 200, at = rnd() % (genome.size() - len);
         for (int i = 0; i < len; i++) D.push_back((rnd() % 100 < 2) ? B[rnd() & 3] : genome[at + i]);
     }
     for (int r = 0; r < 60; r++) {
         qs.push_back(Q.size());
-        int len = 11 + rnd() % 200, at = rnd() % (genome.size() - len);
+        int len = k - 1 + rnd() % 200, at = rnd() % (genome.size() - len);
         for (int i = 0; i < len; i++) Q.push_back((rnd() % 100 < 5) ? B[rnd() & 3] : genome[at + i]);
     }
     ds.push_back(D.size()); qs.push_back(Q.size());
@@ -52,7 +54,7 @@ int main(int argc, char **argv) {
     std::unordered_multimap<uint32_t, uint32_t> qwords;  // code -> e
     for (size_t r = 0; r + 1 < qs.size(); r++) {
         int64_t lo = r == 0 ? (int64_t)qs[r] : (int64_t)qs[r] - 1;
-        for (int64_t e = lo + 11; e < (int64_t)qs[r + 1]; e++) qwords.emplace(fetch16(qpk.data(), e - 11) & KMASK, (uint32_t)e);
+        for (int64_t e = lo + k - 1; e < (int64_t)qs[r + 1]; e++) qwords.emplace(fetch16(qpk.data(), e - (k - 1)) & kmask, (uint32_t)e);
     }
     std::vector<uint32_t> lut2(EXT_LUT3_SIZE);
     build_ext_lut3(lut2.data());
@@ -63,34 +65,34 @@ int main(int argc, char **argv) {
     }
     long hits = 0, bad = 0;
     for (size_t s = 0; s + 1 < ds.size(); s++)
-        for (uint64_t x = ds[s] + 11; x < ds[s + 1]; x++) {
-            uint32_t code = fetch16(dpk.data(), x - 11) & KMASK;
+        for (uint64_t x = ds[s] + k - 1; x < ds[s + 1]; x++) {
+            uint32_t code = fetch16(dpk.data(), x - (k - 1)) & kmask;
             auto range = qwords.equal_range(code);
             for (auto it = range.first; it != range.second; ++it) {
                 uint32_t e = it->second, p = (uint32_t)x + 1;
                 // read containing e
                 size_t r = 0;
                 while (qs[r + 1] <= e) r++;
-                int64_t want = orc_extend(&db, &q, p, (uint64_t)e + 1, r, s);
-                int got = extend_hit(dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                int64_t want = orc_extend_k(&db, &q, p, (uint64_t)e + 1, r, s, k);
+                int got = extend_hit(dpk.data(), qpk.data(), p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1], k);
                 ExtState st;
-                ext_init(st, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
-                while (st.phase < 2) ext_window(st, lut2.data(), dpk.data(), qpk.data(), p, e);
-                if (want != ext_result(st)) { if (bad++ < 10) printf("WINDOW MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, ext_result(st)); }
+                ext_init(st, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1], k);
+                while (st.phase < 2) ext_window(st, lut2.data(), dpk.data(), qpk.data(), p, e, k);
+                if (want != ext_result(st, k)) { if (bad++ < 10) printf("WINDOW MISMATCH s=%zu r=%zu p=%u e=%u want=%ld got=%d\n", s, r, p, e, (long)want, ext_result(st, k)); }
                 {   // the scan kernel's form: first windows of two hits at once, the rest window by window
                     static ExtState prev; static uint32_t prev_p = 0, prev_e = 0; static long prev_want = 0; static bool have_prev = false;
                     ExtState cur;
-                    ext_init(cur, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1]);
+                    ext_init(cur, p, e, (uint32_t)ds[s], (uint32_t)ds[s + 1], (uint32_t)qs[r], (uint32_t)qs[r + 1], k);
                     if (have_prev) {
                         uint32_t mfa, mba, mfb, mbb;
                         ExtState A = prev, Bst = cur;
-                        ext_first_masks(A, dpk.data(), qpk.data(), prev_p, prev_e, mfa, mba);
-                        ext_first_masks(Bst, dpk.data(), qpk.data(), p, e, mfb, mbb);
-                        ext_first2(A, Bst, lut2.data(), mfa, mba, mfb, mbb);
-                        while (A.phase < 2) ext_window(A, lut2.data(), dpk.data(), qpk.data(), prev_p, prev_e);
-                        while (Bst.phase < 2) ext_window(Bst, lut2.data(), dpk.data(), qpk.data(), p, e);
-                        if (prev_want != ext_result(A)) { if (bad++ < 10) printf("FIRST2(A) MISMATCH p=%u e=%u want=%ld got=%d\n", prev_p, prev_e, prev_want, ext_result(A)); }
-                        if (want != ext_result(Bst)) { if (bad++ < 10) printf("FIRST2(B) MISMATCH p=%u e=%u want=%ld got=%d\n", p, e, (long)want, ext_result(Bst)); }
+                        ext_first_masks(A, dpk.data(), qpk.data(), prev_p, prev_e, mfa, mba, k);
+                        ext_first_masks(Bst, dpk.data(), qpk.data(), p, e, mfb, mbb, k);
+                        ext_first2(A, Bst, lut2.data(), mfa, mba, mfb, mbb, k);
+                        while (A.phase < 2) ext_window(A, lut2.data(), dpk.data(), qpk.data(), prev_p, prev_e, k);
+                        while (Bst.phase < 2) ext_window(Bst, lut2.data(), dpk.data(), qpk.data(), p, e, k);
+                        if (prev_want != ext_result(A, k)) { if (bad++ < 10) printf("FIRST2(A) MISMATCH p=%u e=%u want=%ld got=%d\n", prev_p, prev_e, prev_want, ext_result(A, k)); }
+                        if (want != ext_result(Bst, k)) { if (bad++ < 10) printf("FIRST2(B) MISMATCH p=%u e=%u want=%ld got=%d\n", p, e, (long)want, ext_result(Bst, k)); }
                     }
                     prev = cur; prev_p = p; prev_e = e; prev_want = (long)want; have_prev = true;
                 }

@@ -74,7 +74,7 @@ def oracle():
     return _oracle
 
 
-def default_params(n_threads=4, evalue=None, coverage=0.5, identity=0.5, igap=5, egap=2, db_total_len_global=0):
+def default_params(n_threads=4, evalue=None, coverage=0.5, identity=0.5, igap=5, egap=2, db_total_len_global=0, k=12):
     """Thresholds exactly as src/IMSAME.c:44-47,552-569 derives them."""
     p = OrcParams()
     if evalue is None:
@@ -86,7 +86,7 @@ def default_params(n_threads=4, evalue=None, coverage=0.5, identity=0.5, igap=5,
     p.igap = -int(igap)
     p.egap = -int(egap)
     p.n_threads = n_threads
-    p.k = 12
+    p.k = k  # 12 = FIXED_K (src/structs.h:15), the only value the reference itself can pin
     p.db_total_len_global = db_total_len_global
     return p
 

@@ -54,6 +54,18 @@ def test_cli_matches_oracle_file_on_fresh_input(gpu, tmp_path):
     assert len(hp.parse_align_headers(mine)) > 150
 
 
+def test_cli_kmer_flag_matches_generalised_oracle(gpu, tmp_path):
+    """-kmer (no such flag in the reference: FIXED_K = 12 is compiled in) against the oracle with FIXED_K = 10"""
+    dbf, qf = os.path.join(G, "dirty.db.fa"), os.path.join(G, "dirty.q.fa")
+    mine, orc = str(tmp_path / "mine.align"), str(tmp_path / "orc.align")
+    subprocess.check_call([EXE, "-query", qf, "-db", dbf, "-out", mine, "-n_threads", "1", "-kmer", "10", "-evalue", "1e-10",
+                           "-coverage", "0.3", "-identity", "0.6", "-igap", "4", "-egap", "1"], stdout=subprocess.DEVNULL)
+    hp.oracle_align(hp.OracleSeqs(dbf, True), hp.OracleSeqs(qf, False),
+                    hp.default_params(n_threads=1, evalue=1e-10, coverage=0.3, identity=0.6, igap=4, egap=1, k=10), out_path=orc)
+    assert open(mine, "rb").read() == open(orc, "rb").read()
+    assert len(hp.parse_align_headers(mine)) > 10
+
+
 def test_cli_without_out_prints_summary_only(gpu):
     r = subprocess.run([EXE, "-query", os.path.join(G, "synth150.q.fa"), "-db", os.path.join(G, "synth150.db.fa"),
                         "-n_threads", "1"], capture_output=True, text=True)

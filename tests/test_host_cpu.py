@@ -87,6 +87,7 @@ def test_threshold_tables_are_exact(built):
 
 
 @pytest.mark.parametrize("prog,args", [("nw_emul", ["400", "3"]), ("nwp_emul", ["3000", "5"]), ("extend_emul", ["5"]),
+                                       ("extend_emul", ["6", "8"]), ("extend_emul", ["7", "15"]),
                                        ("tb_emul", ["300", "4"])])
 def test_device_functions_on_cpu(built, prog, args, tmp_path):
     """the HD functions the kernels are made of (nw_core.cuh, nwp_core.cuh, extend.cuh, traceback.cuh) + render.c,
@@ -154,6 +155,8 @@ def test_cli_flags_and_errors(built, tmp_path):
     q = os.path.join(G, "dirty.q.fa")
     r = subprocess.run([exe, "-query", q, "-db", q, "-coverage", "0"], capture_output=True, text=True)
     assert r.returncode == 255 and "Min-coverage must be larger than zero" in r.stdout
+    r = subprocess.run([exe, "-query", q, "-db", q, "-kmer", "16"], capture_output=True, text=True)
+    assert r.returncode == 255 and "The seed length must be between 4 and 15" in r.stdout
     if hp.have_reference():
         for args in (["--help"], ["-query", "nope"], ["-query", q, "-db", q, "-identity", "-1"]):
             a = subprocess.run([exe] + args, capture_output=True, text=True)

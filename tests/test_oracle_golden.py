@@ -68,3 +68,18 @@ def test_oracle_vs_live_reference(seed, div, n_threads, tmp_path):
         assert open(ref_out, "rb").read() == open(orc_out, "rb").read()
     assert hp.parse_align_headers(ref_out) == hp.parse_align_headers(orc_out)
     assert len(hp.parse_align_headers(ref_out)) > 100
+
+
+@pytest.mark.parametrize("k", [8, 10, 14])
+def test_generalised_seed_length_forms_agree(k):
+    """k != 12 has no reference (FIXED_K is compiled in, src/structs.h:15): the oracle generalised to
+    FIXED_K = k is only checked for self-consistency -- scan order with early exit == order-free min-key
+    form -- and is pinned to the reference at k = 12 by the tests above"""
+    db = hp.OracleSeqs(os.path.join(G, "dirty.db.fa"), True)
+    q = hp.OracleSeqs(os.path.join(G, "dirty.q.fa"), False)
+    p = hp.default_params(n_threads=3, evalue=1e-10, coverage=0.3, identity=0.6, igap=4, egap=1, k=k)
+    seq, st1 = hp.oracle_align(db, q, p)
+    bulk, st2 = hp.oracle_align(db, q, p, bulk=True)
+    nq = int(q.s.n_seqs)
+    assert hp.best_to_records(seq, nq) == hp.best_to_records(bulk, nq)
+    assert st2.hits >= st1.hits > 0
