@@ -380,6 +380,12 @@ def run_ours(args):
         # K2 algorithmic bytes: Nd/4 + 8 per db word + 4 per hit + 16 per passing hit
         k2_bytes = nd * L / 4 + 8 * float(agg[5].item()) / world + 4 * float(agg[3].item()) / world + 16 * float(agg[6].item()) / world
         k2_gbs = k2_bytes / (ms_k2_max * 1e-3) / 1e9 if ms_k2_max > 0 else 0.0
+        try:  # per-launch DRAM traffic of the two hot kernels out of committed `ncu --set full` captures (tools/ncu_traffic.py)
+            _tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        except Exception:
+            _tr = {}
+        k3_traffic = (_tr.get("nwp_kernel") or _tr.get("nwp_kernel_scale005") or {}) if packed else {}
+        k2_traffic = _tr.get("scan_kernel") or {}
         line = {
             "metric": "query reads aligned/sec", "value": world * nq / (ms_step * 1e-3), "unit": "reads/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -401,9 +407,10 @@ def run_ours(args):
                          "bound": "int32-issue",
                          "achieved": achieved, "peak": int_peak, "unit": "Gop/s",
                          "frac": (achieved / int_peak) if int_peak else None,
-                         "traffic": None,
-                         "traffic_note": "register/shared-memory resident: ncu dram bytes per launch are ~1e-4 of the kernel's "
-                                         "integer work (profiles/r01_ncu_nwp_v4_metrics.txt), HBM is not a bound",
+                         "traffic": k3_traffic.get("dram_bytes_per_launch"),
+                         "traffic_note": "dram__bytes_read + dram__bytes_write of one `ncu --set full` launch (profiles/ncu_traffic.json: "
+                                         + str(k3_traffic.get("report")) + ", " + str(k3_traffic.get("note")) + "); the kernel is register/"
+                                         "shared-memory resident, HBM is not its bound",
                          "ops_per_cell": ops_per_cell, "gcups": gcups,
                          "gcups_roofline": (int_peak / ops_per_cell) if ops_per_cell else None,
                          "frac_survey24": (gcups * OPS_PER_CELL_GENERIC / int_peak) if int_peak else None,
@@ -414,7 +421,10 @@ def run_ours(args):
                          "int_peak_table": ipk},
             "roofline_k2": {"kernel": "scan_kernel (K2, db scan + extension)", "bound": "hbm", "achieved": k2_gbs,
                             "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                            "frac": k2_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "traffic": None,
+                            "frac": k2_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                            "traffic": k2_traffic.get("dram_bytes_per_launch"),
+                            "traffic_note": "per launch = one database segment of <= 0.5 Gbase (profiles/ncu_traffic.json: "
+                                            + str(k2_traffic.get("report")) + "); the algorithmic bytes of `achieved` are per step",
                             "peak_source": which},
             "e2e": e2e, "gpu_launches": int(sum(s["total_launches"] for s in stats_steps)),
             "clocks": clocks, "gen_seconds": t_gen,
