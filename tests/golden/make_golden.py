@@ -26,8 +26,9 @@ def summary_lines(stdout):
     return "".join(l + "\n" for l in stdout.splitlines() if "from the query were found" in l or "Jaccard" in l)
 
 
-def run_case(name, extra=()):
-    db, q = (os.path.join(HERE, f"{name}.{k}.fa") for k in ("db", "q"))
+def run_case(name, extra=(), db_name=None):
+    db = os.path.join(HERE, f"{db_name or name}.db.fa")
+    q = os.path.join(HERE, f"{name}.q.fa")
     out1 = os.path.join(HERE, f"{name}.t1.align")
     so = hp.run_reference(q, db, out1, n_threads=1, extra=extra)
     open(os.path.join(HERE, f"{name}.stdout"), "w").write(summary_lines(so))
@@ -75,6 +76,15 @@ def main():
     dirty(reads, 160, os.path.join(HERE, "dirty.db.fa"), True)
     dirty(qreads, 40, os.path.join(HERE, "dirty.q.fa"), False)
     run_case("dirty", extra=("-coverage", "0.3", "-identity", "0.6", "-evalue", "1e-10", "-igap", "4", "-egap", "1"))
+    # 3 query reads: -n_threads 4 > n_seqs (reads_per_thread = 0, src/IMSAME.c:414,452) and an explicit
+    # "-evalue 1e-20" (atof -> double -> long double, src/IMSAME.c:553: not the default's bit pattern, :44)
+    lines = open(os.path.join(HERE, "synth150.q.fa"), "rb").read().split(b"\n")
+    picked, n = [], 0
+    for i in range(0, len(lines) - 1, 2):
+        if i // 2 in (1, 4, 7):
+            picked += [lines[i], lines[i + 1]]
+    open(os.path.join(HERE, "few.q.fa"), "wb").write(b"\n".join(picked) + b"\n")
+    run_case("few", extra=("-evalue", "1e-20"), db_name="synth150")
 
 
 if __name__ == "__main__":

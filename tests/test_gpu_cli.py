@@ -12,7 +12,13 @@ import synth_cases as sc
 pytestmark = pytest.mark.gpu
 G = os.path.join(hp.ROOT, "tests", "golden")
 EXE = os.path.join(hp.ROOT, "bin", "IMSAME")
-FLAGS = {"synth150": [], "dirty": ["-coverage", "0.3", "-identity", "0.6", "-evalue", "1e-10", "-igap", "4", "-egap", "1"]}
+FLAGS = {"synth150": [], "dirty": ["-coverage", "0.3", "-identity", "0.6", "-evalue", "1e-10", "-igap", "4", "-egap", "1"],
+         "few": ["-evalue", "1e-20"]}  # 3 query reads (fewer than threads in the t4 case) against synth150's database
+DB_OF = {"few": "synth150"}
+
+
+def db_path(name):
+    return os.path.join(G, f"{DB_OF.get(name, name)}.db.fa")
 
 
 def info_lines(stdout):
@@ -22,7 +28,7 @@ def info_lines(stdout):
 @pytest.mark.parametrize("name", sorted(FLAGS))
 def test_cli_t1_output_is_byte_identical_to_reference(gpu, name, tmp_path):
     out = str(tmp_path / "o.align")
-    r = subprocess.run([EXE, "-query", os.path.join(G, f"{name}.q.fa"), "-db", os.path.join(G, f"{name}.db.fa"),
+    r = subprocess.run([EXE, "-query", os.path.join(G, f"{name}.q.fa"), "-db", db_path(name),
                         "-out", out, "-n_threads", "1"] + FLAGS[name], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert open(out, "rb").read() == open(os.path.join(G, f"{name}.t1.align"), "rb").read()
@@ -32,7 +38,7 @@ def test_cli_t1_output_is_byte_identical_to_reference(gpu, name, tmp_path):
 @pytest.mark.parametrize("name", sorted(FLAGS))
 def test_cli_t4_headers_equal_reference(gpu, name, tmp_path):
     out = str(tmp_path / "o.align")
-    subprocess.check_call([EXE, "-query", os.path.join(G, f"{name}.q.fa"), "-db", os.path.join(G, f"{name}.db.fa"),
+    subprocess.check_call([EXE, "-query", os.path.join(G, f"{name}.q.fa"), "-db", db_path(name),
                            "-out", out, "-n_threads", "4"] + FLAGS[name], stdout=subprocess.DEVNULL)
     got = sorted(l for l in open(out, "rb").read().split(b"\n") if hp.HEADER_RE.match(l))
     want = [l for l in open(os.path.join(G, f"{name}.t4.headers"), "rb").read().split(b"\n") if l]

@@ -10,12 +10,19 @@ G = os.path.join(hp.ROOT, "tests", "golden")
 CASES = {
     "synth150": dict(),
     "dirty": dict(coverage=0.3, identity=0.6, evalue=1e-10, igap=4, egap=1),
+    # 3 query reads against synth150's database: -n_threads 4 > n_seqs, explicit -evalue 1e-20 (double, not the default's long double)
+    "few": dict(evalue=1e-20),
 }
+DB_OF = {"few": "synth150"}
+
+
+def db_path(name):
+    return os.path.join(G, f"{DB_OF.get(name, name)}.db.fa")
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_t1_bytes_equal_reference(name, tmp_path):
-    db = hp.OracleSeqs(os.path.join(G, f"{name}.db.fa"), True)
+    db = hp.OracleSeqs(db_path(name), True)
     q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
     out = str(tmp_path / "o.align")
     best, st = hp.oracle_align(db, q, hp.default_params(n_threads=1, **CASES[name]), out_path=out)
@@ -27,7 +34,7 @@ def test_oracle_t1_bytes_equal_reference(name, tmp_path):
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_t4_headers_equal_reference(name, tmp_path):
     """-n_threads changes which reads see the cross-read 'phantom' word"""
-    db = hp.OracleSeqs(os.path.join(G, f"{name}.db.fa"), True)
+    db = hp.OracleSeqs(db_path(name), True)
     q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
     out = str(tmp_path / "o.align")
     hp.oracle_align(db, q, hp.default_params(n_threads=4, **CASES[name]), out_path=out)
@@ -40,14 +47,14 @@ def test_oracle_t4_headers_equal_reference(name, tmp_path):
 @pytest.mark.parametrize("n_threads", [1, 3, 4])
 def test_bulk_min_key_form_equals_scan_order(name, n_threads):
     """winner(read) = argmin (k-mer end asc, db pos desc) over accepted candidates == first accepted"""
-    db = hp.OracleSeqs(os.path.join(G, f"{name}.db.fa"), True)
+    db = hp.OracleSeqs(db_path(name), True)
     q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
     p = hp.default_params(n_threads=n_threads, **CASES[name])
     a, _ = hp.oracle_align(db, q, p)
     b, _ = hp.oracle_align(db, q, p, bulk=True)
     nq = int(q.s.n_seqs)
     assert hp.best_to_records(a, nq) == hp.best_to_records(b, nq)
-    assert len(hp.best_to_records(a, nq)) > 5
+    assert len(hp.best_to_records(a, nq)) > (5 if nq > 5 else 1)
 
 
 @pytest.mark.skipif(not hp.have_reference(), reason="oracle/_ref/IMSAME not built (no /root/reference here)")
