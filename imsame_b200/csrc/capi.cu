@@ -70,7 +70,7 @@ struct imsame_ctx {
     PairRec *pairs = nullptr;
     PairRes *res = nullptr;
     uint32_t *d_small = nullptr;  // [0] n_pairs, [1] work head
-    unsigned long long *d_counters = nullptr;  // [0..3] scan counters, [4] cells, [5] pairs total
+    unsigned long long *d_counters = nullptr;  // [0..3] scan counters, [4] cells, [5] pairs total, [6] pairs aligned, [7] pairs needed in hindsight
     int *d_overflow = nullptr;
     unsigned long long *keys = nullptr, *payload = nullptr, *pkey = nullptr;
     uint64_t keys_cap = 0;
@@ -975,6 +975,9 @@ extern "C" int imsame_gpu_run_end(imsame_ctx *ctx, imsame_stats *st) {
         if (cnt[2] > 0) return IMSAME_EREADSIZE;
     }
     fill_stats(ctx, st, cnt);
+    if (getenv("IMSAME_TRACE"))
+        fprintf(stderr, "[imsame] candidate pairs %llu, aligned %llu, not after their read's final hit in scan order %llu\n",
+                cnt[5], cnt[6], cnt[7]);
     return IMSAME_OK;
 }
 

@@ -373,14 +373,18 @@ __global__ void select_kernel(const PairRec *pairs, const PairRes *res, uint32_t
                               const unsigned long long *best, unsigned long long *payload,
                               unsigned long long *pkey, uint64_t seg_seq_base, unsigned long long *pairs_total) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(pairs_total, (unsigned long long)n);
+    unsigned needed = 0;  // diagnostic: candidates not later in scan order than their read's final hit
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const PairRec pr = pairs[i];
         const PairRes z = res[i];
+        needed += pr.key <= best[pr.r] ? 1u : 0u;
         if ((z.stats & 0x80000000u) && pr.key == best[pr.r]) {
             payload[pr.r] = ((unsigned long long)(seg_seq_base + pr.s) << 32) | (z.stats & 0x7FFFFFFFu);
             pkey[pr.r] = pr.key;  // the key this payload belongs to (run_end drops superseded payloads)
         }
     }
+    needed = __reduce_add_sync(0xffffffffu, needed);
+    if ((threadIdx.x & 31) == 0 && needed) atomicAdd(pairs_total + 2, (unsigned long long)needed);  // counters[7]
 }
 
 // multi-shard: keep the payload only where this shard owns the reduced key
