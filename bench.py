@@ -203,9 +203,12 @@ def run_reference_arm(args):
             "config": {"workload": w["name"], "sample": r["sample"]},
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": r["cores"], "kind": "reference",
                              "sample": r["sample"], "reads_per_s_whole_process": r["reads_per_s_process"]},
-            "e2e": {"value": r["reads_per_s_index_plus_align"], "unit": "reads/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 0,
-                    "what": "index build (src/IMSAME.c:196-289) + alignment phase (:409-467), FASTA already parsed is not separable"}}
+            # the contract: the reference arm's e2e repeats the line's own value.  It is the alignment phase alone
+            # (src/IMSAME.c:409-467), the figure that flatters the reference: on this down-scaled sample its
+            # single-threaded index build (:232-281, part of what imsame_gpu_align replaces) costs 10x the phase
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "what": "alignment phase of the reference (src/IMSAME.c:409-467) on all host threads",
+                    "reads_per_s_index_plus_align": r["reads_per_s_index_plus_align"]}}
     OUT.emit(json.dumps(line))
 
 
