@@ -223,7 +223,7 @@ class Imsame:
         self._check(lib().imsame_gpu_set_nw_mode(self._h, int(mode)))
 
     def set_kmer(self, k):
-        """seed length, 4..15 (default 12 = the reference's FIXED_K); call before set_query / align"""
+        """seed length, 4..16 (default 12 = the reference's FIXED_K); call before set_query / align"""
         self._check(lib().imsame_gpu_set_kmer(self._h, int(k)))
 
     def align(self, db, query, params=None, db_breaks=None):

@@ -602,8 +602,8 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
         blk_kernel<<<std::min<uint32_t>((nq + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ctx->q_start, nq, ctx->q_blk);
         ctx->launches++;
     }
-    const uint32_t ncodes = ncodes_of(ctx->k);
-    const uint32_t n_tiles = (ncodes + SCAN_TILE - 1) / SCAN_TILE;
+    const uint64_t ncodes = ncodes_of(ctx->k);
+    const uint32_t n_tiles = (uint32_t)((ncodes + SCAN_TILE - 1) / SCAN_TILE);
     if (ctx->k_tables != ctx->k) {
         dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
         ctx->off = ctx->cursor = ctx->tile_sums = nullptr;

@@ -24,9 +24,9 @@ namespace imsame {
 constexpr int K = 12;                    // FIXED_K, src/structs.h:15
 constexpr uint32_t KMASK = (1u << (2 * K)) - 1;
 constexpr uint32_t NCODES = 1u << (2 * K);
-constexpr int K_MIN = 4, K_MAX = 15;     // run-time seed lengths (imsame_gpu_set_kmer): 4^k + 1 offsets fit 32 bits
-IMS_HD uint32_t kmask_of(int k) { return (1u << (2 * k)) - 1u; }
-IMS_HD uint32_t ncodes_of(int k) { return 1u << (2 * k); }
+constexpr int K_MIN = 4, K_MAX = 16;     // run-time seed lengths (imsame_gpu_set_kmer): a word is one 32-bit code
+IMS_HD uint32_t kmask_of(int k) { return k >= 16 ? 0xFFFFFFFFu : (1u << (2 * k)) - 1u; }
+IMS_HD uint64_t ncodes_of(int k) { return 1ull << (2 * k); }
 constexpr int MAX_READ = 3000;           // MAX_READ_SIZE, src/structs.h:19
 constexpr uint64_t KEY_NONE = 0x7FFFFFFFFFFFFFFFull;
 constexpr int KEY_POS_BITS = 40;

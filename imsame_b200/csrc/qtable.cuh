@@ -112,10 +112,10 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 
 // phase 0: per-tile sums ; phase 2: write exclusive offsets (tile offset + local scan)
 template <int PHASE>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t *__restrict__ in, uint32_t n,
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(const uint32_t *__restrict__ in, uint64_t n,
                                                                   uint32_t *__restrict__ tile_sums,
                                                                   uint32_t *__restrict__ out) {
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;  // 4^16 counters: 64-bit
     uint32_t v[SCAN_ITEMS], s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             if (q >= xs + (uint32_t)(k - 1) && !word_broken(a, q, k)) {
                 const uint32_t code = fetch16(a.db.pk, (uint64_t)q - (uint32_t)(k - 1)) & kmask_of(k);
                 b0 = a.off[code];
-                cnt = a.off[code + 1] - b0;
+                cnt = a.off[(size_t)code + 1] - b0;
                 c_words++;
             }
         }

@@ -14,7 +14,7 @@
  *
  * Opt-in additions that default to reference behaviour:
  *   -gpus N     shard the database by contiguous read ranges over N GPUs (default 1)
- *   -kmer K     seed length 4..15 (default 12 = the reference's FIXED_K; it has no such flag)
+ *   -kmer K     seed length 4..16 (default 12 = the reference's FIXED_K; it has no such flag)
  *   -device D   first CUDA device to use (default 0)
  */
 #define _GNU_SOURCE
@@ -101,7 +101,7 @@ static void parse_args(int argc, char **av, cli_args *a) {
         if (strcmp(av[i], "-device") == 0 && nxt) a->device = atoi(nxt);
         if (strcmp(av[i], "-kmer") == 0 && nxt) {
             a->kmer = atoi(nxt);
-            if (a->kmer < 4 || a->kmer > 15) terror("The seed length must be between 4 and 15");
+            if (a->kmer < 4 || a->kmer > 16) terror("The seed length must be between 4 and 16");
         }
     }
 }

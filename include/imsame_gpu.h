@@ -165,10 +165,11 @@ int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode);
 
 /* Seed length k.  The reference has exactly one: FIXED_K = 12 (src/structs.h:15),
  * wired into its 12-dimensional Container (src/alignmentFunctions.h:4-6); that is the default here and
- * the only value with a reference to compare against.  Any 4 <= k <= 15 behaves like the reference
+ * the only value with a reference to compare against.  Any 4 <= k <= 16 behaves like the reference
  * recompiled with FIXED_K = k over a flat 4^k table (word positions, phantom word, extension start
  * score k*POINT, t_len).  Call before imsame_gpu_set_query / imsame_gpu_align; a resident query table
- * built with another k is dropped.  The word table needs 2 * 4 * (4^k + 1) bytes of device memory. */
+ * built with another k is dropped.  The word table needs 2 * 4 * (4^k + 1) bytes of device memory
+ * (134 MB at k = 12, 34 GB at k = 16). */
 int imsame_gpu_set_kmer(imsame_ctx *ctx, int k);
 
 /* ---- winners-only traceback (src/alignmentFunctions.c:493-546) ---------- */

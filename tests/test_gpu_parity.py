@@ -280,28 +280,35 @@ def test_runtime_seed_length_matches_generalised_oracle(gpu, k):
 
 
 def test_seed_length_limits(gpu):
-    """k outside 4..15 is refused; k = 15 (2 x 4 GiB of offsets; the oracle's host index stops at 14) is checked
-    through properties: every record's seed is an exact 15-mer match at the reported positions, inside both
-    reads, and its (length, identities) are the oracle's NW result for that pair"""
     from imsame_b200 import api
-    for k in (3, 16, 0, -1):
+    for k in (3, 17, 0, -1):
         with pytest.raises(api.ImsameError):
             gpu.set_kmer(k)
+
+
+@pytest.mark.parametrize("k", [15, 16])
+def test_longest_seeds_through_properties(gpu, k):
+    """k = 15 / 16 (2 x 4 GiB / 2 x 17 GiB of offsets, 64-bit table indices; the oracle's host index stops at 14):
+    every record's seed is an exact k-mer match at the reported positions, inside both reads, and its
+    (length, identities) are the oracle's NW result for that pair; the scan visits every database word once"""
+    from imsame_b200 import api
     db, ds, q, qs = sc.fixed_case(5, 2, 20000, 100, 2000, 300, 0.01)
     try:
-        gpu.set_kmer(15)
-        out, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=1))
+        gpu.set_kmer(k)
+        out, st = gpu.align((db, ds), (q, qs), api.make_params(n_threads=1))
     finally:
         gpu.set_kmer(12)
+    # words the scan saw: every position of every database read that ends a k-mer
+    assert st["n_db_kmers"] == 2000 * (100 - k + 1)
     lib = hp.oracle()
     n = 0
     for r, o in enumerate(out):
         if not o["accepted"]:
             continue
         e, p, s = int(o["qpos_end"]), int(o["db_pos"]), int(o["db_seq"])
-        assert int(ds[s]) <= p - 15 and p <= int(ds[s + 1])
-        assert int(qs[r]) - 1 <= e - 14 and e < int(qs[r + 1])  # - 1: the phantom word
-        assert bytes(q[e - 14:e + 1]) == bytes(db[p - 15:p])
+        assert int(ds[s]) <= p - k and p <= int(ds[s + 1])
+        assert int(qs[r]) - 1 <= e - (k - 1) and e < int(qs[r + 1])  # - 1: the phantom word
+        assert bytes(q[e - (k - 1):e + 1]) == bytes(db[p - k:p])
         x, y = db[int(ds[s]):int(ds[s + 1])], q[int(qs[r]):int(qs[r + 1])]
         assert (int(o["length"]), int(o["identities"])) == _oracle_nw(lib, x, y, 5, 2)[3:]
         n += 1

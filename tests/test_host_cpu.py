@@ -155,8 +155,8 @@ def test_cli_flags_and_errors(built, tmp_path):
     q = os.path.join(G, "dirty.q.fa")
     r = subprocess.run([exe, "-query", q, "-db", q, "-coverage", "0"], capture_output=True, text=True)
     assert r.returncode == 255 and "Min-coverage must be larger than zero" in r.stdout
-    r = subprocess.run([exe, "-query", q, "-db", q, "-kmer", "16"], capture_output=True, text=True)
-    assert r.returncode == 255 and "The seed length must be between 4 and 15" in r.stdout
+    r = subprocess.run([exe, "-query", q, "-db", q, "-kmer", "17"], capture_output=True, text=True)
+    assert r.returncode == 255 and "The seed length must be between 4 and 16" in r.stdout
     if hp.have_reference():
         for args in (["--help"], ["-query", "nope"], ["-query", q, "-db", q, "-identity", "-1"]):
             a = subprocess.run([exe] + args, capture_output=True, text=True)
