@@ -1236,6 +1236,21 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
         }
     }
     std::vector<uint64_t> n_ops_of(nq, 0), first_op(nq, 0);
+    // the op slots of a batch (xlen + ylen + 2 words per pair, ~50 MB) come back through one pinned buffer that is
+    // reused by every batch: as a fresh std::vector per batch they cost a 1 GB zero-fill and a 1 GB pageable copy
+    // on cfg2 (519 k winners)
+    struct Pinned {
+        uint32_t *p = nullptr; uint64_t cap = 0;
+        ~Pinned() { if (p) cudaFreeHost(p); }
+        bool ensure(uint64_t n) {
+            if (n <= cap) return true;
+            if (p) cudaFreeHost(p);
+            p = nullptr; cap = 0;
+            if (cudaMallocHost((void **)&p, (size_t)n * 4) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+            cap = n;
+            return true;
+        }
+    } h_ops;
     size_t w0 = 0;
     while (w0 < winners.size()) {
         // batch: as many winners as fit the table budget
@@ -1288,10 +1303,11 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
                 pb.dr, d_tb, d_tboff, d_str, nb, d_ops, d_opoff, d_nops, d_end);
             ctx->launches++;
         }
-        std::vector<uint32_t> h_ops(op_elems), h_nops(nb), h_end(2ull * nb);
+        std::vector<uint32_t> h_nops(nb), h_end(2ull * nb);
         std::vector<PairRes> h_res(nb);
         cudaError_t ce = cudaGetLastError();
-        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_ops.data(), d_ops, op_elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess && !h_ops.ensure(op_elems)) { cleanup(); return IMSAME_ENOMEM; }
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_ops.p, d_ops, op_elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_nops.data(), d_nops, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_end.data(), d_end, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
         if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_res.data(), pb.dr, (size_t)nb * sizeof(PairRes), cudaMemcpyDeviceToHost, ctx->stream);
@@ -1303,7 +1319,7 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
             const uint64_t r = winners[w0 + i];
             first_op[r] = all_ops.size();
             n_ops_of[r] = h_nops[i];
-            all_ops.insert(all_ops.end(), h_ops.begin() + op_off[i], h_ops.begin() + op_off[i] + h_nops[i]);
+            all_ops.insert(all_ops.end(), h_ops.p + op_off[i], h_ops.p + op_off[i] + h_nops[i]);
             cell_xy[4 * r] = h_res[i].bx; cell_xy[4 * r + 1] = h_res[i].by;
             cell_xy[4 * r + 2] = h_end[2 * i]; cell_xy[4 * r + 3] = h_end[2 * i + 1];
         }
