@@ -176,7 +176,9 @@ int main(int argc, char **av) {
     char err[300];
     imsame_ctx *ctx = NULL;
     if (booting) {
+        const double tw = now_s();
         pthread_join(boot_thread, NULL);
+        if (jo.trace) fprintf(stderr, "[imsame] waited %.3f s for the CUDA context after parsing the FASTA files\n", now_s() - tw);
         ctx = boot.rc == IMSAME_OK ? boot.ctx : NULL; /* on failure run_job tries again and reports */
     }
     int rc = imsame_run_job(&q, &db, &jo, fout, ctx ? &ctx : NULL, &accepted, err, sizeof err);
