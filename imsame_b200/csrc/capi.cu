@@ -91,6 +91,7 @@ struct imsame_ctx {
     uint8_t *stage = nullptr;
     uint8_t *pin[2] = {nullptr, nullptr};  // pinned bounce buffers (upload_pack), their copy-done events
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+    bool pin_busy[2] = {false, false};     // a copy out of the buffer has been enqueued (wait for pin_ev before refilling)
     int nw_grid[9] = {0};
     int nwp_grid[9] = {0};
     bool in_align = false;  // imsame_gpu_align: upload phases belong to the same stats
@@ -290,12 +291,14 @@ int upload_pack(imsame_ctx *ctx, const unsigned char *host, uint64_t n, uint32_t
             for (uint64_t at = 0; at < n; at += PIN_BYTES, i++) {
                 const int b = (int)(i & 1);
                 const uint64_t len = std::min<uint64_t>(PIN_BYTES, n - at);
-                if (i >= 2) CK(cudaEventSynchronize(ctx->pin_ev[b]));  // its previous content has left
+                // its previous content has left (also across calls: segments are uploaded back to back)
+                if (ctx->pin_busy[b]) CK(cudaEventSynchronize(ctx->pin_ev[b]));
                 par_memcpy(ctx->pin[b], host + at, len);
                 {
                     PhaseScope ps(ctx, PH_H2D);
                     CK(cudaMemcpyAsync(ctx->stage, ctx->pin[b], len, cudaMemcpyHostToDevice, ctx->stream));
                     CK(cudaEventRecord(ctx->pin_ev[b], ctx->stream));
+                    ctx->pin_busy[b] = true;
                     ctx->h2d_bytes += len;
                 }
                 {
