@@ -52,9 +52,9 @@ bin/all_vs_all_metagenomes_IMSAME.sh: scripts/all_vs_all_metagenomes_IMSAME.sh
 	cp scripts/all_vs_all_metagenomes_IMSAME.sh $@ && chmod +x $@
 
 oracle: oracle/_build/liboracle.so
-oracle/_build/liboracle.so: oracle/imsame_oracle.c oracle/imsame_oracle.h
+oracle/_build/liboracle.so: oracle/imsame_oracle.c oracle/imsame_sampled.c oracle/imsame_oracle.h
 	@mkdir -p oracle/_build
-	$(CC) -O2 -fPIC -Wall -shared oracle/imsame_oracle.c -lm -o $@
+	$(CC) -O2 -fPIC -Wall $(OMPFLAG) -shared oracle/imsame_oracle.c oracle/imsame_sampled.c -lm -o $@
 
 ref:
 	sh oracle/build_ref.sh

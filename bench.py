@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--nw-mode", type=int, default=0, help="0: packed-word K3 where eligible (default); 1: generic K3 (A/B only)")
     ap.add_argument("--cpu-sample-queries", type=int, default=2000)
     ap.add_argument("--cpu-sample-db", type=int, default=200000)
+    ap.add_argument("--parity-sample", type=int, default=1024,
+                    help="query reads checked against the index-free oracle after the timed region (0 = skip)")
     return ap.parse_args()
 
 
@@ -213,6 +215,63 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
+def sampled_parity(n_sample, rec, db, ds, q, qs, db_total_global, rank, world, nd, L, dist, torch, np):
+    """AFTER the timed region, checker only: a seeded random sample of query reads (accepted and unaccepted)
+    is re-derived by the index-free CPU oracle (oracle/imsame_sampled.c: hash the sample's words, stream this
+    rank's database shard once, replay every e-value-passing hit in the reference's scan order through its NW
+    and filter until the first acceptance) and compared field by field with the records the GPU run produced.
+    Shards: each rank checks its own shard in global coordinates, the oracle's per-shard winners are reduced
+    like the reference's order demands (smallest k-mer end, then largest database position)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as hp
+    nq = len(qs) - 1
+    n_sample = min(n_sample, nq)
+    reads = np.sort(np.random.default_rng(20261018).choice(nq, n_sample, replace=False)).astype(np.uint64)
+    hp.oracle_set_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
+    t0 = time.perf_counter()
+    p = hp.default_params(n_threads=4, db_total_len_global=db_total_global)
+    got, st = hp.oracle_align_sampled(hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs), p, reads,
+                                      db_pos_base=rank * nd * L, db_seq_base=rank * nd)
+    # oracle winners of this shard -> the same (key, payload) words the product reduces
+    from imsame_b200 import sharding
+    ok = np.full(n_sample, sharding.KEY_NONE, dtype=np.int64)
+    op = np.zeros(n_sample, dtype=np.int64)
+    for i, r in enumerate(reads):
+        v = got.get(int(r))
+        if v is not None:
+            ok[i] = sharding.make_key(v[1] - int(qs[int(r)]) + 1, v[2])
+            op[i] = sharding.make_payload(v[0], v[3], v[4])
+    if world > 1:
+        tk, tp = torch.from_numpy(ok).cuda(), torch.from_numpy(op).cuda()
+        local = tk.clone()
+        dist.all_reduce(tk, op=dist.ReduceOp.MIN)
+        tp[(tk != local) | (tk == sharding.KEY_NONE)] = 0
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        ok, op = tk.cpu().numpy(), tp.cpu().numpy()
+    want = sharding.decode(ok, op, qs[reads.astype(np.int64)])
+    mism = 0
+    n_acc = 0
+    first_bad = None
+    for i, r in enumerate(reads):
+        o = rec[int(r)]
+        g = ((int(o["db_seq"]), int(o["qpos_end"]), int(o["db_pos"]), int(o["length"]), int(o["identities"]))
+             if o["accepted"] else None)
+        w = want.get(i)
+        n_acc += w is not None
+        if g != w:
+            mism += 1
+            if first_bad is None:
+                first_bad = {"read": int(r), "gpu": g, "oracle": w}
+    out = {"reads": int(n_sample), "mismatches": int(mism), "oracle_accepted": int(n_acc),
+           "fields": "accepted, db_seq, qpos_end, db_pos, length, identities",
+           "oracle": "oracle/imsame_sampled.c (index-free scan-order replay), per shard + min-key merge",
+           "oracle_hits_this_rank": int(st.hits), "oracle_nw_calls_this_rank": int(st.nw_calls),
+           "seconds": round(time.perf_counter() - t0, 1)}
+    if first_bad:
+        out["first_mismatch"] = first_bad
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -315,6 +374,11 @@ def run_ours(args):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         sharded_check = "stepped == unstepped" if int(flag.item()) == 1 else "MISMATCH between stepped and unstepped sharded runs"
 
+    parity = None
+    if args.parity_sample > 0:
+        parity = sampled_parity(args.parity_sample, rec, db_pin.array, ds, q_pin.array, qs, db_total_global, rank,
+                                world, nd, L, dist, torch, np)
+
     # per-kernel device times of the timed steps (CUDA events on the launching stream, inside the library)
     def avg(k):
         return sum(s[k] for s in stats_steps) / len(stats_steps)
@@ -401,7 +465,7 @@ def run_ours(args):
                        "l2": "inputs (625 MB packed shard + 1 GB query table) exceed the 126 MB L2"},
             "query_reads_per_s": nq / (ms_step * 1e-3),
             "dp_gcups_per_gpu": gcups, "dp_gcups_total": gcups * world,
-            "accepted_reads": n_accepted, "sharded_check": sharded_check,
+            "accepted_reads": n_accepted, "sharded_check": sharded_check, "sampled_parity": parity,
             "work": {"hits": float(agg[3].item()), "evalue_pass": float(agg[6].item()), "nw_pairs": float(agg[4].item()),
                      "cells": cells_all, "ms_k2": ms_k2_max, "ms_k3": ms_k3_max,
                      "ms_other": max(0.0, ms_step - ms_k2_max - ms_k3_max)},

@@ -80,6 +80,7 @@ struct imsame_ctx {
     unsigned long long *run_keys = nullptr, *run_payload = nullptr;
     imsame_params run_params;
     bool run_active = false;
+    bool table_dirty = false;  // the pair table may hold entries of a run that failed before they were binned
     // per segment (stride BINS_STRIDE): [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors |
     // NBINS work heads | 2*NBINS launch ranges
     uint32_t *d_bins = nullptr;
@@ -354,6 +355,7 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
         CK(cudaMemcpy(ctx->d_lut, lut.data(), EXT_LUT3_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     if (want_cap > ctx->hcap) {
+        ctx->hcap = 0;  // a failed allocation below must not leave a stale capacity behind
         dev_free(ctx->hkeys); dev_free(ctx->hvals);
         int rc;
         if ((rc = dev_alloc(ctx, &ctx->hkeys, want_cap))) return rc;
@@ -790,6 +792,8 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
         }
         r0 = r1;
     }
+    // the caller may refill or free its (pinned) host buffers as soon as this returns
+    CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_db = true;
     return IMSAME_OK;
 }
@@ -824,6 +828,9 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     if (!ctx->have_query || !ctx->have_db) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     if (!ctx->in_align) reset_timing(ctx);  // a run of its own: phase times and launch counts start here
+    // field widths of the key (40-bit global position) and of the payload (read index << 32, reduced as int64)
+    if (p->db_pos_base + ctx->db_total >= (1ull << KEY_POS_BITS) || p->db_seq_base + ctx->db_nseqs >= (1ull << 31))
+        return IMSAME_ELIMIT;
     const uint32_t nq = ctx->nq;
     int rc;
     if (ctx->keys_cap < nq) {
@@ -865,7 +872,12 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     CK(cudaMemcpyAsync(ctx->d_nmin, nmin.data(), nmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_lmin, lmin.data(), lmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_imin, imin.data(), imin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->table_dirty) {  // the previous run ended in an error between its scan and the binning: drop its entries
+        CK(cudaMemsetAsync(ctx->hkeys, 0xFF, (size_t)ctx->hcap * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->hvals, 0xFF, (size_t)ctx->hcap * 8, ctx->stream));
+        ctx->table_dirty = false;
+    }
     {
         PhaseScope ps(ctx, PH_SELECT);
         const int g = std::min<int>((nq + 255) / 256, ctx->n_sm * 8);
@@ -887,6 +899,7 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
     const imsame_params *p = &ctx->run_params;
     const SeqMap qm = query_map(ctx), dm = seg_map(s);
     int rc;
+    ctx->table_dirty = true;  // until bin_kernel<1> has emptied the table again (run_begin clears it otherwise)
     // The extension gathers two 32-base windows per hit from random places of the packed query
     // (cfg2: 62.5 MB, 3.4e10 hits), while the database, the bucket offsets (67 MB) and the word positions
     // (956 MB) stream through the same 126 MB L2: keep the query resident (persisting access window),
@@ -977,12 +990,7 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
     ctx->seg_pair_base[seg] = base;
     ctx->seg_pair_count[seg] = n_seg_pairs;
     CK(cudaGetLastError());
-    if (n_seg_pairs && (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE)) {
-        // a hit passed the e-value test while some read exceeds MAX_READ_SIZE: the reference would
-        // abort as soon as such a read reaches NW (src/alignmentFunctions.c:155)
-        ctx->run_active = false;
-        return IMSAME_EREADSIZE;
-    }
+    ctx->table_dirty = false;
     return IMSAME_OK;
 }
 
@@ -1024,6 +1032,13 @@ extern "C" int imsame_gpu_run_select(imsame_ctx *ctx, int seg) {
                                                         ctx->run_params.db_seq_base + ctx->segs[seg].seq_base,
                                                         ctx->d_counters + 5);
     ctx->launches++;
+    if (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE) {
+        // the keys are final here (all bands done, and exchanged between shards in a stepped run)
+        readsize_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->pairs + ctx->seg_pair_base[seg],
+                                                              (uint32_t)ctx->seg_pair_count[seg], seg_map(ctx->segs[seg]),
+                                                              query_map(ctx), ctx->run_keys, ctx->d_counters + 12);
+        ctx->launches++;
+    }
     CK(cudaGetLastError());
     return IMSAME_OK;
 }
@@ -1037,14 +1052,12 @@ extern "C" int imsame_gpu_run_end(imsame_ctx *ctx, imsame_stats *st) {
         mask_payload_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->run_keys, ctx->pkey, ctx->run_payload, ctx->nq);
         ctx->launches++;
     }
-    unsigned long long cnt[8] = {0};
+    unsigned long long cnt[13] = {0};
     CK(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->run_active = false;
-    if (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE) {
-        // the reference only fails when such a read reaches NW (src/alignmentFunctions.c:155)
-        if (cnt[2] > 0) return IMSAME_EREADSIZE;
-    }
+    // an over-long read reached NW before its query read was accepted (readsize_kernel, src/alignmentFunctions.c:155)
+    if (cnt[12]) return IMSAME_EREADSIZE;
     fill_stats(ctx, st, cnt);
     if (getenv("IMSAME_TRACE"))
         fprintf(stderr, "[imsame] candidate pairs %llu, aligned %llu, not after their read's final hit in scan order %llu\n",

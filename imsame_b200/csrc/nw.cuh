@@ -86,7 +86,11 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
         const uint32_t ys = read_start(a.q, pr.r);
         const uint32_t ylen = (a.q.fixed_len ? a.q.fixed_len : a.q.start[pr.r + 1] - ys);
         if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
-        if (a.best && pr.key >= a.best[pr.r]) {  // an earlier hit of this read is already accepted
+        // an earlier hit of this read is already accepted?  best[] is lowered by other warps meanwhile: one lane
+        // reads it, so that the whole warp takes the same branch
+        int pruned_w = 0;
+        if (a.best && lane == 0) pruned_w = pr.key >= a.best[pr.r];
+        if (__shfl_sync(0xffffffffu, pruned_w, 0)) {
             if (lane == 0) { PairRes z; z.score = 0; z.bx = z.by = 0; z.stats = 0; a.res[idx] = z; }
             continue;
         }

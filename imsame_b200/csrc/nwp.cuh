@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
             if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
             xs = read_start(a.db, pr.s);
             xlen = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs);
-            const bool pruned = a.best && pr.key >= a.best[pr.r];  // an earlier hit of this read is accepted
+            // an earlier hit of this read is accepted?  best[] is lowered by other warps meanwhile: one lane of
+            // the half reads it, so that all 16 lanes take the same branch
+            int pruned_h = 0;
+            if (a.best && hl == 0) pruned_h = pr.key >= a.best[pr.r];
+            const bool pruned = __shfl_sync(hmask, pruned_h, 16 * half) != 0;
             if (pruned || xlen < 2 || ylen < 2 || xlen > (uint32_t)PW_MAX_X || ylen > (uint32_t)PW_MAX_Y) {
                 if (hl == 0) {
                     PairRes z; z.score = pruned ? 0 : NW_NEG * 2; z.bx = z.by = 0; z.stats = 0;

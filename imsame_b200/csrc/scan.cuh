@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     int n_parked = 0;  // warp-uniform
 
     for (uint32_t tile = gw; tile < n_tiles; tile += nw) {
-        if (*(volatile int *)a.overflow) break;  // pair table too small: the host grows it and reruns
+        // pair table too small: the host grows it and reruns.  One lane reads the flag (other warps set it
+        // concurrently): the decision must be the same in every lane of the warp
+        if (__shfl_sync(0xffffffffu, lane == 0 ? *(volatile int *)a.overflow : 0, 0)) break;
         const uint32_t q = tile * 32 + lane;  // index of the word's last base
         uint32_t cnt = 0, b0 = 0, xs = 0, xe = 0;
         if (q < a.db.total) {
@@ -385,6 +387,19 @@ __global__ void select_kernel(const PairRec *pairs, const PairRes *res, uint32_t
     }
     needed = __reduce_add_sync(0xffffffffu, needed);
     if ((threadIdx.x & 31) == 0 && needed) atomicAdd(pairs_total + 2, (unsigned long long)needed);  // counters[7]
+}
+
+// "Read size reached for gapped alignment." (src/alignmentFunctions.c:155): the reference stops when an
+// e-value-passing hit with a read of more than MAX_READ_SIZE bases is reached BEFORE its query read has been
+// accepted, i.e. when such a candidate is earlier in scan order than the read's final hit.
+__global__ void readsize_kernel(const PairRec *pairs, uint32_t n, SeqMap db, SeqMap q,
+                                const unsigned long long *best, unsigned long long *flag) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const PairRec pr = pairs[i];
+        const uint32_t ylen = q.fixed_len ? q.fixed_len : q.start[pr.r + 1] - q.start[pr.r];
+        const uint32_t xlen = db.fixed_len ? db.fixed_len : db.start[pr.s + 1] - db.start[pr.s];
+        if ((xlen > (uint32_t)MAX_READ || ylen > (uint32_t)MAX_READ) && pr.key < best[pr.r]) *flag = 1ull;
+    }
 }
 
 // multi-shard: keep the payload only where this shard owns the reduced key

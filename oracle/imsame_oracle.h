@@ -91,6 +91,17 @@ int orc_align_sequential(const orc_seqs *db, const orc_seqs *q, const orc_params
 int orc_align_bulk(const orc_seqs *db, const orc_seqs *q, const orc_params *p, orc_best *best,
                    orc_stats *st);
 
+/* Index-free checker for inputs the reference's own index cannot hold (imsame_sampled.c): the first
+ * accepted hit, in the reference's scan order with its early exit, of the query reads reads[0..n_reads)
+ * against `db` (the whole database or one contiguous shard of it; db_pos_base / db_seq_base make the
+ * result global, p->db_total_len_global is the e-value's database length).  best[i] belongs to reads[i].
+ * Streams the database once on all host threads (OpenMP).  Returns -5 where the reference would stop
+ * with "Read size reached for gapped alignment." (src/alignmentFunctions.c:155). */
+void orc_set_threads(int n);
+int orc_align_sampled(const orc_seqs *db, const orc_seqs *q, const orc_params *p, const uint64_t *reads,
+                      uint64_t n_reads, uint64_t db_pos_base, uint64_t db_seq_base, orc_best *best,
+                      orc_stats *st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,11 @@ def oracle():
                                              C.POINTER(OrcBest), C.c_void_p, C.POINTER(OrcStats)]
         lib.orc_align_bulk.argtypes = [C.POINTER(OrcSeqs), C.POINTER(OrcSeqs), C.POINTER(OrcParams),
                                        C.POINTER(OrcBest), C.POINTER(OrcStats)]
+        lib.orc_set_threads.argtypes = [C.c_int]
+        lib.orc_set_threads.restype = None
+        lib.orc_align_sampled.argtypes = [C.POINTER(OrcSeqs), C.POINTER(OrcSeqs), C.POINTER(OrcParams),
+                                          C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.POINTER(OrcBest), C.POINTER(OrcStats)]
         _oracle = lib
     return _oracle
 
@@ -169,6 +174,27 @@ def oracle_align(db, q, params, bulk=False, out_path=None):
             libc.fclose(fp)
     assert rc == 0, rc
     return best, st
+
+
+def oracle_set_threads(n):
+    oracle().orc_set_threads(int(n))
+
+
+def oracle_align_sampled(db, q, params, reads, db_pos_base=0, db_seq_base=0):
+    """index-free per-read checker (oracle/imsame_sampled.c): first accepted hit of the query reads
+    `reads` against db (whole database or one shard).  Returns ({read: (db_seq, qpos_end, db_pos, length,
+    identities)} for the accepted ones, stats)."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint64)
+    n = len(reads)
+    best = (OrcBest * max(n, 1))()
+    st = OrcStats()
+    rc = oracle().orc_align_sampled(C.byref(db.s), C.byref(q.s), C.byref(params),
+                                    reads.ctypes.data_as(C.POINTER(C.c_uint64)), n, int(db_pos_base),
+                                    int(db_seq_base), best, C.byref(st))
+    assert rc == 0, rc
+    rec = {int(reads[i]): (best[i].db_seq, best[i].qpos_end, best[i].db_pos, best[i].length, best[i].identities)
+           for i in range(n) if best[i].accepted}
+    return rec, st
 
 
 def best_to_records(best, nq):

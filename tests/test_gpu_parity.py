@@ -93,6 +93,53 @@ def test_read_longer_than_the_scan_limit_is_refused(gpu):
     assert int(out["accepted"].sum()) == 1  # the context is still usable
 
 
+def _oracle_rc(db, ds, q, qs, n_threads):
+    """orc_align_sequential's return code (-5 = "Read size reached for gapped alignment.") and records"""
+    odb, oq = hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs)
+    nq = len(qs) - 1
+    best = (hp.OrcBest * nq)()
+    st = hp.OrcStats()
+    p = hp.default_params(n_threads=n_threads)
+    rc = hp.oracle().orc_align_sequential(C.byref(odb.s), C.byref(oq.s), C.byref(p), best, None, C.byref(st))
+    return rc, (hp.best_to_records(best, nq) if rc == 0 else None)
+
+
+def test_read_size_error_exactly_when_the_reference_stops(gpu):
+    """src/alignmentFunctions.c:155: the reference stops only when an e-value-passing hit with a read of more
+    than 3000 bases is reached before its query read is accepted -- not whenever such a read exists"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(71, 3, 50000, 200, 4000, 300, 0.03)
+    rng = np.random.default_rng(3)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    contig = B[rng.integers(0, 4, size=5000)]
+    # (a) a long database contig no query read is related to, in the middle of the database: runs to completion
+    cut = 2000 * 200
+    db_a = np.concatenate([db[:cut], contig, db[cut:]])
+    ds_a = np.concatenate([ds[:2001], ds[2000:] + 5000]).astype(np.uint64)
+    rc, want = _oracle_rc(db_a, ds_a, q, qs, 4)
+    assert rc == 0 and len(want) > 100
+    out, _ = gpu.align((db_a, ds_a), (q, qs), api.make_params(n_threads=4))
+    assert gpu_records(out) == want
+    # (b) one query read is a piece of that contig: its first e-value-passing hit reaches NW with xlen = 5000
+    q_b = q.copy()
+    q_b[40 * 200:41 * 200] = contig[1000:1200]
+    rc, _ = _oracle_rc(db_a, ds_a, q_b, qs, 4)
+    assert rc == -5
+    with pytest.raises(api.ImsameError) as e:
+        gpu.align((db_a, ds_a), (q_b, qs), api.make_params(n_threads=4))
+    assert e.value.code == -5
+    # (c) the same piece also sits in a normal database read that the scan order reaches FIRST and accepts:
+    #     list walks go in descending database position, so a copy placed after the contig wins
+    db_c = db_a.copy()
+    s_late = 3500
+    lo = int(ds_a[s_late])
+    db_c[lo:lo + 200] = contig[1000:1200]
+    rc, want = _oracle_rc(db_c, ds_a, q_b, qs, 4)
+    assert rc == 0 and want[40][0] == s_late
+    out, _ = gpu.align((db_c, ds_a), (q_b, qs), api.make_params(n_threads=4))
+    assert gpu_records(out) == want
+
+
 def test_packed_and_generic_kernels_give_the_same_records(gpu):
     from imsame_b200 import api
     db, ds, q, qs = sc.fixed_case(41, 4, 100000, 250, 30000, 1500, 0.08)
@@ -250,6 +297,48 @@ def test_cfg2_shaped_properties_at_scale(gpu):
         stacked = np.stack([r[f] for r in recs])
         merged = stacked[owner, np.arange(stacked.shape[1])]
         assert np.array_equal(np.where(m_acc, merged, 0), np.where(acc, whole[f], 0)), f
+
+
+def _sampled_check(rec, db, ds, q, qs, reads, db_total_global=0, **kw):
+    p = hp.default_params(n_threads=4, db_total_len_global=db_total_global, **kw)
+    want, st = hp.oracle_align_sampled(hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs), p, reads)
+    got = {int(r): (int(rec[r]["db_seq"]), int(rec[r]["qpos_end"]), int(rec[r]["db_pos"]), int(rec[r]["length"]),
+                    int(rec[r]["identities"])) for r in reads if rec[int(r)]["accepted"]}
+    return got, want, st
+
+
+def test_cfg2_full_size_sampled_against_oracle(gpu):
+    """BASELINE.json configs[1] at FULL size (1 M x 250 bp reads vs 10 M reads: five database segments, 32 bands,
+    ~1e8 candidate pairs, pair-table growth): 1 500 randomly drawn query reads -- accepted and unaccepted --
+    are re-derived by the index-free oracle (oracle/imsame_sampled.c: no database index, scan-order replay
+    with the reference's early exit) and every record field must be equal."""
+    from imsame_b200 import api, hostlib as H
+    L, nd, nq = 250, 10_000_000, 1_000_000
+    pool = H.SynthPool(2001, 1000, 1_000_000)
+    db = pool.db_reads(0, nd, L)
+    q = pool.query_reads(0, nq, L, 0.03)
+    pool.close()
+    ds = np.arange(nd + 1, dtype=np.uint64) * L
+    qs = np.arange(nq + 1, dtype=np.uint64) * L
+    rec, st = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
+    assert st["k2_launches"] >= 5 and st["n_pairs"] > 5e7
+    reads = np.sort(np.random.default_rng(99).choice(nq, 1500, replace=False))
+    got, want, ost = _sampled_check(rec, db, ds, q, qs, reads)
+    assert got == want
+    assert 600 < len(want) < 900 and ost.nw_calls > 20000
+
+
+def test_ragged_multi_segment_sampled_against_oracle(gpu):
+    """ragged reads (30..400 bases: generic NW kernel, read lookup through the block table) over a database of
+    more than one segment, checked like the cfg2 test"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.ragged_case(4242, 300, 1000000, 3_000_000, 60000, 0.04, lo=30, hi=400)
+    assert len(db) > (1 << 29)
+    rec, st = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
+    assert st["k2_launches"] >= 2
+    reads = np.sort(np.random.default_rng(7).choice(len(qs) - 1, 1200, replace=False))
+    got, want, _ = _sampled_check(rec, db, ds, q, qs, reads)
+    assert got == want and len(want) > 300
 
 
 @pytest.mark.parametrize("k", [8, 10, 13, 14])

@@ -90,3 +90,44 @@ def test_generalised_seed_length_forms_agree(k):
     nq = int(q.s.n_seqs)
     assert hp.best_to_records(seq, nq) == hp.best_to_records(bulk, nq)
     assert st2.hits >= st1.hits > 0
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("n_threads", [1, 4])
+def test_sampled_checker_equals_scan_order(name, n_threads):
+    """the index-free per-read checker (oracle/imsame_sampled.c, used on inputs the reference's index cannot
+    hold) gives exactly the scan-order result, for every read and for a subset"""
+    import numpy as np
+    db = hp.OracleSeqs(db_path(name), True)
+    q = hp.OracleSeqs(os.path.join(G, f"{name}.q.fa"), False)
+    p = hp.default_params(n_threads=n_threads, **CASES[name])
+    want = hp.best_to_records(hp.oracle_align(db, q, p)[0], int(q.s.n_seqs))
+    nq = int(q.s.n_seqs)
+    got, st = hp.oracle_align_sampled(db, q, p, np.arange(nq))
+    assert got == want
+    sub = np.arange(nq)[::3][::-1]
+    got, _ = hp.oracle_align_sampled(db, q, p, sub)
+    assert got == {r: v for r, v in want.items() if r in set(int(x) for x in sub)}
+
+
+def test_sampled_checker_on_shards_reduces_to_whole():
+    """per-shard results with global coordinates: the smallest (qpos_end, -db_pos) is the whole-database result"""
+    import numpy as np
+    import synth_cases as sc
+    db, ds, q, qs = sc.ragged_case(77, 3, 40000, 5000, 400, 0.05, lo=40, hi=260)
+    nd, nq = len(ds) - 1, len(qs) - 1
+    p = hp.default_params(n_threads=4)
+    whole = hp.best_to_records(hp.oracle_align(hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs), p)[0], nq)
+    assert len(whole) > 50
+    reads = np.arange(nq)
+    merged = {}
+    Q = hp.OracleSeqs(seq=q, start=qs)
+    for lo, hi in ((0, nd // 3), (nd // 3, nd)):
+        b0, b1 = int(ds[lo]), int(ds[hi])
+        ps = hp.default_params(n_threads=4, db_total_len_global=len(db))
+        got, _ = hp.oracle_align_sampled(hp.OracleSeqs(seq=db[b0:b1], start=ds[lo:hi + 1] - ds[lo]), Q, ps, reads,
+                                         db_pos_base=b0, db_seq_base=lo)
+        for r, v in got.items():
+            if r not in merged or (v[1], -v[2]) < (merged[r][1], -merged[r][2]):
+                merged[r] = v
+    assert merged == whole
