@@ -53,7 +53,8 @@ struct imsame_ctx {
     uint32_t nq = 0, q_total = 0, q_fixed = 0, q_maxlen = 0;
     uint32_t class_mask = 0;
     std::vector<uint32_t> q_start_host;
-    uint32_t *off = nullptr, *cursor = nullptr, *qpos = nullptr, *tile_sums = nullptr;
+    uint32_t *off = nullptr, *cursor = nullptr, *tile_sums = nullptr;
+    QEntry *qtab = nullptr;  // query word table entries, bucket by bucket (qtable.cuh)
     uint64_t n_qwords = 0;
     uint64_t q_threads = 0;
     bool have_query = false;
@@ -229,7 +230,7 @@ void pool_destroy(imsame_ctx *ctx) {
 
 void free_query(imsame_ctx *ctx) {
     pool_free(ctx, ctx->q_pk); pool_free(ctx, ctx->q_start); pool_free(ctx, ctx->q_blk);
-    pool_free(ctx, ctx->qpos);
+    pool_free(ctx, ctx->qtab);
     ctx->have_query = false;
 }
 void free_db(imsame_ctx *ctx) {
@@ -693,7 +694,7 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
     a.n_threads = (uint32_t)std::min<uint64_t>(ctx->q_threads, 0xFFFFFFFFull);
     a.per = (uint32_t)(nq / ctx->q_threads);  // floorl(n_seqs / n_threads), src/IMSAME.c:414
     a.cnt = ctx->cursor;
-    a.qpos = nullptr;
+    a.qtab = nullptr;
     const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
     uint32_t n_words = 0;
     {
@@ -709,11 +710,11 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
     CK(cudaMemcpyAsync(&n_words, ctx->off + ncodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_qwords = n_words;
-    if ((rc = pool_alloc(ctx, &ctx->qpos, (uint64_t)n_words + 1))) return rc;
+    if ((rc = pool_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) return rc;
     {
         PhaseScope ps(ctx, PH_K1);
         CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        a.qpos = ctx->qpos;
+        a.qtab = ctx->qtab;
         qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -940,7 +941,7 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
         {
             PhaseScope ps(ctx, PH_K2);
             ScanArgs a;
-            a.db = dm; a.q = qm; a.off = ctx->off; a.qpos = ctx->qpos; a.brk = s.brk; a.n_brk = s.n_brk;
+            a.db = dm; a.q = qm; a.off = ctx->off; a.qtab = ctx->qtab; a.brk = s.brk; a.n_brk = s.n_brk;
             a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
             a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
             a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;

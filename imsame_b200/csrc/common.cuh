@@ -71,6 +71,48 @@ IMS_HD uint32_t mismatch32(uint64_t a, uint64_t b) {
     return (uint32_t)d;
 }
 
+// even bits of a 64-bit word -> low 32 bits
+IMS_HD uint32_t even_bits64(uint64_t d) {
+    d &= 0x5555555555555555ull;
+    d = (d | (d >> 1)) & 0x3333333333333333ull;
+    d = (d | (d >> 2)) & 0x0F0F0F0F0F0F0F0Full;
+    d = (d | (d >> 4)) & 0x00FF00FF00FF00FFull;
+    d = (d | (d >> 8)) & 0x0000FFFF0000FFFFull;
+    d = (d | (d >> 16)) & 0x00000000FFFFFFFFull;
+    return (uint32_t)d;
+}
+IMS_HD uint32_t rev_bits32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+
+// Bit planes of a 32-base window: lo bit t = low code bit of base t, hi bit t = high code bit.  Two windows
+// in this form differ at base t  <=>  bit t of (lo ^ lo') | (hi ^ hi')  -- two 3-input logic ops for 32 bases,
+// against ~20 shift/mask operations to compare and compress two 2-bit-interleaved words.
+//   forward window:  base t = seq[first + t]
+//   backward window: base u = seq[last - u]   (walk order of src/alignmentFunctions.c:342-357)
+// Bases before index 0 read as code 0 (callers mask them out through their step limits).
+IMS_HD void planes_fwd(const uint32_t *pk, uint64_t first, uint32_t &lo, uint32_t &hi) {
+    const uint64_t w = fetch32(pk, first);
+    lo = even_bits64(w);
+    hi = even_bits64(w >> 1);
+}
+IMS_HD void planes_bwd(const uint32_t *pk, int64_t last, uint32_t &lo, uint32_t &hi) {
+    const int64_t first = last - 31;
+    uint64_t w;
+    if (first >= 0) w = fetch32(pk, (uint64_t)first);
+    else w = first <= -32 ? 0ull : (fetch32(pk, 0) << (2 * (int)(-first)));
+    lo = rev_bits32(even_bits64(w));
+    hi = rev_bits32(even_bits64(w >> 1));
+}
+
 struct SeqMap {
     const uint32_t *pk;     // packed bases
     const uint32_t *start;  // n + 1 offsets

@@ -277,6 +277,50 @@ IMS_HD void ext_first_masks(const ExtState &s, const uint32_t *dpk, const uint32
     if (bm < 32) mb |= 0xFFFFFFFFu << bm;
 }
 
+// ---- the two halves of a seed hit in bit-plane form -------------------------------------------
+// The first window each way of a hit (word ending at query base e, database index p after the word) is
+// formed from two independent halves: what K1 stores per query word (qtable.cuh: QEntry) and what the scan
+// computes once per database position, shared by all hits of that position.  Each half holds its 32 bases
+// after / before the word as bit planes (common.cuh) and the steps left inside its read.
+struct HitHalf {
+    uint32_t f_lo, f_hi, b_lo, b_hi;
+    int froom, broom;  // forward: end - (index after the word); backward: bases of the read before the word
+};
+IMS_HD HitHalf query_half(const uint32_t *qpk, uint32_t e, uint32_t ys, uint32_t yend, int K = imsame::K) {
+    HitHalf h;
+    planes_fwd(qpk, (uint64_t)e + 1, h.f_lo, h.f_hi);
+    planes_bwd(qpk, (int64_t)e - K, h.b_lo, h.b_hi);
+    h.froom = (int)(yend - (e + 1));
+    h.broom = (int)e - (K - 1) - (int)ys;  // -1 for the cross-read "phantom" word
+    return h;
+}
+IMS_HD HitHalf db_half(const uint32_t *dpk, uint32_t p, uint32_t xs, uint32_t xend, int K = imsame::K) {
+    HitHalf h;
+    planes_fwd(dpk, p, h.f_lo, h.f_hi);
+    planes_bwd(dpk, (int64_t)p - (K + 1), h.b_lo, h.b_hi);
+    h.froom = (int)(xend - p);
+    h.broom = (int)(p - (uint32_t)K - xs);
+    return h;
+}
+// v << n, 0 for n >= 32 (PTX shl.b32 clamps; the C++ operator is undefined there)
+IMS_HD uint32_t shl_clamp(uint32_t v, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+#else
+    return n >= 32u ? 0u : v << n;
+#endif
+}
+// = ext_init (fmax, bmax) + ext_first_masks, without touching either sequence
+IMS_HD void hit_first_masks(const HitHalf &d, const HitHalf &q, ExtState &s, uint32_t &mf, uint32_t &mb) {
+    s.fmax = q.froom < d.froom ? q.froom : d.froom;
+    s.bmax = q.broom < d.broom ? q.broom : d.broom;
+    s.pos_f = 0;
+    mf = ((d.f_lo ^ q.f_lo) | (d.f_hi ^ q.f_hi)) | shl_clamp(0xFFFFFFFFu, (uint32_t)(s.fmax < 0 ? 0 : s.fmax));
+    mb = ((d.b_lo ^ q.b_lo) | (d.b_hi ^ q.b_hi)) | shl_clamp(0xFFFFFFFFu, (uint32_t)(s.bmax < 0 ? 0 : s.bmax));
+}
+
 // First forward and first backward window of TWO independent hits, the two dependent chains of
 // table lookups interleaved (the scan kernel is bound by the latency of those chains, not by
 // instruction issue).  On return each state is done (phase 2) or parked-ready: phase 0 / 1 with

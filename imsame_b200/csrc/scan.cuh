@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "extend.cuh"
 #include "nw.cuh"
+#include "qtable.cuh"
 
 namespace imsame {
 
@@ -23,7 +24,7 @@ constexpr int SCAN_THREADS_K2 = SCAN_WARPS * 32;
 struct ScanArgs {
     SeqMap db, q;
     const uint32_t *off;   // query table: bucket offsets (4^12 + 1)
-    const uint32_t *qpos;  // query table: word end positions
+    const QEntry *qtab;    // query table: one entry per query word, bucket by bucket (qtable.cuh)
     const uint32_t *brk;   // database word breaks (segment-local), ascending
     uint32_t n_brk;
     const uint16_t *nmin;  // e-value threshold table by ylen
@@ -95,44 +96,42 @@ __device__ __forceinline__ uint32_t inv_of(uint32_t fixed_len) {
 constexpr int SCAN_QCAP = 64;
 
 struct ParkedWalk {
-    uint32_t p, e;
+    uint32_t p, e, ylen;
     ExtState st;
 };
 // the per-warp queue is stored field by field (10 arrays of SCAN_QCAP words): consecutive lanes touch
 // consecutive banks (as an array of 40-byte structs every access was a 2-way bank conflict)
-constexpr int PARK_FIELDS = 10;
+constexpr int PARK_FIELDS = 11;
 __device__ __forceinline__ void park_store(uint32_t (*q)[SCAN_QCAP], int slot, const ParkedWalk &w) {
     q[0][slot] = w.p; q[1][slot] = w.e;
     q[2][slot] = (uint32_t)w.st.phase; q[3][slot] = (uint32_t)w.st.t; q[4][slot] = (uint32_t)w.st.run;
     q[5][slot] = (uint32_t)w.st.best; q[6][slot] = (uint32_t)w.st.pos_f; q[7][slot] = (uint32_t)w.st.idn2;
-    q[8][slot] = (uint32_t)w.st.fmax; q[9][slot] = (uint32_t)w.st.bmax;
+    q[8][slot] = (uint32_t)w.st.fmax; q[9][slot] = (uint32_t)w.st.bmax; q[10][slot] = w.ylen;
 }
 __device__ __forceinline__ ParkedWalk park_load(const uint32_t (*q)[SCAN_QCAP], int slot) {
     ParkedWalk w;
     w.p = q[0][slot]; w.e = q[1][slot];
     w.st.phase = (int)q[2][slot]; w.st.t = (int)q[3][slot]; w.st.run = (int)q[4][slot];
     w.st.best = (int)q[5][slot]; w.st.pos_f = (int)q[6][slot]; w.st.idn2 = (int)q[7][slot];
-    w.st.fmax = (int)q[8][slot]; w.st.bmax = (int)q[9][slot];
+    w.st.fmax = (int)q[8][slot]; w.st.bmax = (int)q[9][slot]; w.ylen = q[10][slot];
     return w;
 }
 
-__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, uint32_t p, uint32_t e,
+// the e-value test (src/alignmentFunctions.c:139) on a finished walk, through the integer table nmin[ylen]
+// (host/thresholds.c); the query read itself is only looked up for the ~0.3 % of the hits that pass
+__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, uint32_t p, uint32_t e, uint32_t ylen,
                                            const ExtState &st, unsigned long long &c_pass,
                                            unsigned long long &c_anom, int k) {
     const int n = ext_result(st, k);
     if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
-    // fixed-length queries: one threshold; otherwise the read has to be looked up first
-    if (n >= 0 && a.q.fixed_len && n < (int)a.nmin[a.q.fixed_len]) return;
+    if (n >= 0 && n < (int)a.nmin[ylen]) return;
     const uint32_t r = find_read_inv(a.q, q_inv, e);
     const uint32_t ys = read_start(a.q, r);
-    const uint32_t yend = a.q.fixed_len ? ys + a.q.fixed_len : a.q.start[r + 1];
-    if (n < 0 || n >= (int)a.nmin[yend - ys]) {
-        c_pass++;
-        const uint64_t key = make_key(e - ys + 1, a.seg_pos_base + p);
-        if (key < a.best[r]) {
-            const uint32_t s = find_read(a.db, p - 1);
-            pair_insert(a, r, s, key);
-        }
+    c_pass++;
+    const uint64_t key = make_key(e - ys + 1, a.seg_pos_base + p);
+    if (key < a.best[r]) {
+        const uint32_t s = find_read(a.db, p - 1);
+        pair_insert(a, r, s, key);
     }
 }
 
@@ -142,23 +141,32 @@ __device__ __forceinline__ void drain_parked(const ScanArgs &a, uint32_t q_inv, 
                                              unsigned long long &c_pass, unsigned long long &c_anom, int k) {
     ParkedWalk w;
     w.st.phase = 2;
-    w.p = w.e = 0;
+    w.p = w.e = w.ylen = 0;
     if (lane < count) w = park_load(q, first + lane);
     while (__any_sync(0xffffffffu, w.st.phase < 2))
         if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e, k);
-    if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.st, c_pass, c_anom, k);
+    if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.ylen, w.st, c_pass, c_anom, k);
 }
 
 // KT: the seed length as a compile-time constant (12 = the reference's FIXED_K, the only value it has),
 // or 0 = read it from the arguments (imsame_gpu_set_kmer)
+//
+// A warp takes 32 consecutive database positions.  Per position (lane): the word's bucket and the database
+// windows around it as bit planes (common.cuh), kept in shared memory -- they are the same for every hit of
+// the position.  The ~14 hits per position are then spread evenly over the lanes (warp prefix sum + 5-step
+// search), two hits per lane per iteration; a hit reads its 24-byte table entry (consecutive lanes read
+// consecutive entries: a streaming access), forms both first-window mismatch masks with four logic
+// operations and walks them through the max-plus table (extend.cuh: ext_first2).  Walks that are still alive
+// after their first window (true overlaps and ~1 random hit in 4) are parked and finished 32 at a time.
 template <int KT>
 __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     const int k = KT ? KT : a.k;
     __shared__ uint32_t s_park[SCAN_WARPS][PARK_FIELDS][SCAN_QCAP];
     __shared__ uint32_t s_excl[SCAN_WARPS][33];
     __shared__ uint32_t s_b0[SCAN_WARPS][32];
-    __shared__ uint32_t s_xs[SCAN_WARPS][32];
-    __shared__ uint32_t s_xe[SCAN_WARPS][32];
+    __shared__ uint2 s_wf[SCAN_WARPS][32];   // database forward window of the position (lo, hi planes)
+    __shared__ uint2 s_wb[SCAN_WARPS][32];   // database backward window
+    __shared__ int2 s_room[SCAN_WARPS][32];  // steps left inside the database read: forward, backward
     __shared__ uint32_t s_lut[EXT_LUT3_SIZE];
     for (int i = threadIdx.x; i < EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
     __syncthreads();
@@ -174,16 +182,23 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
         // concurrently): the decision must be the same in every lane of the warp
         if (__shfl_sync(0xffffffffu, lane == 0 ? *(volatile int *)a.overflow : 0, 0)) break;
         const uint32_t q = tile * 32 + lane;  // index of the word's last base
-        uint32_t cnt = 0, b0 = 0, xs = 0, xe = 0;
+        uint32_t cnt = 0, b0 = 0;
         if (q < a.db.total) {
             const uint32_t s = find_read_inv(a.db, db_inv, q);
-            xs = read_start(a.db, s);
-            xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
+            const uint32_t xs = read_start(a.db, s);
+            const uint32_t xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
             if (q >= xs + (uint32_t)(k - 1) && !word_broken(a, q, k)) {
                 const uint32_t code = fetch16(a.db.pk, (uint64_t)q - (uint32_t)(k - 1)) & kmask_of(k);
                 b0 = a.off[code];
                 cnt = a.off[(size_t)code + 1] - b0;
                 c_words++;
+                if (cnt) {
+                    // llpos.pos: index after the word (src/IMSAME.c:247,265)
+                    const HitHalf h = db_half(a.db.pk, q + 1, xs, xe, k);
+                    s_wf[warp][lane] = make_uint2(h.f_lo, h.f_hi);
+                    s_wb[warp][lane] = make_uint2(h.b_lo, h.b_hi);
+                    s_room[warp][lane] = make_int2(h.froom, h.broom);
+                }
             }
         }
         uint32_t incl = cnt;
@@ -193,15 +208,9 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             if (lane >= o) incl += y;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        __syncwarp();
         s_excl[warp][lane] = incl - cnt;
         s_b0[warp][lane] = b0;
-        s_xs[warp][lane] = xs;
-        s_xe[warp][lane] = xe;
         __syncwarp();
-        // 64 hits per iteration, two per lane: their loads are issued together and their two chains of
-        // table lookups interleave (ext_first2); what is not finished after one window each way
-        // (long walks = true overlaps, ~1 in 4) is parked and continued 32 at a time
         for (uint32_t h0 = 0; h0 < total; h0 += 64) {
             const uint32_t ha = h0 + lane, hb = h0 + 32 + lane;
             const bool la = ha < total, lb = hb < total;
@@ -213,25 +222,36 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                 if (s_excl[warp][oa + step] <= sa_h) oa += step;
                 if (s_excl[warp][ob + step] <= sb_h) ob += step;
             }
-            const uint32_t ea = a.qpos[s_b0[warp][oa] + (sa_h - s_excl[warp][oa])];
-            const uint32_t eb = a.qpos[s_b0[warp][ob] + (sb_h - s_excl[warp][ob])];
-            const uint32_t pa = tile * 32 + oa + 1, pb = tile * 32 + ob + 1;  // llpos.pos: index after the word
+            const uint2 *qa = reinterpret_cast<const uint2 *>(a.qtab + (s_b0[warp][oa] + (sa_h - s_excl[warp][oa])));
+            const uint2 *qb = reinterpret_cast<const uint2 *>(a.qtab + (s_b0[warp][ob] + (sb_h - s_excl[warp][ob])));
+            // streamed once per database position that hits the bucket: no reuse worth a cache line
+            const uint2 fa = __ldcs(qa), ba = __ldcs(qa + 1), ma = __ldcs(qa + 2);
+            const uint2 fb = __ldcs(qb), bb = __ldcs(qb + 1), mb2 = __ldcs(qb + 2);
+            const uint2 dfa = s_wf[warp][oa], dba = s_wb[warp][oa], dfb = s_wf[warp][ob], dbb = s_wb[warp][ob];
+            const int2 rma = s_room[warp][oa], rmb = s_room[warp][ob];
+            const uint32_t ea = ma.x, eb = mb2.x;
+            const uint32_t pa = tile * 32 + oa + 1, pb = tile * 32 + ob + 1;
             ExtState sta, stb;
-            {
-                const uint32_t ra = find_read_inv(a.q, q_inv, ea), rb = find_read_inv(a.q, q_inv, eb);
-                const uint32_t ysa = read_start(a.q, ra), ysb = read_start(a.q, rb);
-                const uint32_t yea = a.q.fixed_len ? ysa + a.q.fixed_len : a.q.start[ra + 1];
-                const uint32_t yeb = a.q.fixed_len ? ysb + a.q.fixed_len : a.q.start[rb + 1];
-                ext_init(sta, pa, ea, s_xs[warp][oa], s_xe[warp][oa], ysa, yea, k);
-                ext_init(stb, pb, eb, s_xs[warp][ob], s_xe[warp][ob], ysb, yeb, k);
-            }
+            // mismatch bits of the first window each way (step u <-> bit u); steps past a read end are
+            // mismatches (extend.cuh: hit_first_masks = ext_init + ext_first_masks on the two halves)
             uint32_t mfa, mba, mfb, mbb;
-            ext_first_masks(sta, a.db.pk, a.q.pk, pa, ea, mfa, mba, k);
-            ext_first_masks(stb, a.db.pk, a.q.pk, pb, eb, mfb, mbb, k);
+            {
+                HitHalf da, qa_h, dbh, qb_h;
+                da.f_lo = dfa.x; da.f_hi = dfa.y; da.b_lo = dba.x; da.b_hi = dba.y; da.froom = rma.x; da.broom = rma.y;
+                dbh.f_lo = dfb.x; dbh.f_hi = dfb.y; dbh.b_lo = dbb.x; dbh.b_hi = dbb.y; dbh.froom = rmb.x; dbh.broom = rmb.y;
+                qa_h.f_lo = fa.x; qa_h.f_hi = fa.y; qa_h.b_lo = ba.x; qa_h.b_hi = ba.y;
+                qa_h.froom = (int)(ma.y & 0xFFFFu); qa_h.broom = (int)(ma.y >> 16) - 1;
+                qb_h.f_lo = fb.x; qb_h.f_hi = fb.y; qb_h.b_lo = bb.x; qb_h.b_hi = bb.y;
+                qb_h.froom = (int)(mb2.y & 0xFFFFu); qb_h.broom = (int)(mb2.y >> 16) - 1;
+                hit_first_masks(da, qa_h, sta, mfa, mba);
+                hit_first_masks(dbh, qb_h, stb, mfb, mbb);
+            }
             ext_first2(sta, stb, s_lut, mfa, mba, mfb, mbb, k);
             c_hits += (la ? 1 : 0) + (lb ? 1 : 0);
-            if (la && sta.phase == 2) finish_hit(a, q_inv, pa, ea, sta, c_pass, c_anom, k);
-            if (lb && stb.phase == 2) finish_hit(a, q_inv, pb, eb, stb, c_pass, c_anom, k);
+            const uint32_t ylen_a = (ma.y & 0xFFFFu) + (ma.y >> 16) + (uint32_t)(k - 1);
+            const uint32_t ylen_b = (mb2.y & 0xFFFFu) + (mb2.y >> 16) + (uint32_t)(k - 1);
+            if (la && sta.phase == 2) finish_hit(a, q_inv, pa, ea, ylen_a, sta, c_pass, c_anom, k);
+            if (lb && stb.phase == 2) finish_hit(a, q_inv, pb, eb, ylen_b, stb, c_pass, c_anom, k);
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const bool unfinished = half ? (lb && stb.phase < 2) : (la && sta.phase < 2);
@@ -239,7 +259,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                 if (park) {
                     if (unfinished) {
                         ParkedWalk w;
-                        w.p = half ? pb : pa; w.e = half ? eb : ea; w.st = half ? stb : sta;
+                        w.p = half ? pb : pa; w.e = half ? eb : ea; w.ylen = half ? ylen_b : ylen_a; w.st = half ? stb : sta;
                         park_store(s_park[warp], n_parked + __popc(park & ((1u << lane) - 1u)), w);
                     }
                     n_parked += __popc(park);
@@ -252,6 +272,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                 }
             }
         }
+        __syncwarp();  // the next tile overwrites the per-position shared arrays
     }
     if (n_parked) drain_parked(a, q_inv, s_lut, s_park[warp], 0, n_parked, lane, c_pass, c_anom, k);
     // counters: warp-reduce then one atomic per warp

@@ -88,6 +88,18 @@ int main(int argc, char **argv) {
                         ExtState A = prev, Bst = cur;
                         ext_first_masks(A, dpk.data(), qpk.data(), prev_p, prev_e, mfa, mba, k);
                         ext_first_masks(Bst, dpk.data(), qpk.data(), p, e, mfb, mbb, k);
+                        {   // the same masks and step limits from the two bit-plane halves (query table entry + database position)
+                            ExtState C2;
+                            uint32_t mf2, mb2;
+                            const HitHalf dh = db_half(dpk.data(), p, (uint32_t)ds[s], (uint32_t)ds[s + 1], k);
+                            const HitHalf qh = query_half(qpk.data(), e, (uint32_t)qs[r], (uint32_t)qs[r + 1], k);
+                            hit_first_masks(dh, qh, C2, mf2, mb2);
+                            const uint32_t ylen = (uint32_t)qh.froom + (uint32_t)(qh.broom + 1) + (uint32_t)(k - 1);
+                            if (mf2 != mfb || mb2 != mbb || C2.fmax != cur.fmax || C2.bmax != cur.bmax || ylen != qs[r + 1] - qs[r] ||
+                                qh.froom < 0 || qh.broom + 1 < 0) {
+                                if (bad++ < 10) printf("PLANES MISMATCH p=%u e=%u mf %08x/%08x mb %08x/%08x\n", p, e, mf2, mfb, mb2, mbb);
+                            }
+                        }
                         ext_first2(A, Bst, lut2.data(), mfa, mba, mfb, mbb, k);
                         while (A.phase < 2) ext_window(A, lut2.data(), dpk.data(), qpk.data(), prev_p, prev_e, k);
                         while (Bst.phase < 2) ext_window(Bst, lut2.data(), dpk.data(), qpk.data(), p, e, k);
