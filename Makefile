@@ -12,8 +12,9 @@ NVFLAGS   := -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
 OUT       := imsame_b200/_lib
 HOST_SRC  := imsame_b200/host/fasta.c imsame_b200/host/thresholds.c imsame_b200/host/synth.c \
              imsame_b200/host/render.c
-GPU_SRC   := imsame_b200/csrc/capi.cu
-GPU_HDR   := $(wildcard imsame_b200/csrc/*.cuh) include/imsame_gpu.h
+GPU_SRC   := imsame_b200/csrc/capi.cu imsame_b200/csrc/nwp_launch.cu
+GPU_OBJ   := $(OUT)/capi.o $(OUT)/nwp_launch.o
+GPU_HDR   := $(wildcard imsame_b200/csrc/*.cuh) $(wildcard imsame_b200/csrc/*.inc) $(wildcard imsame_b200/csrc/*.h) include/imsame_gpu.h imsame_b200/host/imsame_host.h
 
 all: $(OUT)/libimsame_host.so $(OUT)/libimsame_gpu.so bin/IMSAME bin/IMSAME_allvsall bin/revComp bin/all_vs_all_metagenomes_IMSAME.sh
 
@@ -21,11 +22,15 @@ $(OUT)/libimsame_host.so: $(HOST_SRC) imsame_b200/host/imsame_host.h include/ims
 	@mkdir -p $(OUT)
 	$(CC) $(CFLAGS) -shared $(HOST_SRC) -lm -o $@
 
-$(OUT)/libimsame_gpu.so: $(GPU_SRC) $(GPU_HDR) imsame_b200/host/thresholds.c
+$(OUT)/%.o: imsame_b200/csrc/%.cu $(GPU_HDR)
 	@mkdir -p $(OUT)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OUT)/ptxas_$*.log || (cat $(OUT)/ptxas_$*.log; false)
+	@grep -E "error|warning|spill" $(OUT)/ptxas_$*.log | grep -v "0 bytes spill\|pragma unroll" || true
+
+$(OUT)/libimsame_gpu.so: $(GPU_OBJ) imsame_b200/host/thresholds.c
 	$(CC) $(CFLAGS) -c imsame_b200/host/thresholds.c -o $(OUT)/thresholds.o
-	$(NVCC) $(NVFLAGS) -shared $(GPU_SRC) $(OUT)/thresholds.o -o $@ 2> $(OUT)/ptxas.log || (cat $(OUT)/ptxas.log; false)
-	@grep -E "error|warning|spill" $(OUT)/ptxas.log | grep -v "0 bytes spill" || true
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -shared $(GPU_OBJ) $(OUT)/thresholds.o -ldl -o $@
+	@cat $(OUT)/ptxas_capi.log $(OUT)/ptxas_nwp_launch.log > $(OUT)/ptxas.log
 
 JOB_SRC   := imsame_b200/host/imsame_job.c imsame_b200/host/imsame_job.h
 

@@ -280,8 +280,6 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     # torchrun pins OMP_NUM_THREADS=1; the synthetic generator (host/synth.c) is OpenMP
     H.set_synth_threads(max(1, (os.cpu_count() or 1) // max(1, world)))
     if not torch.cuda.is_available():
@@ -322,17 +320,19 @@ def run_ours(args):
     ctx.set_db((db_pin.array, ds))
     torch.cuda.synchronize()
 
-    def exchange():
-        dist.all_reduce(keys, op=dist.ReduceOp.MIN)          # C1: min-key reduction over NVLink (8 MB)
+    if world > 1:
+        # the reductions are the library's own (imsame_gpu_run_sharded: ncclAllReduce(ncclUint64, ncclMin) of the keys
+        # between k-mer-end bands, ncclMax of the owner's payload); torch.distributed only hands the communicator id around
+        box = [api.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], world, rank)
 
     def step():
         if world == 1:
             return ctx.run(params, keys.data_ptr(), payload.data_ptr())
         # shards exchange the per-read keys between k-mer-end bands, so an accepted early hit in one
         # shard prunes the later candidates of that read in every shard (the reference's early exit)
-        st = ctx.run_stepped(params, keys.data_ptr(), payload.data_ptr(), exchange=exchange, exchange_every=2)
-        dist.all_reduce(payload, op=dist.ReduceOp.MAX)       # the owner's payload (others are zero)
-        return st
+        return ctx.run_sharded(params, keys.data_ptr(), payload.data_ptr())
 
     def barrier():
         if world > 1:
@@ -372,7 +372,8 @@ def run_ours(args):
         same = bool(torch.equal(k2, keys)) and bool(torch.equal(p2, payload))
         flag = torch.tensor([1 if same else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        sharded_check = "stepped == unstepped" if int(flag.item()) == 1 else "MISMATCH between stepped and unstepped sharded runs"
+        sharded_check = ("library NCCL band-stepped run == independent shard runs reduced through torch.distributed" if int(flag.item()) == 1
+                         else "MISMATCH between the band-stepped library run and the unstepped torch-reduced run"
 
     parity = None
     if args.parity_sample > 0:
@@ -408,8 +409,7 @@ def run_ours(args):
                 # of the shard, band-stepped run with the key exchange, owner's payload, records to the host
                 ctx2.set_query((q_pin.array, qs), params)
                 ctx2.set_db((db_pin.array, ds))
-                st = ctx2.run_stepped(params, keys.data_ptr(), payload.data_ptr(), exchange=exchange, exchange_every=2)
-                dist.all_reduce(payload, op=dist.ReduceOp.MAX)
+                st = ctx2.run_sharded(params, keys.data_ptr(), payload.data_ptr())
                 out = ctx2.fetch(keys.data_ptr(), payload.data_ptr())
                 st["h2d_bytes"] = int(nd * L + nq * L)
                 st["d2h_bytes"] = int(16 * nq)
@@ -427,8 +427,8 @@ def run_ours(args):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3,
                "what": ("imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records"
                         if world == 1 else
-                        "per rank: set_query + set_db (pinned host ASCII reads -> H2D -> pack -> query table) -> band-stepped run "
-                        "with NCCL key exchange -> owner payload reduction -> D2H records"),
+                        "per rank: set_query + set_db (pinned host ASCII reads -> H2D -> pack -> query table) -> imsame_gpu_run_sharded "
+                        "(band-stepped run, ncclMin key reductions and the owner's payload inside the library) -> D2H records"),
                "device_phases_ms": e2e_phases}
 
     if rank == 0:

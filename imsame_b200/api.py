@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("k2_launches", C.c_uint32), ("k3_launches", C.c_uint32), ("total_launches", C.c_uint32),
-                ("k3_packed_launches", C.c_uint32)]
+                ("k3_packed_launches", C.c_uint32), ("ms_comm", C.c_float), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -62,7 +62,8 @@ SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "im
            "imsame_gpu_run", "imsame_gpu_n_segments", "imsame_gpu_n_bands", "imsame_gpu_run_begin",
            "imsame_gpu_run_scan", "imsame_gpu_run_band", "imsame_gpu_run_select", "imsame_gpu_run_end",
            "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode",
-           "imsame_gpu_set_kmer",
+           "imsame_gpu_set_kmer", "imsame_gpu_comm_id", "imsame_gpu_comm_init", "imsame_gpu_comm_free",
+           "imsame_gpu_run_sharded", "imsame_gpu_align_sharded",
            "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
 _lib = None
@@ -110,6 +111,12 @@ def lib():
                                            C.POINTER(C.POINTER(C.c_uint32)), vp]
         l.imsame_gpu_set_nw_mode.argtypes = [vp, C.c_int]
         l.imsame_gpu_set_kmer.argtypes = [vp, C.c_int]
+        l.imsame_gpu_comm_id.argtypes = [vp]
+        l.imsame_gpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+        l.imsame_gpu_comm_free.argtypes = [vp]
+        l.imsame_gpu_run_sharded.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, C.POINTER(Stats)]
+        l.imsame_gpu_align_sharded.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(SeqInfo), C.POINTER(SeqInfo),
+                                               C.POINTER(Params), vp, C.POINTER(Stats)]
         l.imsame_gpu_free.argtypes = [vp]
         l.imsame_gpu_free.restype = None
         l.imsame_gpu_host_alloc.argtypes = [u64]
@@ -276,6 +283,23 @@ class Imsame:
         self._check(L.imsame_gpu_run_end(self._h, C.byref(st)))
         return st.as_dict()
 
+    # -- database sharded over several GPUs, reduced by NCCL inside the library
+    def comm_init(self, comm_id, n_ranks, rank):
+        """join the communicator named by the 128 bytes rank 0 obtained from comm_id()"""
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        self._check(lib().imsame_gpu_comm_init(self._h, C.cast(buf, C.c_void_p), int(n_ranks), int(rank)))
+
+    def comm_free(self):
+        self._check(lib().imsame_gpu_comm_free(self._h))
+
+    def run_sharded(self, params, d_keys=0, d_payload=0, exchange_every=0):
+        """collective: scan + NW over this rank's shard with ncclMin key reductions between bands and the
+        owner's payload (ncclMax) at the end; d_keys / d_payload hold the reduced result on every rank"""
+        st = Stats()
+        self._check(lib().imsame_gpu_run_sharded(self._h, C.byref(params), C.c_void_p(d_keys), C.c_void_p(d_payload),
+                                                 int(exchange_every), C.byref(st)))
+        return st.as_dict()
+
     def n_segments(self):
         return lib().imsame_gpu_n_segments(self._h)
 
@@ -325,6 +349,35 @@ class Imsame:
                                               C.cast(yp, C.c_void_p), yl.ctypes.data, -int(igap), -int(egap),
                                               out.ctypes.data, C.byref(ms)))
         return out, ms.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_id():
+    """128 opaque bytes naming a new communicator (ncclGetUniqueId); hand them to every rank"""
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    rc = lib().imsame_gpu_comm_id(C.cast(buf, C.c_void_p))
+    if rc:
+        raise ImsameError(rc)
+    return bytes(buf)
+
+
+def align_sharded(ctxs, db, query, params=None, db_breaks=None):
+    """one process, len(ctxs) GPUs: imsame_gpu_align_sharded.  Returns (records, [stats per shard])."""
+    params = params or make_params()
+    d, k1 = _seqinfo(db[0], db[1], db_breaks)
+    q, k2 = _seqinfo(query[0], query[1])
+    n = len(ctxs)
+    out = np.zeros(int(q.n_seqs), dtype=BEST_DTYPE)
+    hs = (C.c_void_p * n)(*[c._h for c in ctxs])
+    st = (Stats * n)()
+    rc = lib().imsame_gpu_align_sharded(hs, n, C.byref(d), C.byref(q), C.byref(params), out.ctypes.data, st)
+    if rc:
+        raise ImsameError(rc, lib().imsame_gpu_last_cuda_error(ctxs[0]._h).decode())
+    for c in ctxs:
+        c.nq = int(q.n_seqs)
+    return out, [s.as_dict() for s in st]
 
 
 def header_fields(read, rec, ylen):

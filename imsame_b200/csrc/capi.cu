@@ -15,7 +15,7 @@
 #include "../../include/imsame_gpu.h"
 #include "../host/imsame_host.h"
 #include "nw.cuh"
-#include "nwp.cuh"
+#include "nwp_launch.h"
 #include "qtable.cuh"
 #include "scan.cuh"
 
@@ -35,7 +35,7 @@ struct Seg {
     uint32_t *pk = nullptr, *start = nullptr, *blk = nullptr, *brk = nullptr;
 };
 
-enum Phase { PH_PACKQ, PH_K1, PH_PACKDB, PH_K2, PH_K2B, PH_K3, PH_SELECT, PH_H2D, PH_D2H, PH_COUNT };
+enum Phase { PH_PACKQ, PH_K1, PH_PACKDB, PH_K2, PH_K2B, PH_K3, PH_SELECT, PH_H2D, PH_D2H, PH_COMM, PH_COUNT };
 
 }  // namespace
 
@@ -81,6 +81,11 @@ struct imsame_ctx {
     unsigned long long *run_keys = nullptr, *run_payload = nullptr;
     imsame_params run_params;
     bool run_active = false;
+    bool run_masked = false;   // the payloads of superseded keys have been dropped (run_mask)
+    // communicator of a sharded database (capi_sharded.inc): NCCL over NVLink, one rank per GPU
+    void *comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    unsigned long long *comm_flag = nullptr;  // one device word for status / read-size reductions
     bool table_dirty = false;  // the pair table may hold entries of a run that failed before they were binned
     // per segment (stride BINS_STRIDE): [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors |
     // NBINS work heads | 2*NBINS launch ranges
@@ -347,7 +352,7 @@ int ensure_work_buffers(imsame_ctx *ctx, uint32_t want_cap) {
         if ((rc = dev_alloc(ctx, &ctx->d_small, 4))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_counters, 16))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_overflow, 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->d_nmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->d_nmin, EXT_MAX_READ + 1))) return rc;  // every read length the scan admits
         if ((rc = dev_alloc(ctx, &ctx->d_lmin, IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_imin, 2 * IMSAME_MAX_READ_SIZE + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->d_lut, EXT_LUT3_SIZE))) return rc;
@@ -419,49 +424,23 @@ int launch_nw_class(imsame_ctx *ctx, const NwArgs &a, int c) {
     return rc;
 }
 
-// packed-word kernel (nwp.cuh) of NW class C: 16 lanes x 2C columns.  cl >= 0 (every query read has the
-// same length): the variant with the last column's slot compiled in.
-template <int C, int CL>
-void launch_nwp_variant(imsame_ctx *ctx, const NwArgs &a, int cl) {
-    if (cl == CL) {
-        nwp_kernel<2 * C, CL><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
-        return;
+// packed-word kernel (nwp.cuh) of NW class c; its ~150 instantiations live in their own translation unit
+// (nwp_launch.cu) so that the two halves of the library compile side by side
+int launch_nwp_class(imsame_ctx *ctx, NwArgs a, int c) {
+    c = c < 1 ? 1 : (c > 8 ? 8 : c);
+    if (!ctx->nwp_grid[c]) {
+        const int per_sm = nwp_blocks_per_sm(c);
+        if (per_sm < 0) { ctx->cuda_err = "cudaOccupancyMaxActiveBlocksPerMultiprocessor(nwp_kernel)"; return IMSAME_ECUDA; }
+        ctx->nwp_grid[c] = std::max(1, per_sm) * ctx->n_sm;
     }
-    if constexpr (CL + 1 < 2 * C) launch_nwp_variant<C, CL + 1>(ctx, a, cl);
-    else nwp_kernel<2 * C, -1><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
-}
-
-template <int C>
-int launch_nwp(imsame_ctx *ctx, NwArgs a) {
-    if (!ctx->nwp_grid[C]) {
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nwp_kernel<2 * C, -1>, NWP_THREADS, 0));
-        ctx->nwp_grid[C] = std::max(1, per_sm) * ctx->n_sm;
-    }
-    a.s_class = C;
+    a.s_class = c;
     a.one = 1;
-    int cl = -1;
-    if (a.q.fixed_len >= 2 && !a.check_class && nw_class_of(a.q.fixed_len) == C) cl = (int)((a.q.fixed_len - 2) % (2 * C));
-    if (cl >= 0) launch_nwp_variant<C, 0>(ctx, a, cl);
-    else nwp_kernel<2 * C, -1><<<ctx->nwp_grid[C], NWP_THREADS, 0, ctx->stream>>>(a);
+    nwp_launch(c, ctx->nwp_grid[c], ctx->stream, a);
     ctx->launches++;
     ctx->k3_launches++;
     ctx->k3_packed++;
     CK(cudaGetLastError());
     return IMSAME_OK;
-}
-
-int launch_nwp_class(imsame_ctx *ctx, const NwArgs &a, int c) {
-    switch (c) {
-        case 1: return launch_nwp<1>(ctx, a);
-        case 2: return launch_nwp<2>(ctx, a);
-        case 3: return launch_nwp<3>(ctx, a);
-        case 4: return launch_nwp<4>(ctx, a);
-        case 5: return launch_nwp<5>(ctx, a);
-        case 6: return launch_nwp<6>(ctx, a);
-        case 7: return launch_nwp<7>(ctx, a);
-        default: return launch_nwp<8>(ctx, a);
-    }
 }
 
 bool use_packed(const imsame_ctx *ctx, uint32_t xmax, uint32_t ymax, int igap, int egap) {
@@ -536,7 +515,7 @@ void fill_stats(imsame_ctx *ctx, imsame_stats *st, const unsigned long long *cnt
     if (any) cudaEventElapsedTime(&total, first, last);
     st->ms_pack_query = acc[PH_PACKQ]; st->ms_k1 = acc[PH_K1]; st->ms_pack_db = acc[PH_PACKDB];
     st->ms_k2 = acc[PH_K2]; st->ms_k2b = acc[PH_K2B]; st->ms_k3 = acc[PH_K3]; st->ms_select = acc[PH_SELECT];
-    st->ms_h2d = acc[PH_H2D]; st->ms_d2h = acc[PH_D2H]; st->ms_total = total;
+    st->ms_h2d = acc[PH_H2D]; st->ms_d2h = acc[PH_D2H]; st->ms_total = total; st->ms_comm = acc[PH_COMM];
     st->h2d_bytes = ctx->h2d_bytes; st->d2h_bytes = ctx->d2h_bytes;
     st->k2_launches = ctx->k2_launches; st->k3_launches = ctx->k3_launches; st->total_launches = ctx->launches;
     st->k3_packed_launches = ctx->k3_packed;
@@ -562,6 +541,8 @@ const char *imsame_gpu_strerror(int code) {
         case IMSAME_EREADSIZE: return "Read size reached for gapped alignment.";
         case IMSAME_ESTATE: return "call order violated";
         case IMSAME_ELIMIT: return "input exceeds an implementation limit";
+        case IMSAME_EPEER: return "another database shard failed";
+        case IMSAME_ENCCL: return "NCCL unavailable or failed";
         default: return "unknown error";
     }
 }
@@ -611,6 +592,8 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
         if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
         if (ctx->pin_ev[b]) cudaEventDestroy(ctx->pin_ev[b]);
     }
+    imsame_gpu_comm_free(ctx);
+    dev_free(ctx->comm_flag);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -865,9 +848,10 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     if ((rc = ensure_work_buffers(ctx, cap))) return rc;
 
     // exact threshold tables (host, long double) -> device
-    std::vector<uint16_t> nmin(IMSAME_MAX_READ_SIZE + 1), lmin(IMSAME_MAX_READ_SIZE + 1), imin(2 * IMSAME_MAX_READ_SIZE + 1);
+    const uint32_t nmin_len = std::max<uint32_t>(IMSAME_MAX_READ_SIZE, ctx->q_maxlen);
+    std::vector<uint16_t> nmin((size_t)nmin_len + 1), lmin(IMSAME_MAX_READ_SIZE + 1), imin(2 * IMSAME_MAX_READ_SIZE + 1);
     const uint64_t db_total_global = p->db_total_len_global ? p->db_total_len_global : ctx->db_total;
-    imsame_build_nmin(p->min_e_value, db_total_global, nmin.data());
+    imsame_build_nmin_upto(p->min_e_value, db_total_global, nmin.data(), nmin_len);
     imsame_build_lmin(p->min_coverage, lmin.data());
     imsame_build_imin(p->min_identity, imin.data());
     CK(cudaMemcpyAsync(ctx->d_nmin, nmin.data(), nmin.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -889,6 +873,7 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     }
     CK(cudaStreamSynchronize(ctx->stream));  // the host tables go out of scope
     ctx->run_active = true;
+    ctx->run_masked = false;
     return IMSAME_OK;
 }
 
@@ -1045,13 +1030,22 @@ extern "C" int imsame_gpu_run_select(imsame_ctx *ctx, int seg) {
 }
 
 // drop payloads that a later, smaller key (another segment or, after a reduction, another shard) superseded
+static int run_mask(imsame_ctx *ctx) {
+    if (ctx->run_masked) return IMSAME_OK;
+    PhaseScope ps(ctx, PH_SELECT);
+    mask_payload_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->run_keys, ctx->pkey, ctx->run_payload, ctx->nq);
+    ctx->launches++;
+    ctx->run_masked = true;
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
 extern "C" int imsame_gpu_run_end(imsame_ctx *ctx, imsame_stats *st) {
     if (!ctx || !ctx->run_active) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     {
-        PhaseScope ps(ctx, PH_SELECT);
-        mask_payload_kernel<<<ctx->n_sm * 4, 256, 0, ctx->stream>>>(ctx->run_keys, ctx->pkey, ctx->run_payload, ctx->nq);
-        ctx->launches++;
+        int rc = run_mask(ctx);
+        if (rc) return rc;
     }
     unsigned long long cnt[13] = {0};
     CK(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1422,3 +1416,5 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
 }
 
 }  // extern "C"
+
+#include "capi_sharded.inc"

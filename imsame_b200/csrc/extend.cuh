@@ -204,17 +204,49 @@ IMS_HD void ext_init(ExtState &s, uint32_t p, uint32_t e, uint32_t xs, uint32_t 
     s.phase = s.fmax > 0 ? 0 : (s.bmax > 0 ? 1 : 2);
 }
 
-// one table step (8 bases) of a walk
-IMS_HD void ext_step(const uint32_t *lut, uint32_t m8, int &run, int &best) {
+// one table step (8 bases: bits c .. c+7 of the window's mismatch mask) of a walk
+IMS_HD void ext_step(const uint32_t *lut, uint32_t mm, int c, int &run, int &best) {
     uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
     row = row < 9u ? row : 9u;
-    const uint32_t e = lut[row * 256u + m8];
+    const uint32_t e = lut[row * 256u + ((mm >> c) & 0xFFu)];
     const int key = run + (int)(funnel_r(e, e, 8) & EXT_X_MASK);
     best = key > best ? key : best;
     run += (int)(e & EXT_Y_MASK) - (8 << EXT_SC_SHIFT);
 }
 
-IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
+// The same table with both addends of a step spelled out (8 bytes per entry): the scan kernel's copy in shared
+// memory.  A step is then 7 instructions instead of 11 -- shift, clamp, one byte permute that forms the index
+// from the mask byte and the row, one 64-bit shared load, one fused add-maximum, one add -- at the price of
+// twice the table bytes per lookup; the kernel is bound by instruction issue (round 2 profile), not by the
+// shared-memory pipe.
+struct ExtXY {
+    int x;   // ((maximum prefix score + 1) << 15) + step of its last occurrence
+    int yd;  // (score change << 15) + steps executed
+};
+IMS_HD ExtXY ext_xy_of(uint32_t e) {
+    ExtXY v;
+    v.x = (int)(funnel_r(e, e, 8) & EXT_X_MASK);
+    v.yd = (int)(e & EXT_Y_MASK) - (8 << EXT_SC_SHIFT);
+    return v;
+}
+IMS_HD void ext_step(const ExtXY *lut, uint32_t mm, int c, int &run, int &best) {
+    uint32_t row = (uint32_t)run >> EXT_SC_SHIFT;
+    row = row < 9u ? row : 9u;
+#if defined(__CUDA_ARCH__)
+    const uint32_t idx = __byte_perm(mm, row, 0x5540u | (uint32_t)(c >> 3));  // row << 8 | mask byte (row < 256)
+    const int2 e = *reinterpret_cast<const int2 *>(lut + idx);
+    best = __viaddmax_s32(run, e.x, best);
+    run += e.y;
+#else
+    const ExtXY e = lut[row * 256u + ((mm >> c) & 0xFFu)];
+    const int key = run + e.x;
+    best = key > best ? key : best;
+    run += e.yd;
+#endif
+}
+
+template <class LUT>
+IMS_HD void ext_window(ExtState &s, const LUT *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
                        uint32_t e, int K = imsame::K) {
     const bool bwd = s.phase == 1;
     const int maxs = bwd ? s.bmax : s.fmax;
@@ -236,7 +268,7 @@ IMS_HD void ext_window(ExtState &s, const uint32_t *lut, const uint32_t *dpk, co
     int run = s.run, best = s.best;
     const int sc0 = run >> EXT_SC_SHIFT;
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) ext_step(lut, (mm >> c) & 0xFFu, run, best);
+    for (int c = 0; c < 32; c += 8) ext_step(lut, mm, c, run, best);
     const int sc1 = run >> EXT_SC_SHIFT;
     // +-1 per step: 2 * matches = steps + score change (also true for the padded steps)
     s.idn2 += ((run - s.run) & (int)EXT_POS_MASK) + sc1 - sc0;
@@ -325,14 +357,15 @@ IMS_HD void hit_first_masks(const HitHalf &d, const HitHalf &q, ExtState &s, uin
 // table lookups interleaved (the scan kernel is bound by the latency of those chains, not by
 // instruction issue).  On return each state is done (phase 2) or parked-ready: phase 0 / 1 with
 // t = 32, to be continued by ext_window.
-IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t mfa, uint32_t mba, uint32_t mfb,
+template <class LUT>
+IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const LUT *lut, uint32_t mfa, uint32_t mba, uint32_t mfb,
                        uint32_t mbb, int K = imsame::K) {
     const int k0 = K << EXT_SC_SHIFT, kb = k0 + EXT_BEST_BIAS;
     int ra = k0, ba = kb, rb = k0, bb = kb;
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
-        ext_step(lut, (mfa >> c) & 0xFFu, ra, ba);
-        ext_step(lut, (mfb >> c) & 0xFFu, rb, bb);
+        ext_step(lut, mfa, c, ra, ba);
+        ext_step(lut, mfb, c, rb, bb);
     }
     const int sca = ra >> EXT_SC_SHIFT, scb = rb >> EXT_SC_SHIFT;
     const bool fa_over = sca == 0 || sa.fmax <= 32, fb_over = scb == 0 || sb.fmax <= 32;
@@ -341,8 +374,8 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const uint32_t *lut, uint32_t
     const int hra = ra2 >> EXT_SC_SHIFT, hrb = rb2 >> EXT_SC_SHIFT;
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
-        ext_step(lut, (mba >> c) & 0xFFu, ra2, ba2);
-        ext_step(lut, (mbb >> c) & 0xFFu, rb2, bb2);
+        ext_step(lut, mba, c, ra2, ba2);
+        ext_step(lut, mbb, c, rb2, bb2);
     }
     if (sa.bmax <= 0) { ra2 = hra << EXT_SC_SHIFT; ba2 = kb; }  // no room: no backward step at all
     if (sb.bmax <= 0) { rb2 = hrb << EXT_SC_SHIFT; bb2 = kb; }

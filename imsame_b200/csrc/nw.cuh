@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
 }
 
 // K4b: one thread per winner walks the stored back-pointers (traceback.cuh)
-__global__ void tb_walk_kernel(const PairRes *res, const uint16_t *tb, const uint64_t *tb_off,
+static __global__ void tb_walk_kernel(const PairRes *res, const uint16_t *tb, const uint64_t *tb_off,
                                const uint32_t *strides, uint32_t n_pairs, uint32_t *ops,
                                const uint64_t *ops_off, uint32_t *n_ops, uint32_t *end_xy) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) {

@@ -1,0 +1,15 @@
+// nwp_launch.h -- host entry points of the packed-word NW kernels (nwp.cuh), compiled in nwp_launch.cu
+#pragma once
+#include <cuda_runtime.h>
+#include "nw.cuh"
+#include "nwp_core.cuh"
+
+namespace imsame {
+
+// resident blocks per SM of the class-c kernel (16 lanes x 2c columns per pair), < 0 on a CUDA error
+int nwp_blocks_per_sm(int c);
+// launch the class-c kernel; when every query read of the run has the same length (a.q.fixed_len) the
+// variant with the last column's register slot compiled in is chosen
+void nwp_launch(int c, int grid, cudaStream_t stream, const NwArgs &a);
+
+}  // namespace imsame

@@ -90,41 +90,47 @@ __device__ __forceinline__ uint32_t inv_of(uint32_t fixed_len) {
     return fixed_len >= 2 ? (uint32_t)((1ull << 32) / fixed_len) : 0u;
 }
 
-// A walk that is still running after its first window in either direction (a true overlap: up to
-// a whole read both ways) is parked in a per-warp queue; parked walks are finished 32 at a time,
-// so the many short walks of random hits never wait for the few long ones.
+// A walk that is still alive after its first window in either direction (a true overlap: up to a whole read
+// both ways; or one of the ~25 % of random hits that survive 32 bases) is parked in a per-warp queue.  The
+// queue is worked off 32 walks at a time, ONE further window per walk and round; what is still alive goes
+// back into the queue.  Every lane of a round has a window to do, however different the walks' lengths are
+// (round 1 ran each batch of 32 to completion: half of the lanes idle behind the batch's longest walk).
 constexpr int SCAN_QCAP = 64;
 
 struct ParkedWalk {
     uint32_t p, e, ylen;
     ExtState st;
 };
-// the per-warp queue is stored field by field (10 arrays of SCAN_QCAP words): consecutive lanes touch
-// consecutive banks (as an array of 40-byte structs every access was a 2-way bank conflict)
-constexpr int PARK_FIELDS = 11;
+// seven words per walk, stored field by field (7 arrays of SCAN_QCAP words): consecutive lanes touch
+// consecutive banks
+constexpr int PARK_FIELDS = 7;
 __device__ __forceinline__ void park_store(uint32_t (*q)[SCAN_QCAP], int slot, const ParkedWalk &w) {
     q[0][slot] = w.p; q[1][slot] = w.e;
-    q[2][slot] = (uint32_t)w.st.phase; q[3][slot] = (uint32_t)w.st.t; q[4][slot] = (uint32_t)w.st.run;
-    q[5][slot] = (uint32_t)w.st.best; q[6][slot] = (uint32_t)w.st.pos_f; q[7][slot] = (uint32_t)w.st.idn2;
-    q[8][slot] = (uint32_t)w.st.fmax; q[9][slot] = (uint32_t)w.st.bmax; q[10][slot] = w.ylen;
+    q[2][slot] = (uint32_t)w.st.run; q[3][slot] = (uint32_t)w.st.best;
+    q[4][slot] = (uint32_t)w.st.pos_f | ((uint32_t)w.st.idn2 << 15);                 // <= 32767 | <= 65534
+    q[5][slot] = (uint32_t)(w.st.fmax < 0 ? 0 : w.st.fmax) | ((uint32_t)(w.st.bmax < 0 ? 0 : w.st.bmax) << 16);
+    q[6][slot] = w.ylen | ((uint32_t)w.st.phase << 15) | ((uint32_t)w.st.t << 11);  // t: multiple of 32, < 32768
 }
 __device__ __forceinline__ ParkedWalk park_load(const uint32_t (*q)[SCAN_QCAP], int slot) {
     ParkedWalk w;
     w.p = q[0][slot]; w.e = q[1][slot];
-    w.st.phase = (int)q[2][slot]; w.st.t = (int)q[3][slot]; w.st.run = (int)q[4][slot];
-    w.st.best = (int)q[5][slot]; w.st.pos_f = (int)q[6][slot]; w.st.idn2 = (int)q[7][slot];
-    w.st.fmax = (int)q[8][slot]; w.st.bmax = (int)q[9][slot]; w.ylen = q[10][slot];
+    w.st.run = (int)q[2][slot]; w.st.best = (int)q[3][slot];
+    const uint32_t pi = q[4][slot], fb = q[5][slot], yt = q[6][slot];
+    w.st.pos_f = (int)(pi & 0x7FFFu); w.st.idn2 = (int)(pi >> 15);
+    w.st.fmax = (int)(fb & 0xFFFFu); w.st.bmax = (int)(fb >> 16);
+    w.ylen = yt & 0x7FFFu; w.st.phase = (int)((yt >> 15) & 1u); w.st.t = (int)((yt >> 16) << 5);
     return w;
 }
 
 // the e-value test (src/alignmentFunctions.c:139) on a finished walk, through the integer table nmin[ylen]
-// (host/thresholds.c); the query read itself is only looked up for the ~0.3 % of the hits that pass
-__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, uint32_t p, uint32_t e, uint32_t ylen,
-                                           const ExtState &st, unsigned long long &c_pass,
+// (host/thresholds.c); the query read itself is only looked up for the ~0.3 % of the hits that pass.
+// thr_fixed: nmin of the one read length when all query reads have the same, else -1.
+__device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, int thr_fixed, uint32_t p, uint32_t e,
+                                           uint32_t ylen, const ExtState &st, unsigned long long &c_pass,
                                            unsigned long long &c_anom, int k) {
     const int n = ext_result(st, k);
+    if (n >= 0 && n < (thr_fixed >= 0 ? thr_fixed : (int)a.nmin[ylen])) return;
     if (n < 0) c_anom++;  // the reference's unsigned wrap (:373) would make this pass; unreachable
-    if (n >= 0 && n < (int)a.nmin[ylen]) return;
     const uint32_t r = find_read_inv(a.q, q_inv, e);
     const uint32_t ys = read_start(a.q, r);
     c_pass++;
@@ -135,43 +141,57 @@ __device__ __forceinline__ void finish_hit(const ScanArgs &a, uint32_t q_inv, ui
     }
 }
 
-// finish `count` (<= 32) parked walks, one per lane
-__device__ __forceinline__ void drain_parked(const ScanArgs &a, uint32_t q_inv, const uint32_t *s_lut,
-                                             const uint32_t (*q)[SCAN_QCAP], int first, int count, int lane,
-                                             unsigned long long &c_pass, unsigned long long &c_anom, int k) {
+// one round: the last (up to) 32 parked walks advance by one window each; returns the new queue length
+__device__ __forceinline__ int drain_round(const ScanArgs &a, uint32_t q_inv, int thr_fixed, const ExtXY *s_lut,
+                                           uint32_t (*q)[SCAN_QCAP], int n_parked, int lane,
+                                           unsigned long long &c_pass, unsigned long long &c_anom, int k) {
+    const int take = n_parked < 32 ? n_parked : 32, first = n_parked - take;
     ParkedWalk w;
     w.st.phase = 2;
     w.p = w.e = w.ylen = 0;
-    if (lane < count) w = park_load(q, first + lane);
-    while (__any_sync(0xffffffffu, w.st.phase < 2))
-        if (w.st.phase < 2) ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e, k);
-    if (lane < count) finish_hit(a, q_inv, w.p, w.e, w.ylen, w.st, c_pass, c_anom, k);
+    if (lane < take) w = park_load(q, first + lane);
+    __syncwarp();  // every slot has been read before any is overwritten
+    if (lane < take) {
+        ext_window(w.st, s_lut, a.db.pk, a.q.pk, w.p, w.e, k);
+        if (w.st.phase == 2) finish_hit(a, q_inv, thr_fixed, w.p, w.e, w.ylen, w.st, c_pass, c_anom, k);
+    }
+    const bool again = lane < take && w.st.phase < 2;
+    const unsigned m = __ballot_sync(0xffffffffu, again);
+    if (again) park_store(q, first + __popc(m & ((1u << lane) - 1u)), w);
+    __syncwarp();
+    return first + __popc(m);
 }
 
 // KT: the seed length as a compile-time constant (12 = the reference's FIXED_K, the only value it has),
 // or 0 = read it from the arguments (imsame_gpu_set_kmer)
 //
-// A warp takes 32 consecutive database positions.  Per position (lane): the word's bucket and the database
-// windows around it as bit planes (common.cuh), kept in shared memory -- they are the same for every hit of
-// the position.  The ~14 hits per position are then spread evenly over the lanes (warp prefix sum + 5-step
-// search), two hits per lane per iteration; a hit reads its 24-byte table entry (consecutive lanes read
-// consecutive entries: a streaming access), forms both first-window mismatch masks with four logic
+// A warp takes 32 consecutive database positions.  Per position with a non-empty bucket: the bucket and the
+// database windows around the word as bit planes (common.cuh), kept in shared memory -- they are the same
+// for every hit of the position.  The ~14 hits per position are then spread evenly over the lanes, two hits
+// per lane per iteration: the position a hit belongs to comes from a 64-bit mask of the bucket starts inside
+// the iteration's 64 hit slots (two warp-wide OR reductions + population counts; round 1 searched a prefix
+// array with five dependent shared-memory loads per hit).  A hit reads its 24-byte table entry (consecutive
+// lanes read consecutive entries: a streaming access), forms both first-window mismatch masks with four logic
 // operations and walks them through the max-plus table (extend.cuh: ext_first2).  Walks that are still alive
-// after their first window (true overlaps and ~1 random hit in 4) are parked and finished 32 at a time.
+// after their first window are parked (above).
 template <int KT>
 __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     const int k = KT ? KT : a.k;
     __shared__ uint32_t s_park[SCAN_WARPS][PARK_FIELDS][SCAN_QCAP];
-    __shared__ uint32_t s_excl[SCAN_WARPS][33];
-    __shared__ uint32_t s_b0[SCAN_WARPS][32];
-    __shared__ uint2 s_wf[SCAN_WARPS][32];   // database forward window of the position (lo, hi planes)
-    __shared__ uint2 s_wb[SCAN_WARPS][32];   // database backward window
-    __shared__ int2 s_room[SCAN_WARPS][32];  // steps left inside the database read: forward, backward
-    __shared__ uint32_t s_lut[EXT_LUT3_SIZE];
-    for (int i = threadIdx.x; i < EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = a.lut[i];
+    // per non-empty position of the warp's tile, in position order
+    __shared__ uint32_t s_excl[SCAN_WARPS][32];  // first hit slot of the position's bucket
+    __shared__ uint32_t s_b0[SCAN_WARPS][32];    // first table entry of the bucket
+    __shared__ uint32_t s_p[SCAN_WARPS][32];     // llpos.pos: index after the word (src/IMSAME.c:247,265)
+    __shared__ uint2 s_wf[SCAN_WARPS][32];       // database forward window (lo, hi planes)
+    __shared__ uint2 s_wb[SCAN_WARPS][32];       // database backward window
+    __shared__ int2 s_room[SCAN_WARPS][32];      // steps left inside the database read: forward, backward
+    __shared__ __align__(8) ExtXY s_lut[EXT_LUT3_SIZE];
+    for (int i = threadIdx.x; i < EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = ext_xy_of(a.lut[i]);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     const uint32_t q_inv = inv_of(a.q.fixed_len), db_inv = inv_of(a.db.fixed_len);
+    const int thr_fixed = a.q.fixed_len ? (int)a.nmin[a.q.fixed_len] : -1;
     const uint32_t n_tiles = (a.db.total + 31) / 32;
     const uint32_t gw = blockIdx.x * SCAN_WARPS + warp, nw = gridDim.x * SCAN_WARPS;
     unsigned long long c_words = 0, c_hits = 0, c_pass = 0, c_anom = 0;
@@ -182,23 +202,16 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
         // concurrently): the decision must be the same in every lane of the warp
         if (__shfl_sync(0xffffffffu, lane == 0 ? *(volatile int *)a.overflow : 0, 0)) break;
         const uint32_t q = tile * 32 + lane;  // index of the word's last base
-        uint32_t cnt = 0, b0 = 0;
+        uint32_t cnt = 0, b0 = 0, xs = 0, xe = 0;
         if (q < a.db.total) {
             const uint32_t s = find_read_inv(a.db, db_inv, q);
-            const uint32_t xs = read_start(a.db, s);
-            const uint32_t xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
+            xs = read_start(a.db, s);
+            xe = a.db.fixed_len ? xs + a.db.fixed_len : a.db.start[s + 1];
             if (q >= xs + (uint32_t)(k - 1) && !word_broken(a, q, k)) {
                 const uint32_t code = fetch16(a.db.pk, (uint64_t)q - (uint32_t)(k - 1)) & kmask_of(k);
                 b0 = a.off[code];
                 cnt = a.off[(size_t)code + 1] - b0;
                 c_words++;
-                if (cnt) {
-                    // llpos.pos: index after the word (src/IMSAME.c:247,265)
-                    const HitHalf h = db_half(a.db.pk, q + 1, xs, xe, k);
-                    s_wf[warp][lane] = make_uint2(h.f_lo, h.f_hi);
-                    s_wb[warp][lane] = make_uint2(h.b_lo, h.b_hi);
-                    s_room[warp][lane] = make_int2(h.froom, h.broom);
-                }
             }
         }
         uint32_t incl = cnt;
@@ -208,20 +221,35 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             if (lane >= o) incl += y;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        s_excl[warp][lane] = incl - cnt;
-        s_b0[warp][lane] = b0;
+        const unsigned ne = __ballot_sync(0xffffffffu, cnt != 0);
+        if (cnt) {
+            const int slot = __popc(ne & lt_mask);
+            const HitHalf h = db_half(a.db.pk, q + 1, xs, xe, k);
+            s_excl[warp][slot] = incl - cnt;
+            s_b0[warp][slot] = b0;
+            s_p[warp][slot] = q + 1;
+            s_wf[warp][slot] = make_uint2(h.f_lo, h.f_hi);
+            s_wb[warp][slot] = make_uint2(h.b_lo, h.b_hi);
+            s_room[warp][slot] = make_int2(h.froom, h.broom);
+        }
         __syncwarp();
+        // lane i keeps the first hit slot of the i-th non-empty position
+        const uint32_t my_start = lane < __popc(ne) ? s_excl[warp][lane] : 0xFFFFFFFFu;
+        int n_before = 0;  // non-empty positions whose bucket starts before h0 (warp-uniform)
         for (uint32_t h0 = 0; h0 < total; h0 += 64) {
+            // bit j of (m_lo, m_hi): a bucket starts at hit slot h0 + j
+            const uint32_t d = my_start - h0;
+            const uint32_t m_lo = __reduce_or_sync(0xffffffffu, d < 32u ? 1u << d : 0u);
+            const uint32_t m_hi = __reduce_or_sync(0xffffffffu, (d - 32u) < 32u ? 1u << (d - 32u) : 0u);
+            const int c_lo = __popc(m_lo);
+            // position of a hit slot = (number of bucket starts at or before it) - 1; slots past the last hit
+            // fall into the last bucket and are clamped to the last hit
+            const int oa = n_before + __popc(m_lo & le_mask) - 1;
+            const int ob = n_before + c_lo + __popc(m_hi & le_mask) - 1;
+            n_before += c_lo + __popc(m_hi);
             const uint32_t ha = h0 + lane, hb = h0 + 32 + lane;
             const bool la = ha < total, lb = hb < total;
-            // owner = last lane whose exclusive prefix is <= h (dead slots search for the last hit)
             const uint32_t sa_h = la ? ha : total - 1, sb_h = lb ? hb : total - 1;
-            int oa = 0, ob = 0;
-#pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                if (s_excl[warp][oa + step] <= sa_h) oa += step;
-                if (s_excl[warp][ob + step] <= sb_h) ob += step;
-            }
             const uint2 *qa = reinterpret_cast<const uint2 *>(a.qtab + (s_b0[warp][oa] + (sa_h - s_excl[warp][oa])));
             const uint2 *qb = reinterpret_cast<const uint2 *>(a.qtab + (s_b0[warp][ob] + (sb_h - s_excl[warp][ob])));
             // streamed once per database position that hits the bucket: no reuse worth a cache line
@@ -230,7 +258,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             const uint2 dfa = s_wf[warp][oa], dba = s_wb[warp][oa], dfb = s_wf[warp][ob], dbb = s_wb[warp][ob];
             const int2 rma = s_room[warp][oa], rmb = s_room[warp][ob];
             const uint32_t ea = ma.x, eb = mb2.x;
-            const uint32_t pa = tile * 32 + oa + 1, pb = tile * 32 + ob + 1;
+            const uint32_t pa = s_p[warp][oa], pb = s_p[warp][ob];
             ExtState sta, stb;
             // mismatch bits of the first window each way (step u <-> bit u); steps past a read end are
             // mismatches (extend.cuh: hit_first_masks = ext_init + ext_first_masks on the two halves)
@@ -250,8 +278,8 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             c_hits += (la ? 1 : 0) + (lb ? 1 : 0);
             const uint32_t ylen_a = (ma.y & 0xFFFFu) + (ma.y >> 16) + (uint32_t)(k - 1);
             const uint32_t ylen_b = (mb2.y & 0xFFFFu) + (mb2.y >> 16) + (uint32_t)(k - 1);
-            if (la && sta.phase == 2) finish_hit(a, q_inv, pa, ea, ylen_a, sta, c_pass, c_anom, k);
-            if (lb && stb.phase == 2) finish_hit(a, q_inv, pb, eb, ylen_b, stb, c_pass, c_anom, k);
+            if (la && sta.phase == 2) finish_hit(a, q_inv, thr_fixed, pa, ea, ylen_a, sta, c_pass, c_anom, k);
+            if (lb && stb.phase == 2) finish_hit(a, q_inv, thr_fixed, pb, eb, ylen_b, stb, c_pass, c_anom, k);
 #pragma unroll
             for (int half = 0; half < 2; half++) {
                 const bool unfinished = half ? (lb && stb.phase < 2) : (la && sta.phase < 2);
@@ -260,21 +288,19 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
                     if (unfinished) {
                         ParkedWalk w;
                         w.p = half ? pb : pa; w.e = half ? eb : ea; w.ylen = half ? ylen_b : ylen_a; w.st = half ? stb : sta;
-                        park_store(s_park[warp], n_parked + __popc(park & ((1u << lane) - 1u)), w);
+                        park_store(s_park[warp], n_parked + __popc(park & lt_mask), w);
                     }
                     n_parked += __popc(park);
                     __syncwarp();
-                    if (n_parked >= 32) {
-                        n_parked -= 32;
-                        drain_parked(a, q_inv, s_lut, s_park[warp], n_parked, 32, lane, c_pass, c_anom, k);
-                        __syncwarp();
-                    }
+                    while (n_parked >= 32)
+                        n_parked = drain_round(a, q_inv, thr_fixed, s_lut, s_park[warp], n_parked, lane, c_pass, c_anom, k);
                 }
             }
         }
         __syncwarp();  // the next tile overwrites the per-position shared arrays
     }
-    if (n_parked) drain_parked(a, q_inv, s_lut, s_park[warp], 0, n_parked, lane, c_pass, c_anom, k);
+    while (n_parked > 0)
+        n_parked = drain_round(a, q_inv, thr_fixed, s_lut, s_park[warp], n_parked, lane, c_pass, c_anom, k);
     // counters: warp-reduce then one atomic per warp
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {

@@ -44,6 +44,7 @@ void imsame_fasta_view(const imsame_fasta *f, imsame_seqinfo *v);
 /* nmin[ylen], ylen in [0, IMSAME_MAX_READ_SIZE]: smallest n = 2*idents - t_len
  * with 0.333L*ylen*db_total_len*expl(-0.275*(4n)) < min_e_value; 65535 = never. */
 void imsame_build_nmin(long double min_e_value, uint64_t db_total_len, uint16_t *nmin);
+void imsame_build_nmin_upto(long double min_e_value, uint64_t db_total_len, uint16_t *nmin, uint64_t max_ylen);
 /* lmin[ylen]: smallest length with (long double)length/ylen >= min_coverage */
 void imsame_build_lmin(long double min_coverage, uint16_t *lmin);
 /* imin[len], len in [0, 2*IMSAME_MAX_READ_SIZE]: smallest identities with

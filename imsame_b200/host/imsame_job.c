@@ -17,31 +17,16 @@ static double now_s(void) {
     return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 
-/* one database shard on one GPU */
+/* contexts of a multi-GPU job come up side by side (0.5 - 1 s each) */
 typedef struct {
-    int device;
-    imsame_ctx *ctx; /* borrowed (cached) or NULL: create + destroy */
-    const imsame_seqinfo *query;
-    imsame_seqinfo db;
-    imsame_params params;
-    imsame_best *best;
-    imsame_stats stats;
-    int kmer;
-    int rc;
-    char err[256];
-} shard_job;
+    int device, kmer, rc;
+    imsame_ctx *ctx;
+} ctx_job;
 
-static void *shard_main(void *arg) {
-    shard_job *j = (shard_job *)arg;
-    imsame_ctx *ctx = j->ctx;
-    if (!ctx) {
-        j->rc = imsame_gpu_create(&ctx, j->device);
-        if (j->rc) return NULL;
-    }
-    j->rc = imsame_gpu_set_kmer(ctx, j->kmer);
-    if (!j->rc) j->rc = imsame_gpu_align(ctx, &j->db, j->query, &j->params, j->best, &j->stats);
-    if (j->rc) snprintf(j->err, sizeof j->err, "%s", imsame_gpu_last_cuda_error(ctx));
-    if (!j->ctx) imsame_gpu_destroy(ctx);
+static void *ctx_main(void *arg) {
+    ctx_job *j = (ctx_job *)arg;
+    j->rc = imsame_gpu_create(&j->ctx, j->device);
+    if (!j->rc) j->rc = imsame_gpu_set_kmer(j->ctx, j->kmer);
     return NULL;
 }
 
@@ -66,72 +51,52 @@ int imsame_run_job(const imsame_fasta *qf, const imsame_fasta *dbf, const imsame
     p.igap = o->igap;
     p.egap = o->egap;
     p.n_threads = o->n_threads;
+    const int kmer = o->kmer ? o->kmer : 12; /* FIXED_K, src/structs.h:15 */
 
     int ng = o->gpus < 1 ? 1 : o->gpus;
     if ((uint64_t)ng > db.n_seqs) ng = (int)db.n_seqs;
-    imsame_ctx *ctx = NULL; /* single-GPU jobs: one context for alignment and traceback, kept if the caller caches */
+    imsame_ctx *ctx = NULL; /* device `o->device`: alignment (shard 0) and traceback; kept if the caller caches */
     int rc = IMSAME_OK;
+    if (ctx_cache && *ctx_cache) ctx = *ctx_cache;
     if (ng == 1) {
-        if (ctx_cache && *ctx_cache) ctx = *ctx_cache;
-        else if ((rc = imsame_gpu_create(&ctx, o->device))) { free(best); return rc; }
+        if (!ctx && (rc = imsame_gpu_create(&ctx, o->device))) { free(best); return rc; }
         if (ctx_cache) *ctx_cache = ctx;
-    }
-    shard_job *jobs = (shard_job *)calloc((size_t)ng, sizeof(shard_job));
-    pthread_t *th = (pthread_t *)calloc((size_t)ng, sizeof(pthread_t));
-    for (int g = 0; g < ng; g++) {
-        /* contiguous read ranges; global coordinates keep keys and the e-value exact */
-        uint64_t r0 = db.n_seqs * (uint64_t)g / (uint64_t)ng, r1 = db.n_seqs * (uint64_t)(g + 1) / (uint64_t)ng;
-        uint64_t b0 = db.start_pos[r0], b1 = db.start_pos[r1];
-        shard_job *j = &jobs[g];
-        j->device = o->device + g;
-        j->ctx = ng == 1 ? ctx : NULL;
-        j->query = &qv;
-        j->db.sequences = db.sequences + b0;
-        j->db.total_len = b1 - b0;
-        j->db.n_seqs = r1 - r0;
-        uint64_t *st = (uint64_t *)malloc((r1 - r0 + 1) * sizeof(uint64_t));
-        for (uint64_t r = r0; r <= r1; r++) st[r - r0] = db.start_pos[r] - b0;
-        j->db.start_pos = st;
-        uint64_t nb = 0, *bk = (uint64_t *)malloc((db.n_breaks + 1) * sizeof(uint64_t));
-        for (uint64_t k = 0; k < db.n_breaks; k++)
-            if (db.break_pos[k] >= b0 && db.break_pos[k] < b1) bk[nb++] = db.break_pos[k] - b0;
-        j->db.break_pos = bk;
-        j->db.n_breaks = nb;
-        j->params = p;
-        j->params.db_total_len_global = db.total_len;
-        j->params.db_pos_base = b0;
-        j->params.db_seq_base = r0;
-        j->kmer = o->kmer ? o->kmer : 12; /* FIXED_K, src/structs.h:15 */
-        j->best = ng == 1 ? best : (imsame_best *)calloc(q.n_seqs, sizeof(imsame_best));
-        if (ng == 1) shard_main(j);
-        else if (pthread_create(&th[g], NULL, shard_main, j)) { j->rc = IMSAME_ECUDA; snprintf(j->err, sizeof j->err, "pthread_create"); }
-    }
-    for (int g = 0; g < ng; g++) {
-        if (ng > 1 && !(jobs[g].rc == IMSAME_ECUDA && !strcmp(jobs[g].err, "pthread_create"))) pthread_join(th[g], NULL);
-        if (jobs[g].rc && !rc) {
-            rc = jobs[g].rc;
-            if (err && errlen) snprintf(err, errlen, "device %d: %s", jobs[g].device, jobs[g].err);
+        rc = imsame_gpu_set_kmer(ctx, kmer);
+        if (!rc) rc = imsame_gpu_align(ctx, &dv, &qv, &p, best, NULL);
+        if (rc && err && errlen) snprintf(err, errlen, "%s", imsame_gpu_last_cuda_error(ctx));
+    } else {
+        /* the database sharded by contiguous read ranges over ng GPUs; the per-read first accepted hit is
+           reduced with NCCL inside the library (imsame_gpu_align_sharded), replacing src/IMSAME.c:430-467 */
+        ctx_job *jobs = (ctx_job *)calloc((size_t)ng, sizeof(ctx_job));
+        pthread_t *th = (pthread_t *)calloc((size_t)ng, sizeof(pthread_t));
+        imsame_ctx **ctxs = (imsame_ctx **)calloc((size_t)ng, sizeof(imsame_ctx *));
+        for (int g = 0; g < ng; g++) {
+            jobs[g].device = o->device + g;
+            jobs[g].kmer = kmer;
+            if (g == 0 && ctx) { jobs[g].ctx = ctx; jobs[g].rc = imsame_gpu_set_kmer(ctx, kmer); continue; }
+            if (pthread_create(&th[g], NULL, ctx_main, &jobs[g])) { ctx_main(&jobs[g]); th[g] = 0; }
         }
-    }
-    if (!rc && ng > 1) {
-        /* first accepted hit in the reference's scan order: k-mer end ascending, db position descending */
-        for (uint64_t r = 0; r < q.n_seqs; r++)
-            for (int g = 0; g < ng; g++) {
-                const imsame_best *c = &jobs[g].best[r];
-                if (!c->accepted) continue;
-                if (!best[r].accepted || c->qpos_end < best[r].qpos_end ||
-                    (c->qpos_end == best[r].qpos_end && c->db_pos > best[r].db_pos))
-                    best[r] = *c;
+        for (int g = 0; g < ng; g++) {
+            if (th[g]) pthread_join(th[g], NULL);
+            ctxs[g] = jobs[g].ctx;
+            if (jobs[g].rc && !rc) {
+                rc = jobs[g].rc;
+                if (err && errlen) snprintf(err, errlen, "device %d: %s", jobs[g].device, imsame_gpu_strerror(rc));
             }
+        }
+        if (o->trace) { fprintf(stderr, "[imsame] %d contexts %.3f s\n", ng, now_s() - tp); tp = now_s(); }
+        if (!rc) {
+            rc = imsame_gpu_align_sharded(ctxs, ng, &dv, &qv, &p, best, NULL);
+            if (rc && err && errlen) snprintf(err, errlen, "%s", imsame_gpu_last_cuda_error(ctxs[0]));
+        }
+        for (int g = 1; g < ng; g++) imsame_gpu_destroy(ctxs[g]);
+        ctx = ctxs[0];
+        if (ctx_cache && ctx) *ctx_cache = ctx;
+        free(jobs);
+        free(th);
+        free(ctxs);
     }
-    for (int g = 0; g < ng; g++) {
-        if (ng > 1) free(jobs[g].best);
-        free((void *)jobs[g].db.start_pos);
-        free((void *)jobs[g].db.break_pos);
-    }
-    free(jobs);
-    free(th);
-    if (rc) { free(best); if (ctx && !ctx_cache) imsame_gpu_destroy(ctx); return rc; }
+    if (rc) { free(best); if (ctx && !(ctx_cache && *ctx_cache == ctx)) imsame_gpu_destroy(ctx); return rc; }
     for (uint64_t r = 0; r < q.n_seqs; r++) accepted += best[r].accepted;
     if (o->trace) { fprintf(stderr, "[imsame] align (all shards) %.3f s\n", now_s() - tp); tp = now_s(); }
 

@@ -24,8 +24,14 @@ static long double evalue_of(uint64_t n, uint64_t ylen, uint64_t db_total_len) {
 }
 
 void imsame_build_nmin(long double min_e_value, uint64_t db_total_len, uint16_t *nmin) {
-    const uint64_t n_max = 2ull * IMSAME_MAX_READ_SIZE + 64;
-    for (uint64_t ylen = 0; ylen <= IMSAME_MAX_READ_SIZE; ylen++) {
+    imsame_build_nmin_upto(min_e_value, db_total_len, nmin, IMSAME_MAX_READ_SIZE);
+}
+
+/* reads longer than MAX_READ_SIZE still go through the e-value test: the reference only stops when such a
+ * read reaches NW (src/alignmentFunctions.c:155), so the scan needs their thresholds too */
+void imsame_build_nmin_upto(long double min_e_value, uint64_t db_total_len, uint16_t *nmin, uint64_t max_ylen) {
+    const uint64_t n_max = 2ull * max_ylen + 64 < 65534 ? 2ull * max_ylen + 64 : 65534;
+    for (uint64_t ylen = 0; ylen <= max_ylen; ylen++) {
         /* e is non-increasing in n: binary search for the first n with e < min */
         if (!(evalue_of(n_max, ylen, db_total_len) < min_e_value)) { nmin[ylen] = 65535; continue; }
         uint64_t lo = 0, hi = n_max; /* invariant: pass(hi) */

@@ -35,7 +35,9 @@ enum {
     IMSAME_ENOMEM = -4,    /* host or device allocation failed */
     IMSAME_EREADSIZE = -5, /* "Read size reached for gapped alignment." (src/alignmentFunctions.c:155) */
     IMSAME_ESTATE = -6,    /* call order violated (e.g. run before set_query) */
-    IMSAME_ELIMIT = -7     /* input exceeds an implementation limit (documented in DESIGN.md) */
+    IMSAME_ELIMIT = -7,    /* input exceeds an implementation limit (documented in DESIGN.md) */
+    IMSAME_EPEER = -8,     /* sharded run: another shard failed (its own code is returned on its rank) */
+    IMSAME_ENCCL = -9      /* NCCL missing or failed (see imsame_gpu_last_cuda_error) */
 };
 
 /* Replaces SeqInfo (src/structs.h:40-45), filled like src/IMSAME.c:199-226,323-347:
@@ -92,6 +94,8 @@ typedef struct imsame_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint32_t k2_launches, k3_launches, total_launches;
     uint32_t k3_packed_launches; /* of k3_launches: packed-word kernel (imsame_gpu_set_nw_mode) */
+    float ms_comm;               /* NCCL reductions of a sharded run (imsame_gpu_run_sharded) */
+    uint32_t reserved;
 } imsame_stats;
 
 typedef struct imsame_ctx imsame_ctx;
@@ -150,6 +154,35 @@ int imsame_gpu_fetch(imsame_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_
                      imsame_best *out);
 
 #define IMSAME_KEY_NONE 0x7FFFFFFFFFFFFFFFull
+
+/* ---- database sharded over several GPUs: the reduction lives in the library -------------------
+ * Replaces the pthread fan-out + join of src/IMSAME.c:430-467 at the scale the reference cannot reach:
+ * the database is cut into contiguous read ranges, one per GPU, the query and its word table are
+ * replicated, and the per-read first accepted hit -- a minimum over the scan-order key -- is reduced
+ * with ncclAllReduce(ncclUint64, ncclMin) over NVLink between k-mer-end bands (an accepted early hit
+ * in one shard prunes the later candidates of that read in every shard, like the reference's early
+ * exit, src/alignmentFunctions.c:172,189), followed by one ncclMax of the owner's payload.
+ * NCCL is loaded at run time (libnccl.so.2; the one already in the process if there is one).
+ *
+ * One rank per context.  Ranks may live in one process (imsame_gpu_align_sharded does everything)
+ * or in one process per GPU: rank 0 calls imsame_gpu_comm_id, hands the 128 bytes to the others by
+ * any means (torch.distributed, MPI, a file), every rank calls imsame_gpu_comm_init, then
+ * set_query / set_db(its shard) / imsame_gpu_run_sharded with params->db_*_base/global set. */
+#define IMSAME_COMM_ID_BYTES 128
+int imsame_gpu_comm_id(void *id /* IMSAME_COMM_ID_BYTES */);
+int imsame_gpu_comm_init(imsame_ctx *ctx, const void *id, int n_ranks, int rank);
+int imsame_gpu_comm_free(imsame_ctx *ctx);
+/* imsame_gpu_run over this rank's resident shard with the key exchange every `exchange_every` bands
+ * (<= 0: library default).  On return d_keys / d_payload (or the context's own buffers) hold the
+ * REDUCED result on every rank; imsame_gpu_fetch decodes it.  Collective: every rank must call it. */
+int imsame_gpu_run_sharded(imsame_ctx *ctx, const imsame_params *params, uint64_t *d_keys,
+                           uint64_t *d_payload, int exchange_every, imsame_stats *stats);
+/* One process, n GPUs: cut `db` into n contiguous read ranges, upload, build the query table on every
+ * GPU, run sharded, decode into out (nq entries).  ctxs[i] must sit on n different devices; stats: n
+ * entries or NULL.  The communicator is created on first use and kept in the contexts. */
+int imsame_gpu_align_sharded(imsame_ctx *const *ctxs, int n, const imsame_seqinfo *db,
+                             const imsame_seqinfo *query, const imsame_params *params, imsame_best *out,
+                             imsame_stats *stats);
 
 /* ---- NW on explicit pairs (src/alignmentFunctions.c:389-560 in isolation) */
 /* X[i] / Y[i]: ASCII reads; out5[i*5..] = score, bx, by, length, identities */

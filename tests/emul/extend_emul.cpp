@@ -58,6 +58,8 @@ int main(int argc, char **argv) {
     }
     std::vector<uint32_t> lut2(EXT_LUT3_SIZE);
     build_ext_lut3(lut2.data());
+    std::vector<ExtXY> lutxy(EXT_LUT3_SIZE);  // the scan kernel's shared-memory form of the same table
+    for (int i = 0; i < EXT_LUT3_SIZE; i++) lutxy[i] = ext_xy_of(lut2[i]);
     // window_mismatch (32-bit halves) against the 64-bit form
     for (size_t i = 0; i + 40 < D.size() && i + 40 < Q.size(); i += 3) {
         size_t j = (i * 7 + 5) % (Q.size() - 40);
@@ -100,9 +102,9 @@ int main(int argc, char **argv) {
                                 if (bad++ < 10) printf("PLANES MISMATCH p=%u e=%u mf %08x/%08x mb %08x/%08x\n", p, e, mf2, mfb, mb2, mbb);
                             }
                         }
-                        ext_first2(A, Bst, lut2.data(), mfa, mba, mfb, mbb, k);
-                        while (A.phase < 2) ext_window(A, lut2.data(), dpk.data(), qpk.data(), prev_p, prev_e, k);
-                        while (Bst.phase < 2) ext_window(Bst, lut2.data(), dpk.data(), qpk.data(), p, e, k);
+                        ext_first2(A, Bst, lutxy.data(), mfa, mba, mfb, mbb, k);
+                        while (A.phase < 2) ext_window(A, lutxy.data(), dpk.data(), qpk.data(), prev_p, prev_e, k);
+                        while (Bst.phase < 2) ext_window(Bst, lutxy.data(), dpk.data(), qpk.data(), p, e, k);
                         if (prev_want != ext_result(A, k)) { if (bad++ < 10) printf("FIRST2(A) MISMATCH p=%u e=%u want=%ld got=%d\n", prev_p, prev_e, prev_want, ext_result(A, k)); }
                         if (want != ext_result(Bst, k)) { if (bad++ < 10) printf("FIRST2(B) MISMATCH p=%u e=%u want=%ld got=%d\n", p, e, (long)want, ext_result(Bst, k)); }
                     }

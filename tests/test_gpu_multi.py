@@ -41,7 +41,16 @@ def _worker(rank, world, port, tmpdir):
     ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")
     payload = torch.empty(nq, dtype=torch.int64, device="cuda")
-    if os.environ.get("IMSAME_TEST_STEPPED", "1") == "1":
+    mode = os.environ.get("IMSAME_TEST_STEPPED", "1")
+    if mode == "nccl_in_library":
+        # the product path: the library's own communicator (ncclCommInitRank from 128 bytes handed around by
+        # torch.distributed) and its band-stepped run with ncclMin / ncclMax reductions inside
+        box = [api.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], world, rank)
+        st = ctx.run_sharded(p, keys.data_ptr(), payload.data_ptr())
+        assert st["ms_comm"] > 0
+    elif mode == "1":
         # keys exchanged between bands (what bench.py does), payload of the owner at the end
         ctx.run_stepped(p, keys.data_ptr(), payload.data_ptr(),
                         exchange=lambda: dist.all_reduce(keys, op=dist.ReduceOp.MIN), exchange_every=3)
@@ -61,12 +70,12 @@ def _worker(rank, world, port, tmpdir):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("stepped", ["1", "0"])
+@pytest.mark.parametrize("stepped", ["nccl_in_library", "1", "0"])
 def test_nccl_sharded_equals_single_gpu(gpu, tmp_path, stepped):
     import torch.multiprocessing as mp
     from imsame_b200 import api
     os.environ["IMSAME_TEST_STEPPED"] = stepped
-    port = 29700 + (os.getpid() % 1000) + int(stepped)
+    port = 29700 + (os.getpid() % 1000) + len(stepped)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     rec = np.load(tmp_path / "rec.npy")
     db, ds, q, qs = sc.fixed_case(31, 4, 80000, 150, 16000, 1500, 0.03)
@@ -74,6 +83,34 @@ def test_nccl_sharded_equals_single_gpu(gpu, tmp_path, stepped):
     for f in ("accepted", "db_seq", "qpos_end", "db_pos", "length", "identities"):
         assert np.array_equal(rec[f], whole[f]), f
     assert int(whole["accepted"].sum()) > 300
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_align_sharded_in_one_process_equals_oracle(gpu):
+    """imsame_gpu_align_sharded: one process, one context per GPU, NCCL inside the library; ragged reads and
+    word breaks so that shard boundaries, global coordinates and the break lists are all exercised"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.ragged_case(515, 3, 50000, 9000, 700, 0.05, lo=30, hi=300)
+    rng = np.random.default_rng(1)
+    brk = np.unique(rng.integers(1, len(db), size=800)).astype(np.uint64)
+    brk = np.array([b for b in brk if b not in set(ds.tolist())], dtype=np.uint64)
+    odb, oq = hp.OracleSeqs(seq=db, start=ds, brk=brk), hp.OracleSeqs(seq=q, start=qs)
+    want = hp.best_to_records(hp.oracle_align(odb, oq, hp.default_params(n_threads=4))[0], len(qs) - 1)
+    n = min(_n_gpus(), 4)
+    ctxs = [gpu] + [api.Imsame(d) for d in range(1, n)]
+    try:
+        for _ in range(2):  # the second call reuses the communicator kept in the contexts
+            out, stats = api.align_sharded(ctxs, (db, ds), (q, qs), api.make_params(n_threads=4), db_breaks=brk)
+            got = {int(r): (int(o["db_seq"]), int(o["qpos_end"]), int(o["db_pos"]), int(o["length"]), int(o["identities"]))
+                   for r, o in enumerate(out) if o["accepted"]}
+            assert got == want and len(want) > 150
+            assert len(stats) == n and all(s["ms_comm"] > 0 and s["n_db_kmers"] > 0 for s in stats)
+            assert sum(s["n_db_kmers"] for s in stats) == gpu.align((db, ds), (q, qs), api.make_params(n_threads=4),
+                                                                     db_breaks=brk)[1]["n_db_kmers"]
+    finally:
+        for c in ctxs[1:]:
+            c.close()
+        gpu.comm_free()
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
