@@ -33,6 +33,8 @@ struct Seg {
     uint64_t pos_base = 0, seq_base = 0;  // offsets inside the shard handed to set_db
     uint32_t n = 0, total = 0, fixed_len = 0, n_brk = 0;
     uint32_t *pk = nullptr, *start = nullptr, *blk = nullptr, *brk = nullptr;
+    cudaEvent_t ready = nullptr;  // bases uploaded and packed (recorded on the upload stream)
+    bool wait_ready = false;      // the scan has to wait for `ready` (uploaded on another stream)
 };
 
 enum Phase { PH_PACKQ, PH_K1, PH_PACKDB, PH_K2, PH_K2B, PH_K3, PH_SELECT, PH_H2D, PH_D2H, PH_COMM, PH_COUNT };
@@ -42,10 +44,13 @@ enum Phase { PH_PACKQ, PH_K1, PH_PACKDB, PH_K2, PH_K2B, PH_K3, PH_SELECT, PH_H2D
 struct imsame_ctx {
     int device = 0;
     int n_sm = 0;
-    size_t l2_persist_max = 0, l2_window_max = 0;  // persisting-L2 limits of the device
-    int l2_pin = 1;                                // pin the packed query in L2 during the scan
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    // imsame_gpu_align uploads on a stream of its own, so that the database segments arrive and are packed while
+    // the scan of the earlier ones runs; everywhere else uploads share `stream`
+    cudaStream_t copy_stream = nullptr;
+    cudaStream_t up_stream = nullptr;  // the stream uploads currently go to (== stream outside imsame_gpu_align)
+    cudaEvent_t q_ready = nullptr;     // query packed (recorded on up_stream)
     std::string cuda_err;
 
     // query
@@ -143,15 +148,16 @@ cudaEvent_t new_event(imsame_ctx *ctx) {
 }
 struct PhaseScope {
     imsame_ctx *ctx;
+    cudaStream_t stream;
     imsame_ctx::Span sp;
-    PhaseScope(imsame_ctx *c, int ph) : ctx(c) {
+    PhaseScope(imsame_ctx *c, int ph, cudaStream_t on = nullptr) : ctx(c), stream(on ? on : c->stream) {
         sp.ph = ph;
         sp.a = new_event(c);
         sp.b = new_event(c);
-        cudaEventRecord(sp.a, c->stream);
+        cudaEventRecord(sp.a, stream);
     }
     ~PhaseScope() {
-        cudaEventRecord(sp.b, ctx->stream);
+        cudaEventRecord(sp.b, stream);
         ctx->spans.push_back(sp);
     }
 };
@@ -239,7 +245,10 @@ void free_query(imsame_ctx *ctx) {
     ctx->have_query = false;
 }
 void free_db(imsame_ctx *ctx) {
-    for (Seg &s : ctx->segs) { pool_free(ctx, s.pk); pool_free(ctx, s.start); pool_free(ctx, s.blk); pool_free(ctx, s.brk); }
+    for (Seg &s : ctx->segs) {
+        pool_free(ctx, s.pk); pool_free(ctx, s.start); pool_free(ctx, s.blk); pool_free(ctx, s.brk);
+        if (s.ready) cudaEventDestroy(s.ready);
+    }
     ctx->segs.clear();
     ctx->have_db = false;
 }
@@ -282,6 +291,7 @@ static bool host_is_pageable(const void *p) {
 }
 
 int upload_pack(imsame_ctx *ctx, const unsigned char *host, uint64_t n, uint32_t *pk, int ph_pack) {
+    cudaStream_t up = ctx->up_stream ? ctx->up_stream : ctx->stream;
     if (!ctx->stage) { int rc = dev_alloc(ctx, &ctx->stage, STAGE_BYTES); if (rc) return rc; }
     if (n >= 2 * PIN_BYTES && host_is_pageable(host)) {
         for (int b = 0; b < 2; b++)
@@ -302,17 +312,17 @@ int upload_pack(imsame_ctx *ctx, const unsigned char *host, uint64_t n, uint32_t
                 if (ctx->pin_busy[b]) CK(cudaEventSynchronize(ctx->pin_ev[b]));
                 par_memcpy(ctx->pin[b], host + at, len);
                 {
-                    PhaseScope ps(ctx, PH_H2D);
-                    CK(cudaMemcpyAsync(ctx->stage, ctx->pin[b], len, cudaMemcpyHostToDevice, ctx->stream));
-                    CK(cudaEventRecord(ctx->pin_ev[b], ctx->stream));
+                    PhaseScope ps(ctx, PH_H2D, up);
+                    CK(cudaMemcpyAsync(ctx->stage, ctx->pin[b], len, cudaMemcpyHostToDevice, up));
+                    CK(cudaEventRecord(ctx->pin_ev[b], up));
                     ctx->pin_busy[b] = true;
                     ctx->h2d_bytes += len;
                 }
                 {
-                    PhaseScope ps(ctx, ph_pack);
+                    PhaseScope ps(ctx, ph_pack, up);
                     const uint64_t words = (len + 15) / 16;
                     const int grid = (int)std::min<uint64_t>((words + 255) / 256, (uint64_t)ctx->n_sm * 16);
-                    pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->stage, len, pk + at / 16);
+                    pack_kernel<<<grid, 256, 0, up>>>(ctx->stage, len, pk + at / 16);
                     ctx->launches++;
                 }
             }
@@ -323,15 +333,15 @@ int upload_pack(imsame_ctx *ctx, const unsigned char *host, uint64_t n, uint32_t
     for (uint64_t at = 0; at < n; at += STAGE_BYTES) {
         const uint64_t len = std::min<uint64_t>(STAGE_BYTES, n - at);
         {
-            PhaseScope ps(ctx, PH_H2D);
-            CK(cudaMemcpyAsync(ctx->stage, host + at, len, cudaMemcpyHostToDevice, ctx->stream));
+            PhaseScope ps(ctx, PH_H2D, up);
+            CK(cudaMemcpyAsync(ctx->stage, host + at, len, cudaMemcpyHostToDevice, up));
             ctx->h2d_bytes += len;
         }
         {
-            PhaseScope ps(ctx, ph_pack);
+            PhaseScope ps(ctx, ph_pack, up);
             const uint64_t words = (len + 15) / 16;
             const int grid = (int)std::min<uint64_t>((words + 255) / 256, (uint64_t)ctx->n_sm * 16);
-            pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->stage, len, pk + at / 16);
+            pack_kernel<<<grid, 256, 0, up>>>(ctx->stage, len, pk + at / 16);
             ctx->launches++;
         }
     }
@@ -561,13 +571,9 @@ int imsame_gpu_create(imsame_ctx **out, int device) {
     imsame_ctx *ctx = new imsame_ctx();
     ctx->device = device;
     ctx->n_sm = prop.multiProcessorCount;
-    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-    if (getenv("IMSAME_NO_L2_PIN")) ctx->l2_pin = 0;
-    if (getenv("IMSAME_TRACE"))
-        fprintf(stderr, "[imsame] L2 %d B, persisting max %zu B, access window max %zu B\n", prop.l2CacheSize,
-                ctx->l2_persist_max, ctx->l2_window_max);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return IMSAME_ECUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->q_ready, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return IMSAME_ECUDA; }
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<K>, SCAN_THREADS_K2, 0);
     if (const char *e = getenv("IMSAME_SCAN_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));  // tuning knob
@@ -596,6 +602,8 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     dev_free(ctx->comm_flag);
     for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->q_ready) cudaEventDestroy(ctx->q_ready);
     delete ctx;
 }
 
@@ -648,8 +656,15 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
     int rc;
     const uint64_t words = ((uint64_t)total + 15) / 16 + PAD_WORDS;
     if ((rc = pool_alloc(ctx, &ctx->q_pk, words))) return rc;
-    CK(cudaMemsetAsync(ctx->q_pk, 0, words * 4, ctx->stream));
-    if ((rc = upload_pack(ctx, q->sequences, total, ctx->q_pk, PH_PACKQ))) return rc;
+    {
+        cudaStream_t up = ctx->up_stream ? ctx->up_stream : ctx->stream;
+        CK(cudaMemsetAsync(ctx->q_pk, 0, words * 4, up));
+        if ((rc = upload_pack(ctx, q->sequences, total, ctx->q_pk, PH_PACKQ))) return rc;
+        if (up != ctx->stream) {  // the query table is built on the main stream
+            CK(cudaEventRecord(ctx->q_ready, up));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->q_ready, 0));
+        }
+    }
     if (!ctx->q_fixed) {
         if ((rc = pool_alloc(ctx, &ctx->q_start, (uint64_t)nq + 1))) return rc;
         if ((rc = upload_u32(ctx, ctx->q_start, ctx->q_start_host.data(), (uint64_t)nq + 1))) return rc;
@@ -708,7 +723,13 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
 }
 
 // ---- database shard: upload + pack in segments of < 2^31 bases -------------------------------
-int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
+}  // extern "C"
+
+namespace {
+
+// segment boundaries, device buffers and the small per-segment arrays (read offsets of ragged reads, word
+// breaks); the bases themselves follow segment by segment (db_upload_seg)
+int db_layout(imsame_ctx *ctx, const imsame_seqinfo *db) {
     if (!ctx || !db || !db->sequences || !db->start_pos || db->n_seqs == 0) return IMSAME_EARG;
     if (db->n_seqs >= 0xFFFFFF00ull) return IMSAME_ELIMIT;
     cudaSetDevice(ctx->device);
@@ -745,9 +766,8 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
         int rc;
         const uint64_t words = ((uint64_t)s.total + 15) / 16 + PAD_WORDS;
         if ((rc = pool_alloc(ctx, &s.pk, words))) return rc;
+        if (cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming) != cudaSuccess) { pool_free(ctx, s.pk); return IMSAME_ECUDA; }
         ctx->segs.push_back(s);
-        CK(cudaMemsetAsync(s.pk + words - PAD_WORDS - 1, 0, (PAD_WORDS + 1) * 4, ctx->stream));
-        if ((rc = upload_pack(ctx, db->sequences + base, s.total, s.pk, PH_PACKDB))) return rc;
         Seg &ss = ctx->segs.back();
         if (!fixed) {
             tmp.resize((size_t)s.n + 1);
@@ -776,9 +796,33 @@ int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
         }
         r0 = r1;
     }
-    // the caller may refill or free its (pinned) host buffers as soon as this returns
-    CK(cudaStreamSynchronize(ctx->stream));
     ctx->have_db = true;
+    return IMSAME_OK;
+}
+
+// bases of one segment: H2D (staged) + 2-bit packing on the upload stream
+int db_upload_seg(imsame_ctx *ctx, const imsame_seqinfo *db, int seg) {
+    Seg &s = ctx->segs[(size_t)seg];
+    cudaStream_t up = ctx->up_stream ? ctx->up_stream : ctx->stream;
+    const uint64_t words = ((uint64_t)s.total + 15) / 16 + PAD_WORDS;
+    CK(cudaMemsetAsync(s.pk + words - PAD_WORDS - 1, 0, (PAD_WORDS + 1) * 4, up));
+    int rc = upload_pack(ctx, db->sequences + s.pos_base, s.total, s.pk, PH_PACKDB);
+    if (rc) return rc;
+    s.wait_ready = up != ctx->stream;
+    if (s.wait_ready) CK(cudaEventRecord(s.ready, up));
+    return IMSAME_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db) {
+    int rc = db_layout(ctx, db);
+    for (int seg = 0; seg < (int)ctx->segs.size() && !rc; seg++) rc = db_upload_seg(ctx, db, seg);
+    if (rc) { if (ctx) ctx->have_db = false; return rc; }
+    // the caller may refill or free its (pinned) host buffers as soon as this returns
+    CK(cudaStreamSynchronize(ctx->up_stream ? ctx->up_stream : ctx->stream));
     return IMSAME_OK;
 }
 
@@ -877,70 +921,46 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     return IMSAME_OK;
 }
 
-// K2 + K2b for one segment: scan, extend, collect candidates, sort them into (class, band) bins
-extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
-    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
-    cudaSetDevice(ctx->device);
-    const Seg &s = ctx->segs[seg];
+// K2 for one segment, asynchronously: scan, extend, collect the candidates in the pair table
+static int scan_launch(imsame_ctx *ctx, int seg) {
+    Seg &s = ctx->segs[(size_t)seg];
     const imsame_params *p = &ctx->run_params;
-    const SeqMap qm = query_map(ctx), dm = seg_map(s);
-    int rc;
     ctx->table_dirty = true;  // until bin_kernel<1> has emptied the table again (run_begin clears it otherwise)
-    // The extension gathers two 32-base windows per hit from random places of the packed query
-    // (cfg2: 62.5 MB, 3.4e10 hits), while the database, the bucket offsets (67 MB) and the word positions
-    // (956 MB) stream through the same 126 MB L2: keep the query resident (persisting access window),
-    // everything else on this stream is marked streaming.  Reset after the scan.
-    bool pinned = false;
-    if (ctx->l2_pin && !getenv("IMSAME_NO_L2_PIN") && ctx->l2_persist_max && ctx->l2_window_max) {
-        const size_t qbytes = ((size_t)ctx->q_total + 15) / 16 * 4;
-        const size_t win = std::min(qbytes, ctx->l2_window_max);
-        const size_t carve = std::min(win, ctx->l2_persist_max);
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof av);
-            av.accessPolicyWindow.base_ptr = (void *)ctx->q_pk;
-            av.accessPolicyWindow.num_bytes = win;
-            av.accessPolicyWindow.hitRatio = win ? (float)std::min(1.0, (double)carve / (double)win) : 0.f;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            pinned = cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
-        }
-        cudaGetLastError();
+    if (s.wait_ready) {       // the segment was uploaded on another stream (imsame_gpu_align)
+        CK(cudaStreamWaitEvent(ctx->stream, s.ready, 0));
+        s.wait_ready = false;
     }
-    struct Unpin {
-        imsame_ctx *c; bool on;
-        ~Unpin() {
-            if (!on) return;
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof av);
-            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-            cudaCtxResetPersistingL2Cache();
-            cudaGetLastError();
-        }
-    } unpin{ctx, pinned};
-    for (int attempt = 0; attempt < 8; attempt++) {
-        CK(cudaMemsetAsync(ctx->d_small, 0, 4 * sizeof(uint32_t), ctx->stream));
-        CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int), ctx->stream));
-        // counters of a failed attempt must not be kept: snapshot/restore is avoided by scanning into scratch
-        CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
-        {
-            PhaseScope ps(ctx, PH_K2);
-            ScanArgs a;
-            a.db = dm; a.q = qm; a.off = ctx->off; a.qtab = ctx->qtab; a.brk = s.brk; a.n_brk = s.n_brk;
-            a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
-            a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
-            a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;
-            a.k = ctx->q_k;
-            if (ctx->q_k == K) scan_kernel<K><<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
-            else scan_kernel<0><<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
-            ctx->launches++; ctx->k2_launches++;
-        }
+    CK(cudaMemsetAsync(ctx->d_small, 0, 4 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_overflow, 0, sizeof(int), ctx->stream));
+    // counters of a failed attempt must not be kept: snapshot/restore is avoided by scanning into scratch
+    CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    PhaseScope ps(ctx, PH_K2);
+    ScanArgs a;
+    a.db = seg_map(s); a.q = query_map(ctx); a.off = ctx->off; a.qtab = ctx->qtab; a.brk = s.brk; a.n_brk = s.n_brk;
+    a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
+    a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
+    a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;
+    a.k = ctx->q_k;
+    if (ctx->q_k == K) scan_kernel<K><<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
+    else scan_kernel<0><<<ctx->scan_grid, SCAN_THREADS_K2, 0, ctx->stream>>>(a);
+    ctx->launches++; ctx->k2_launches++;
+    CK(cudaGetLastError());
+    return IMSAME_OK;
+}
+
+// wait for the scan of the segment (re-running it with a larger pair table if that overflowed), then K2b: sort
+// the candidates into (class, band) bins
+static int scan_finish(imsame_ctx *ctx, int seg) {
+    const SeqMap qm = query_map(ctx);
+    int rc;
+    for (int attempt = 0;; attempt++) {
         int overflow = 0;
         CK(cudaMemcpyAsync(&overflow, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (!overflow) break;
         if (ctx->hcap >= (1u << 30) || attempt == 7) return IMSAME_ELIMIT;
         if ((rc = ensure_work_buffers(ctx, ctx->hcap * 2))) return rc;  // reallocates + clears the table
+        if ((rc = scan_launch(ctx, seg))) return rc;
     }
     uint32_t *bins = ctx->d_bins + (size_t)seg * BINS_STRIDE;
     uint32_t *bin_count = bins, *bin_off = bins + NW_NBINS, *launch_range = bins + 4 * NW_NBINS + 4;
@@ -978,6 +998,13 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
     CK(cudaGetLastError());
     ctx->table_dirty = false;
     return IMSAME_OK;
+}
+
+extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
+    cudaSetDevice(ctx->device);
+    int rc = scan_launch(ctx, seg);
+    return rc ? rc : scan_finish(ctx, seg);
 }
 
 // K3 for one band of one segment (every NW class present in the query)
@@ -1141,29 +1168,55 @@ int imsame_gpu_fetch(imsame_ctx *ctx, const uint64_t *d_keys, const uint64_t *d_
     return IMSAME_OK;
 }
 
+// One call = index build (src/IMSAME.c:232-281) + thread fan-out (:409-467).  The uploads run on a stream of
+// their own, one database segment ahead of the scan: H2D + packing of segment s+1 overlap K2 of segment s
+// (the reference reads and indexes its whole database before the first alignment starts,
+// src/IMSAME.c:196-289).
+static int align_pipelined(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
+                           const imsame_params *p, imsame_stats *local) {
+    int rc;
+    if ((rc = imsame_gpu_set_query(ctx, query, p))) return rc;
+    if ((rc = db_layout(ctx, db))) return rc;
+    if ((rc = imsame_gpu_run_begin(ctx, p, nullptr, nullptr))) return rc;
+    const int nseg = (int)ctx->segs.size();
+    if ((rc = db_upload_seg(ctx, db, 0))) return rc;
+    for (int seg = 0; seg < nseg; seg++) {
+        if ((rc = scan_launch(ctx, seg))) return rc;
+        // issued while the scan runs; pageable input keeps the host busy here (pinned bounce buffers)
+        if (seg + 1 < nseg && (rc = db_upload_seg(ctx, db, seg + 1))) return rc;
+        if ((rc = scan_finish(ctx, seg))) return rc;
+    }
+    for (int band = 0; band < NW_BANDS; band++)
+        for (int seg = 0; seg < nseg; seg++)
+            if ((rc = imsame_gpu_run_band(ctx, seg, band))) return rc;
+    for (int seg = 0; seg < nseg; seg++)
+        if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
+    return imsame_gpu_run_end(ctx, local);
+}
+
 int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
                      const imsame_params *p, imsame_best *out, imsame_stats *st) {
     if (!ctx || !db || !query || !p || !out) return IMSAME_EARG;
+    cudaSetDevice(ctx->device);
     reset_timing(ctx);
-    int rc;
     const bool trace = getenv("IMSAME_TRACE") != nullptr;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
-    if ((rc = imsame_gpu_set_query(ctx, query, p))) return rc;
-    const double t1 = now();
-    if ((rc = imsame_gpu_set_db(ctx, db))) return rc;
-    const double t2 = now();
     imsame_stats local;
     memset(&local, 0, sizeof(local));
     ctx->in_align = true;
-    rc = run_impl(ctx, p, nullptr, nullptr, &local);
+    ctx->up_stream = ctx->copy_stream;
+    int rc = align_pipelined(ctx, db, query, p, &local);
+    ctx->up_stream = nullptr;
     ctx->in_align = false;
-    if (rc) return rc;
+    ctx->run_active = false;
+    // nothing of the caller's buffers is in flight when this returns, whatever happened
+    cudaStreamSynchronize(ctx->copy_stream);
+    for (Seg &s : ctx->segs) s.wait_ready = false;
+    if (rc) { ctx->have_db = false; return rc; }
     const double t3 = now();
     if ((rc = imsame_gpu_fetch(ctx, nullptr, nullptr, out))) return rc;
-    if (trace)
-        fprintf(stderr, "[imsame] host wall ms: set_query %.1f  set_db %.1f  run %.1f  fetch %.1f\n", t1 - t0, t2 - t1, t3 - t2,
-                now() - t3);
+    if (trace) fprintf(stderr, "[imsame] host wall ms: upload + table + scan + NW %.1f  fetch %.1f\n", t3 - t0, now() - t3);
     uint64_t acc = 0;
     for (uint32_t r = 0; r < ctx->nq; r++) acc += out[r].accepted;
     if (st) {

@@ -219,10 +219,17 @@ IMS_HD void ext_step(const uint32_t *lut, uint32_t mm, int c, int &run, int &bes
 // from the mask byte and the row, one 64-bit shared load, one fused add-maximum, one add -- at the price of
 // twice the table bytes per lookup; the kernel is bound by instruction issue (round 2 profile), not by the
 // shared-memory pipe.
+// Shared-memory banks: mismatch bits are 1 three times out of four, so the low bits of a mask byte are mostly
+// 1111 and a warp's 32 lookups crowded into a few banks (9.6 wavefronts per lookup measured).  The ExtXY table
+// is therefore indexed by the FOLDED byte  b ^ (b >> 4)  (a bijection on 0..255; the XOR of two biased bits is
+// nearly fair), applied to all four bytes of a mask at once (ext_prep).
 struct ExtXY {
     int x;   // ((maximum prefix score + 1) << 15) + step of its last occurrence
     int yd;  // (score change << 15) + steps executed
 };
+IMS_HD uint32_t ext_fold8(uint32_t b) { return (b ^ (b >> 4)) & 0xFFu; }
+IMS_HD uint32_t ext_prep(const ExtXY *, uint32_t mm) { return mm ^ ((mm >> 4) & 0x0F0F0F0Fu); }
+IMS_HD uint32_t ext_prep(const uint32_t *, uint32_t mm) { return mm; }
 IMS_HD ExtXY ext_xy_of(uint32_t e) {
     ExtXY v;
     v.x = (int)(funnel_r(e, e, 8) & EXT_X_MASK);
@@ -267,6 +274,7 @@ IMS_HD void ext_window(ExtState &s, const LUT *lut, const uint32_t *dpk, const u
     if (rem < 32) mm |= 0xFFFFFFFFu << rem;      // steps past the read end: mismatches (change neither maximum nor matches)
     int run = s.run, best = s.best;
     const int sc0 = run >> EXT_SC_SHIFT;
+    mm = ext_prep(lut, mm);
 #pragma unroll
     for (int c = 0; c < 32; c += 8) ext_step(lut, mm, c, run, best);
     const int sc1 = run >> EXT_SC_SHIFT;
@@ -362,6 +370,7 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const LUT *lut, uint32_t mfa,
                        uint32_t mbb, int K = imsame::K) {
     const int k0 = K << EXT_SC_SHIFT, kb = k0 + EXT_BEST_BIAS;
     int ra = k0, ba = kb, rb = k0, bb = kb;
+    mfa = ext_prep(lut, mfa); mba = ext_prep(lut, mba); mfb = ext_prep(lut, mfb); mbb = ext_prep(lut, mbb);
 #pragma unroll
     for (int c = 0; c < 32; c += 8) {
         ext_step(lut, mfa, c, ra, ba);

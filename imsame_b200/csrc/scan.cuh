@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
     __shared__ uint2 s_wb[SCAN_WARPS][32];       // database backward window
     __shared__ int2 s_room[SCAN_WARPS][32];      // steps left inside the database read: forward, backward
     __shared__ __align__(8) ExtXY s_lut[EXT_LUT3_SIZE];
-    for (int i = threadIdx.x; i < EXT_LUT3_SIZE; i += SCAN_THREADS_K2) s_lut[i] = ext_xy_of(a.lut[i]);
+    for (int i = threadIdx.x; i < EXT_LUT3_SIZE; i += SCAN_THREADS_K2)
+        s_lut[(i & ~0xFF) | (int)ext_fold8((uint32_t)i & 0xFFu)] = ext_xy_of(a.lut[i]);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);

@@ -59,7 +59,7 @@ int main(int argc, char **argv) {
     std::vector<uint32_t> lut2(EXT_LUT3_SIZE);
     build_ext_lut3(lut2.data());
     std::vector<ExtXY> lutxy(EXT_LUT3_SIZE);  // the scan kernel's shared-memory form of the same table
-    for (int i = 0; i < EXT_LUT3_SIZE; i++) lutxy[i] = ext_xy_of(lut2[i]);
+    for (int i = 0; i < EXT_LUT3_SIZE; i++) lutxy[(i & ~0xFF) | (int)ext_fold8((uint32_t)i & 0xFFu)] = ext_xy_of(lut2[i]);
     // window_mismatch (32-bit halves) against the 64-bit form
     for (size_t i = 0; i + 40 < D.size() && i + 40 < Q.size(); i += 3) {
         size_t j = (i * 7 + 5) % (Q.size() - 40);
