@@ -35,6 +35,7 @@ struct Seg {
     uint32_t *pk = nullptr, *start = nullptr, *blk = nullptr, *brk = nullptr;
     cudaEvent_t ready = nullptr;  // bases uploaded and packed (recorded on the upload stream)
     bool wait_ready = false;      // the scan has to wait for `ready` (uploaded on another stream)
+    bool borrowed = false;        // the buffers belong to an imsame_sample
 };
 
 enum Phase { PH_PACKQ, PH_K1, PH_PACKDB, PH_K2, PH_K2B, PH_K3, PH_SELECT, PH_H2D, PH_D2H, PH_COMM, PH_COUNT };
@@ -59,7 +60,9 @@ struct imsame_ctx {
     uint32_t class_mask = 0;
     std::vector<uint32_t> q_start_host;
     uint32_t *off = nullptr, *cursor = nullptr, *tile_sums = nullptr;
+    uint32_t *off_own = nullptr;  // the context's own offsets table (`off` may point into a resident sample instead)
     QEntry *qtab = nullptr;  // query word table entries, bucket by bucket (qtable.cuh)
+    bool q_borrowed = false;  // the query buffers and its word table belong to an imsame_sample
     uint64_t n_qwords = 0;
     uint64_t q_threads = 0;
     bool have_query = false;
@@ -240,13 +243,20 @@ void pool_destroy(imsame_ctx *ctx) {
 }
 
 void free_query(imsame_ctx *ctx) {
-    pool_free(ctx, ctx->q_pk); pool_free(ctx, ctx->q_start); pool_free(ctx, ctx->q_blk);
-    pool_free(ctx, ctx->qtab);
+    if (ctx->q_borrowed) {
+        ctx->q_pk = ctx->q_start = ctx->q_blk = nullptr;
+        ctx->qtab = nullptr;
+        ctx->off = ctx->off_own;
+        ctx->q_borrowed = false;
+    } else {
+        pool_free(ctx, ctx->q_pk); pool_free(ctx, ctx->q_start); pool_free(ctx, ctx->q_blk);
+        pool_free(ctx, ctx->qtab);
+    }
     ctx->have_query = false;
 }
 void free_db(imsame_ctx *ctx) {
     for (Seg &s : ctx->segs) {
-        pool_free(ctx, s.pk); pool_free(ctx, s.start); pool_free(ctx, s.blk); pool_free(ctx, s.brk);
+        if (!s.borrowed) { pool_free(ctx, s.pk); pool_free(ctx, s.start); pool_free(ctx, s.blk); pool_free(ctx, s.brk); }
         if (s.ready) cudaEventDestroy(s.ready);
     }
     ctx->segs.clear();
@@ -538,6 +548,66 @@ void fill_stats(imsame_ctx *ctx, imsame_stats *st, const unsigned long long *cnt
 
 }  // namespace
 
+// K1 over the resident packed query (ctx->q_pk ...): histogram of the words, exclusive scan, scatter of the
+// table entries.  off_dst / qtab_out: build into a resident sample's own offsets table and hand the entries
+// (plain allocation) to the caller; nullptr: the context's own table and the recycled pool.
+static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_out) {
+    int rc;
+    const uint32_t nq = ctx->nq, total = ctx->q_total;
+    const uint64_t ncodes = ncodes_of(ctx->k);
+    const uint32_t n_tiles = (uint32_t)((ncodes + SCAN_TILE - 1) / SCAN_TILE);
+    if (ctx->k_tables != ctx->k) {
+        dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
+        ctx->off_own = ctx->cursor = ctx->tile_sums = nullptr;
+        ctx->k_tables = 0;
+        if ((rc = dev_alloc(ctx, &ctx->off_own, (uint64_t)ncodes + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->cursor, (uint64_t)ncodes + 1))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->tile_sums, (uint64_t)n_tiles + 1))) return rc;
+        ctx->k_tables = ctx->k;
+    }
+    ctx->off = off_dst ? off_dst : ctx->off_own;
+    QTableArgs a;
+    a.k = ctx->k;
+    a.q.pk = ctx->q_pk; a.q.start = ctx->q_start; a.q.blk = ctx->q_blk; a.q.n = nq; a.q.total = total;
+    a.q.fixed_len = ctx->q_fixed;
+    a.n_threads = (uint32_t)std::min<uint64_t>(ctx->q_threads, 0xFFFFFFFFull);
+    a.per = (uint32_t)(nq / ctx->q_threads);  // floorl(n_seqs / n_threads), src/IMSAME.c:414
+    a.cnt = ctx->cursor;
+    a.qtab = nullptr;
+    const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
+    uint32_t n_words = 0;
+    {
+        PhaseScope ps(ctx, PH_K1);
+        CK(cudaMemsetAsync(ctx->cursor, 0, ((size_t)ncodes + 1) * 4, ctx->stream));
+        qtable_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
+        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
+        scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, n_tiles);
+        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
+        ctx->launches += 4;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(&n_words, ctx->off + ncodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_qwords = n_words;
+    if (qtab_out) {
+        if ((rc = dev_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) return rc;
+        *qtab_out = ctx->qtab;
+    } else if ((rc = pool_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) {
+        return rc;
+    }
+    {
+        PhaseScope ps(ctx, PH_K1);
+        CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        a.qtab = ctx->qtab;
+        qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->q_k = ctx->k;
+    ctx->have_query = true;
+    return IMSAME_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 extern "C" {
 
@@ -589,7 +659,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     free_query(ctx);
     free_db(ctx);
     pool_destroy(ctx);
-    dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
+    dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
     dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
@@ -674,52 +744,7 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
         blk_kernel<<<std::min<uint32_t>((nq + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ctx->q_start, nq, ctx->q_blk);
         ctx->launches++;
     }
-    const uint64_t ncodes = ncodes_of(ctx->k);
-    const uint32_t n_tiles = (uint32_t)((ncodes + SCAN_TILE - 1) / SCAN_TILE);
-    if (ctx->k_tables != ctx->k) {
-        dev_free(ctx->off); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
-        ctx->off = ctx->cursor = ctx->tile_sums = nullptr;
-        ctx->k_tables = 0;
-        if ((rc = dev_alloc(ctx, &ctx->off, (uint64_t)ncodes + 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->cursor, (uint64_t)ncodes + 1))) return rc;
-        if ((rc = dev_alloc(ctx, &ctx->tile_sums, (uint64_t)n_tiles + 1))) return rc;
-        ctx->k_tables = ctx->k;
-    }
-    QTableArgs a;
-    a.k = ctx->k;
-    a.q.pk = ctx->q_pk; a.q.start = ctx->q_start; a.q.blk = ctx->q_blk; a.q.n = nq; a.q.total = total;
-    a.q.fixed_len = ctx->q_fixed;
-    a.n_threads = (uint32_t)std::min<uint64_t>(ctx->q_threads, 0xFFFFFFFFull);
-    a.per = (uint32_t)(nq / ctx->q_threads);  // floorl(n_seqs / n_threads), src/IMSAME.c:414
-    a.cnt = ctx->cursor;
-    a.qtab = nullptr;
-    const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
-    uint32_t n_words = 0;
-    {
-        PhaseScope ps(ctx, PH_K1);
-        CK(cudaMemsetAsync(ctx->cursor, 0, ((size_t)ncodes + 1) * 4, ctx->stream));
-        qtable_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
-        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
-        scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, n_tiles);
-        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
-        ctx->launches += 4;
-        CK(cudaGetLastError());
-    }
-    CK(cudaMemcpyAsync(&n_words, ctx->off + ncodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_qwords = n_words;
-    if ((rc = pool_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) return rc;
-    {
-        PhaseScope ps(ctx, PH_K1);
-        CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        a.qtab = ctx->qtab;
-        qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
-        ctx->launches++;
-        CK(cudaGetLastError());
-    }
-    ctx->q_k = ctx->k;
-    ctx->have_query = true;
-    return IMSAME_OK;
+    return build_query_table(ctx, nullptr, nullptr);
 }
 
 // ---- database shard: upload + pack in segments of < 2^31 bases -------------------------------
