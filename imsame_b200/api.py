@@ -64,6 +64,7 @@ SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "im
            "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode",
            "imsame_gpu_set_kmer", "imsame_gpu_comm_id", "imsame_gpu_comm_init", "imsame_gpu_comm_free",
            "imsame_gpu_run_sharded", "imsame_gpu_align_sharded",
+           "imsame_gpu_sample_create", "imsame_gpu_sample_revcomp", "imsame_gpu_sample_free", "imsame_gpu_align_samples",
            "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
 _lib = None
@@ -117,6 +118,11 @@ def lib():
         l.imsame_gpu_run_sharded.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, C.POINTER(Stats)]
         l.imsame_gpu_align_sharded.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(SeqInfo), C.POINTER(SeqInfo),
                                                C.POINTER(Params), vp, C.POINTER(Stats)]
+        l.imsame_gpu_sample_create.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(vp)]
+        l.imsame_gpu_sample_revcomp.argtypes = [vp, vp, C.POINTER(vp)]
+        l.imsame_gpu_sample_free.argtypes = [vp, vp]
+        l.imsame_gpu_sample_free.restype = None
+        l.imsame_gpu_align_samples.argtypes = [vp, vp, vp, C.POINTER(Params), vp, C.POINTER(Stats)]
         l.imsame_gpu_free.argtypes = [vp]
         l.imsame_gpu_free.restype = None
         l.imsame_gpu_host_alloc.argtypes = [u64]
@@ -283,6 +289,28 @@ class Imsame:
         self._check(L.imsame_gpu_run_end(self._h, C.byref(st)))
         return st.as_dict()
 
+    # -- read sets resident on the device (all-vs-all)
+    def sample(self, reads, breaks=None):
+        """upload + pack once; returns a handle usable as database or query of align_samples"""
+        d, keep = _seqinfo(reads[0], reads[1], breaks)
+        h = C.c_void_p()
+        self._check(lib().imsame_gpu_sample_create(self._h, C.byref(d), C.byref(h)))
+        return Sample(self, h, int(d.n_seqs))
+
+    def sample_revcomp(self, sample):
+        """reverse complement on the device, records in reverse order (what revComp writes)"""
+        h = C.c_void_p()
+        self._check(lib().imsame_gpu_sample_revcomp(self._h, sample._h, C.byref(h)))
+        return Sample(self, h, sample.n)
+
+    def align_samples(self, db, query, params=None):
+        params = params or make_params()
+        out = np.zeros(query.n, dtype=BEST_DTYPE)
+        st = Stats()
+        self._check(lib().imsame_gpu_align_samples(self._h, db._h, query._h, C.byref(params), out.ctypes.data, C.byref(st)))
+        self.nq = query.n
+        return out, st.as_dict()
+
     # -- database sharded over several GPUs, reduced by NCCL inside the library
     def comm_init(self, comm_id, n_ranks, rank):
         """join the communicator named by the 128 bytes rank 0 obtained from comm_id()"""
@@ -349,6 +377,18 @@ class Imsame:
                                               C.cast(yp, C.c_void_p), yl.ctypes.data, -int(igap), -int(egap),
                                               out.ctypes.data, C.byref(ms)))
         return out, ms.value
+
+
+class Sample:
+    """a read set resident on the device (imsame_gpu_sample_*)"""
+
+    def __init__(self, ctx, handle, n):
+        self.ctx, self._h, self.n = ctx, handle, n
+
+    def free(self):
+        if self._h:
+            lib().imsame_gpu_sample_free(self.ctx._h, self._h)
+            self._h = C.c_void_p()
 
 
 COMM_ID_BYTES = 128

@@ -1496,3 +1496,4 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
 }  // extern "C"
 
 #include "capi_sharded.inc"
+#include "capi_samples.inc"

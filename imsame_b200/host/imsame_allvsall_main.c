@@ -4,8 +4,11 @@
  * what the script produces with the drop-in IMSAME and revComp), same resume rule (existing outputs
  * are kept) -- but every sample is parsed once, its reverse complement (src/reverseComplement.c, incl.
  * the reversed record order that renumbers db_seq) is built in memory instead of a temporary Y.r.EXT
- * file, and all 2 * n(n-1)/2 comparisons share one CUDA context and its device buffers.  The script
- * starts 56 IMSAME and 28 revComp processes for 8 samples and re-parses every file 14 times.
+ * file, and all 2 * n(n-1)/2 comparisons share one CUDA context.  Every sample is also uploaded and packed
+ * ONCE (imsame_gpu_sample_create): it stays on the device as the database of later comparisons, keeps the word
+ * table built for it as a query, and its reverse complement is made on the device from the packed form
+ * (imsame_gpu_sample_revcomp).  The script starts 56 IMSAME and 28 revComp processes for 8 samples and
+ * re-parses every file 14 times.
  *
  * usage: IMSAME_allvsall metagenomes_directory coverage similarity threads file_extension outpath [-device D]
  */
@@ -36,8 +39,11 @@ static double now_s(void) {
 
 typedef struct {
     char *name;            /* file name without ".EXT" */
-    imsame_fasta fwd, rev; /* parsed forward sample / parsed revComp(sample) */
+    imsame_fasta fwd, rev; /* parsed forward sample / parsed revComp(sample): what the records are rendered from */
     int have_fwd, have_rev;
+    imsame_sample *dfwd, *drev; /* the same two read sets resident on the device */
+    int has_u;                  /* the file contains a 'U': revComp turns it into an 'A' the loader keeps, so the
+                                   reverse complement has to be uploaded from the text form */
 } sample;
 
 static int by_name(const void *a, const void *b) { return strcoll(((const sample *)a)->name, ((const sample *)b)->name); }
@@ -61,6 +67,7 @@ static void need_reverse(sample *s, const char *dir, const char *ext) {
     snprintf(path, sizeof path, "%s/%s.%s", dir, s->name, ext);
     imsame_file_image img;
     if (imsame_file_map(path, &img)) terror("opening IN sequence FASTA file");
+    s->has_u = memchr(img.data, 'U', img.len) != NULL || memchr(img.data, 'u', img.len) != NULL;
     unsigned char *rc = NULL;
     size_t rc_len = 0;
     if (imsame_revcomp_mem(img.data, img.len, &rc, &rc_len)) terror("memory for Seq");
@@ -68,6 +75,35 @@ static void need_reverse(sample *s, const char *dir, const char *ext) {
     if (imsame_fasta_parse_mem(rc, rc_len, 1, &s->rev)) terror("Could not allocate memory for database vector");
     free(rc);
     s->have_rev = 1;
+}
+
+static void gpu_fail(const char *what, int rc, imsame_ctx *ctx) {
+    char msg[512];
+    snprintf(msg, sizeof msg, "%s: %s / %s", what, imsame_gpu_strerror(rc), ctx ? imsame_gpu_last_cuda_error(ctx) : "");
+    terror(msg);
+}
+
+/* the device copies (lazily, once per sample) */
+static void need_forward_dev(sample *s, imsame_ctx *ctx) {
+    if (s->dfwd) return;
+    imsame_seqinfo v;
+    imsame_fasta_view(&s->fwd, &v);
+    const int rc = imsame_gpu_sample_create(ctx, &v, &s->dfwd);
+    if (rc) gpu_fail("uploading a sample", rc, ctx);
+}
+
+static void need_reverse_dev(sample *s, imsame_ctx *ctx) {
+    if (s->drev) return;
+    int rc;
+    if (s->has_u || !s->have_fwd) {
+        imsame_seqinfo v;
+        imsame_fasta_view(&s->rev, &v);
+        rc = imsame_gpu_sample_create(ctx, &v, &s->drev);
+    } else {
+        need_forward_dev(s, ctx);
+        rc = imsame_gpu_sample_revcomp(ctx, s->dfwd, &s->drev);
+    }
+    if (rc) gpu_fail("reverse complement of a sample", rc, ctx);
 }
 
 int main(int argc, char **av) {
@@ -124,6 +160,21 @@ int main(int argc, char **av) {
                 need_forward(&sm[i], dir, ext);
                 if (rev) need_reverse(&sm[j], dir, ext); else need_forward(&sm[j], dir, ext);
                 const imsame_fasta *q = &sm[i].fwd, *db = rev ? &sm[j].rev : &sm[j].fwd;
+                if (q->n_seqs > 0 && db->n_seqs > 0 && !getenv("IMSAME_NO_RESIDENT")) {
+                    if (!ctx) {
+                        const int crc = imsame_gpu_create(&ctx, jo.device);
+                        if (crc) gpu_fail("no usable GPU", crc, NULL);
+                    }
+                    if (rev && !sm[j].have_fwd) need_forward(&sm[j], dir, ext);
+                    need_forward_dev(&sm[i], ctx);
+                    if (rev) need_reverse_dev(&sm[j], ctx); else need_forward_dev(&sm[j], ctx);
+                    jo.q_sample = sm[i].dfwd;
+                    jo.db_sample = rev ? sm[j].drev : sm[j].dfwd;
+                    if ((rev ? db->total_len : db->total_len) > (1ull << 29)) jo.q_sample = NULL, jo.db_sample = NULL; /* > one segment */
+                } else {
+                    jo.q_sample = NULL;
+                    jo.db_sample = NULL;
+                }
                 FILE *fout = fopen(path, "wt");
                 const double t0 = now_s();
                 uint64_t accepted = 0;
@@ -145,6 +196,10 @@ int main(int argc, char **av) {
                 fflush(stdout);
             }
     fprintf(stdout, "[INFO] %" PRIu64 " comparisons of %zu samples in %.3f s\n", jobs, n, now_s() - t_all);
+    for (size_t i = 0; i < n; i++) {
+        imsame_gpu_sample_free(ctx, sm[i].dfwd);
+        imsame_gpu_sample_free(ctx, sm[i].drev);
+    }
     if (ctx) imsame_gpu_destroy(ctx);
     for (size_t i = 0; i < n; i++) {
         if (sm[i].have_fwd) imsame_fasta_free(&sm[i].fwd);

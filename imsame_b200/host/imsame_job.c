@@ -62,7 +62,10 @@ int imsame_run_job(const imsame_fasta *qf, const imsame_fasta *dbf, const imsame
         if (!ctx && (rc = imsame_gpu_create(&ctx, o->device))) { free(best); return rc; }
         if (ctx_cache) *ctx_cache = ctx;
         rc = imsame_gpu_set_kmer(ctx, kmer);
-        if (!rc) rc = imsame_gpu_align(ctx, &dv, &qv, &p, best, NULL);
+        if (!rc) {
+            if (o->q_sample && o->db_sample) rc = imsame_gpu_align_samples(ctx, o->db_sample, o->q_sample, &p, best, NULL);
+            else rc = imsame_gpu_align(ctx, &dv, &qv, &p, best, NULL);
+        }
         if (rc && err && errlen) snprintf(err, errlen, "%s", imsame_gpu_last_cuda_error(ctx));
     } else {
         /* the database sharded by contiguous read ranges over ng GPUs; the per-read first accepted hit is

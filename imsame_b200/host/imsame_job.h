@@ -16,6 +16,10 @@ typedef struct imsame_job_opts {
     int gpus, device;
     int trace; /* phase wall times on stderr */
     int kmer;  /* seed length, 0 = the reference's FIXED_K (12) */
+    /* optional (gpus == 1): the two read sets already resident on the device (imsame_gpu_sample_*); the host
+       copies q / db are still what the records are rendered from */
+    imsame_sample *q_sample;
+    const imsame_sample *db_sample;
 } imsame_job_opts;
 
 /* Aligns every read of q against db and writes the records of the accepted reads to fout (may be

@@ -205,6 +205,26 @@ int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode);
  * (134 MB at k = 12, 34 GB at k = 16). */
 int imsame_gpu_set_kmer(imsame_ctx *ctx, int k);
 
+/* ---- read sets resident on the device (all-vs-all) ------------------------
+ * bin/all_vs_all_metagenomes_IMSAME.sh:27-58 runs IMSAME once per ordered pair of samples and once
+ * more against the reverse complement (revComp, src/reverseComplement.c): every sample is parsed,
+ * indexed or scanned 14 times.  A sample is uploaded and packed ONCE here, serves as the database
+ * of any number of comparisons, and keeps the word table built for it as a query.  Its reverse
+ * complement is made on the device from the packed form: revComp writes the records in reverse order
+ * (src/reverseComplement.c:56) and reverses each one, which together is the whole concatenated array
+ * reversed and complemented; start offsets and word breaks are mirrored.  (Letters other than
+ * A/C/G/T/U are dropped by the loader either way; a sample containing U must be reverse-complemented
+ * as text instead, because revComp turns U into A, which the loader keeps.)
+ * A sample used as a database must fit one segment (2^29 bases, IMSAME_ELIMIT otherwise). */
+typedef struct imsame_sample imsame_sample;
+int imsame_gpu_sample_create(imsame_ctx *ctx, const imsame_seqinfo *reads, imsame_sample **out);
+int imsame_gpu_sample_revcomp(imsame_ctx *ctx, const imsame_sample *in, imsame_sample **out);
+void imsame_gpu_sample_free(imsame_ctx *ctx, imsame_sample *s);
+/* imsame_gpu_align with both read sets resident (same results).  The query's word table is built on
+ * first use for (seed length, params->n_threads) and kept in the sample. */
+int imsame_gpu_align_samples(imsame_ctx *ctx, const imsame_sample *db, imsame_sample *query,
+                             const imsame_params *params, imsame_best *out, imsame_stats *stats);
+
 /* ---- winners-only traceback (src/alignmentFunctions.c:493-546) ---------- */
 /* For each accepted read of `best`, NW is recomputed on the device with one
  * back-pointer code per cell and walked back from the best border cell.  The

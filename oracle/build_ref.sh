@@ -15,4 +15,8 @@ gcc -O3 -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE -w -DVERBOSE \
     "$REF/alignmentFunctions.c" "$REF/commonFunctions.c" "$REF/IMSAME.c" -lpthread -lm -o "$HERE/_ref/IMSAME"
 gcc -O3 -D_FILE_OFFSET_BITS=64 -D_LARGEFILE64_SOURCE -w \
     "$REF/commonFunctions.c" "$REF/reverseComplement.c" -o "$HERE/_ref/revComp"
+# the reference's own workflow script, unmodified, next to the reference binaries it calls through its BINDIR
+# (bin/all_vs_all_metagenomes_IMSAME.sh:10): used by tools/allvsall_bench.py --reference (cfg4 baseline)
+cp "$REF/../bin/all_vs_all_metagenomes_IMSAME.sh" "$HERE/_ref/all_vs_all_metagenomes_IMSAME.sh"
+chmod +x "$HERE/_ref/all_vs_all_metagenomes_IMSAME.sh"
 echo "build_ref: built $HERE/_ref/IMSAME and revComp"

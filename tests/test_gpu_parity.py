@@ -299,6 +299,57 @@ def test_cfg2_shaped_properties_at_scale(gpu):
         assert np.array_equal(np.where(m_acc, merged, 0), np.where(acc, whole[f], 0)), f
 
 
+def _revcomp_reads(seq, start):
+    """what revComp (src/reverseComplement.c:56-112) + the loader give for A/C/G/T-only reads: records in reverse
+    order, each reverse-complemented = the whole concatenated array reversed and complemented"""
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    total = len(seq)
+    return comp[seq[::-1]].copy(), (total - np.asarray(start, dtype=np.int64)[::-1]).astype(np.uint64)
+
+
+def test_resident_samples_and_device_revcomp(gpu):
+    """read sets uploaded once (imsame_gpu_sample_*), word table kept in the query sample,
+    reverse complement made on the device from the packed form -- same records as imsame_gpu_align on host
+    buffers and as the oracle; fixed-length and ragged reads with word breaks; 16-base word boundaries"""
+    from imsame_b200 import api
+    cases = [sc.fixed_case(88, 3, 40000, 150, 6000, 700, 0.04),
+             sc.ragged_case(89, 3, 40000, 5000, 500, 0.05, lo=20, hi=300),
+             sc.fixed_case(90, 2, 20000, 61, 3000, 400, 0.03)]  # total % 16 != 0
+    p = api.make_params(n_threads=4)
+    for ci, (db, ds, q, qs) in enumerate(cases):
+        brk = None
+        if ci == 1:
+            rng = np.random.default_rng(5)
+            brk = np.unique(rng.integers(1, len(db), size=600)).astype(np.uint64)
+            brk = np.array([b for b in brk if b not in set(ds.tolist())], dtype=np.uint64)
+        rdb, rds = _revcomp_reads(db, ds)
+        rbrk = None if brk is None else np.sort(len(db) - brk.astype(np.int64)).astype(np.uint64)
+        S_db, S_q = gpu.sample((db, ds), brk), gpu.sample((q, qs))
+        S_rev = gpu.sample_revcomp(S_db)
+        try:
+            for _ in range(2):  # the second round reuses the word table kept in the query sample
+                out, st = gpu.align_samples(S_db, S_q, p)
+                want, _ = oracle_records(db, ds, q, qs, 4, breaks=brk)
+                assert gpu_records(out) == want and len(want) > 100
+                out_r, _ = gpu.align_samples(S_rev, S_q, p)
+                host_r, _ = gpu.align((rdb, rds), (q, qs), p, db_breaks=rbrk)
+                assert gpu_records(out_r) == gpu_records(host_r)
+                want_r, _ = oracle_records(rdb, rds, q, qs, 4, breaks=rbrk)
+                assert gpu_records(out_r) == want_r
+            # a sample is also a query: the database sample against itself finds every read
+            self_out, _ = gpu.align_samples(S_db, S_db, p)
+            assert int(self_out["accepted"].sum()) > 0.95 * (len(ds) - 1)
+        finally:
+            for s_ in (S_db, S_q, S_rev):
+                s_.free()
+    # the context is still usable with host buffers afterwards
+    db, ds, q, qs = cases[0]
+    out, _ = gpu.align((db, ds), (q, qs), p)
+    assert gpu_records(out) == oracle_records(db, ds, q, qs, 4)[0]
+
+
 def _sampled_check(rec, db, ds, q, qs, reads, db_total_global=0, **kw):
     p = hp.default_params(n_threads=4, db_total_len_global=db_total_global, **kw)
     want, st = hp.oracle_align_sampled(hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs), p, reads)
