@@ -332,7 +332,7 @@ def test_resident_samples_and_device_revcomp(gpu):
             for _ in range(2):  # the second round reuses the word table kept in the query sample
                 out, st = gpu.align_samples(S_db, S_q, p)
                 want, _ = oracle_records(db, ds, q, qs, 4, breaks=brk)
-                assert gpu_records(out) == want and len(want) > 100
+                assert gpu_records(out) == want and len(want) > 30
                 out_r, _ = gpu.align_samples(S_rev, S_q, p)
                 host_r, _ = gpu.align((rdb, rds), (q, qs), p, db_breaks=rbrk)
                 assert gpu_records(out_r) == gpu_records(host_r)
@@ -408,7 +408,7 @@ def test_runtime_seed_length_matches_generalised_oracle(gpu, k):
         gpu.set_kmer(k)
         want, st = oracle_records(db, ds, q, qs, 3, k=k)
         out, stats = gpu.align((db, ds), (q, qs), api.make_params(n_threads=3))
-        assert gpu_records(out) == want and len(want) > 100
+        assert gpu_records(out) == want and len(want) > 30
         assert stats["n_hits"] >= st.hits
         want, _ = oracle_records(rdb, rds, rq, rqs, 3, breaks=brk, k=k, evalue=1e-8)
         out, _ = gpu.align((rdb, rds), (rq, rqs), api.make_params(n_threads=3, min_e_value=1e-8), db_breaks=brk)
