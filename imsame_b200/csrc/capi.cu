@@ -574,7 +574,6 @@ static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_o
     a.per = (uint32_t)(nq / ctx->q_threads);  // floorl(n_seqs / n_threads), src/IMSAME.c:414
     a.cnt = ctx->cursor;
     a.qtab = nullptr;
-    a.qstride = 0;
     const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
     uint32_t n_words = 0;
     {
@@ -591,16 +590,15 @@ static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_o
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_qwords = n_words;
     if (qtab_out) {
-        if ((rc = dev_alloc(ctx, &ctx->qtab, qtab_words(n_words)))) return rc;
+        if ((rc = dev_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) return rc;
         *qtab_out = ctx->qtab;
-    } else if ((rc = pool_alloc(ctx, &ctx->qtab, qtab_words(n_words)))) {
+    } else if ((rc = pool_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) {
         return rc;
     }
     {
         PhaseScope ps(ctx, PH_K1);
         CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         a.qtab = ctx->qtab;
-        a.qstride = qtab_stride(n_words);
         qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -963,7 +961,7 @@ static int scan_launch(imsame_ctx *ctx, int seg) {
     CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PhaseScope ps(ctx, PH_K2);
     ScanArgs a;
-    a.db = seg_map(s); a.q = query_map(ctx); a.off = ctx->off; a.qtab = ctx->qtab; a.qstride = qtab_stride(ctx->n_qwords); a.brk = s.brk; a.n_brk = s.n_brk;
+    a.db = seg_map(s); a.q = query_map(ctx); a.off = ctx->off; a.qtab = ctx->qtab; a.brk = s.brk; a.n_brk = s.n_brk;
     a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
     a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
     a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;

@@ -10,7 +10,7 @@
 // chunk starts its word stream on the LAST base of the previous read and never
 // uses its own last base (src/alignmentFunctions.c:93-105,189-199).
 //
-// A table entry (24 bytes) carries everything the database scan needs to extend a seed hit
+// A table entry (QEntry, 24 bytes) carries everything the database scan needs to extend a seed hit
 // on this word: the 32 query bases after and the 32 before it as bit planes (common.cuh) and the room
 // left inside the read on both sides.  The scan then reads the entries of a bucket as ONE contiguous
 // stream instead of chasing word position -> read bounds -> two query windows through three dependent
@@ -54,25 +54,25 @@ __global__ void blk_kernel(const uint32_t *__restrict__ start, uint32_t n, uint3
     }
 }
 
-// The 24 bytes of entry i are stored as three 8-byte words in three planes of the table (structure of arrays):
-//   plane 0, word i: (f_lo, f_hi)  query bases e+1 .. e+32 (forward walk, src/alignmentFunctions.c:318-333)
-//   plane 1, word i: (b_lo, b_hi)  query bases e-k, e-k-1, .. (backward walk, :342-357), bit u = base e-k-u
-//   plane 2, word i: (e, lim)      e = index of the word's last base (curr_pos); lim = fq | bq1 << 16: steps left
-//                                  inside the read, forward (yend - e - 1) and backward + 1 (e - k + 2 - ys; 0 for
-//                                  the phantom word); ylen = fq + bq1 + k - 1
-// so that the 32 lanes of a warp, which read 32 consecutive entries, fetch 3 x 256 contiguous bytes.  (As an array
-// of 24-byte structs each of the three loads touched all 24 sectors of the warp's 768 bytes: 2x the DRAM traffic
-// and 3x the L1 wavefronts, round 2 profile.)
-typedef uint2 QEntry;  // one 8-byte word of a plane
-IMS_HD uint64_t qtab_stride(uint64_t n_words) { return (n_words + 16) & ~15ull; }  // words per plane
-IMS_HD uint64_t qtab_words(uint64_t n_words) { return 3 * qtab_stride(n_words); }
+struct QEntry {
+    uint32_t f_lo, f_hi;  // query bases e+1 .. e+32 (forward walk, src/alignmentFunctions.c:318-333)
+    uint32_t b_lo, b_hi;  // query bases e-k, e-k-1, .. (backward walk, :342-357), bit u = base e-k-u
+    uint32_t e;           // index of the word's last base (curr_pos)
+    uint32_t lim;         // fq | bq1 << 16: steps left inside the read, forward (yend - e - 1) and
+                          // backward + 1 (e - k + 2 - ys; 0 for the phantom word); ylen = fq + bq1 + k - 1
+};
+static_assert(sizeof(QEntry) == 24, "QEntry is read as three 8-byte words");
+// Array of structs on purpose.  Storing the three 8-byte words in three planes makes every warp load a coalesced
+// 256 bytes, but a bucket (~14 entries) then lies in three 114-byte pieces instead of one 343-byte piece, and DRAM
+// is read in 128-byte lines: measured 487 GB instead of 340 GB of DRAM reads per 0.5 Gbase segment and 547 instead
+// of 505 ms per cfg2 step (profiles/r02_ncu_scan_v12_full_summary.txt vs ..._v11_...).  The three loads of a lane
+// hit the same sectors, so the first one brings them into L1 (hit rate 58 % of the ideal 67 %).
 
 struct QTableArgs {
     SeqMap q;
     uint32_t per, n_threads;  // chunking of src/IMSAME.c:414,433
     uint32_t *cnt;            // pass 0: histogram ; pass 1: bucket cursors
-    QEntry *qtab;             // three planes of `qstride` words
-    uint64_t qstride;
+    QEntry *qtab;
     int k;                    // seed length (the reference: FIXED_K = 12, src/structs.h:15)
 };
 
@@ -98,9 +98,10 @@ __global__ void qtable_kernel(QTableArgs a) {
         const uint32_t slot = atomicAdd(&a.cnt[code], 1u);
         if (PASS == 1) {
             const HitHalf h = query_half(a.q.pk, e, ys, yend, a.k);
-            a.qtab[slot] = make_uint2(h.f_lo, h.f_hi);
-            a.qtab[a.qstride + slot] = make_uint2(h.b_lo, h.b_hi);
-            a.qtab[2 * a.qstride + slot] = make_uint2(e, (uint32_t)h.froom | ((uint32_t)(h.broom + 1) << 16));  // reads <= 32767 bases
+            uint2 *dst = reinterpret_cast<uint2 *>(a.qtab + slot);
+            dst[0] = make_uint2(h.f_lo, h.f_hi);
+            dst[1] = make_uint2(h.b_lo, h.b_hi);
+            dst[2] = make_uint2(e, (uint32_t)h.froom | ((uint32_t)(h.broom + 1) << 16));  // reads <= 32767 bases
         }
     }
 }

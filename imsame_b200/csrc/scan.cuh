@@ -24,8 +24,7 @@ constexpr int SCAN_THREADS_K2 = SCAN_WARPS * 32;
 struct ScanArgs {
     SeqMap db, q;
     const uint32_t *off;   // query table: bucket offsets (4^12 + 1)
-    const QEntry *qtab;    // query table: one entry per query word, bucket by bucket, in three planes (qtable.cuh)
-    uint64_t qstride;      // words per plane
+    const QEntry *qtab;    // query table: one entry per query word, bucket by bucket (qtable.cuh)
     const uint32_t *brk;   // database word breaks (segment-local), ascending
     uint32_t n_brk;
     const uint16_t *nmin;  // e-value threshold table by ylen
@@ -252,11 +251,11 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
             const uint32_t ha = h0 + lane, hb = h0 + 32 + lane;
             const bool la = ha < total, lb = hb < total;
             const uint32_t sa_h = la ? ha : total - 1, sb_h = lb ? hb : total - 1;
-            const uint2 *qa = a.qtab + (s_b0[warp][oa] + (sa_h - s_excl[warp][oa]));
-            const uint2 *qb = a.qtab + (s_b0[warp][ob] + (sb_h - s_excl[warp][ob]));
+            const uint2 *qa = reinterpret_cast<const uint2 *>(a.qtab + (s_b0[warp][oa] + (sa_h - s_excl[warp][oa])));
+            const uint2 *qb = reinterpret_cast<const uint2 *>(a.qtab + (s_b0[warp][ob] + (sb_h - s_excl[warp][ob])));
             // streamed once per database position that hits the bucket: no reuse worth a cache line
-            const uint2 fa = __ldcs(qa), ba = __ldcs(qa + a.qstride), ma = __ldcs(qa + 2 * a.qstride);
-            const uint2 fb = __ldcs(qb), bb = __ldcs(qb + a.qstride), mb2 = __ldcs(qb + 2 * a.qstride);
+            const uint2 fa = __ldcs(qa), ba = __ldcs(qa + 1), ma = __ldcs(qa + 2);
+            const uint2 fb = __ldcs(qb), bb = __ldcs(qb + 1), mb2 = __ldcs(qb + 2);
             const uint2 dfa = s_wf[warp][oa], dba = s_wb[warp][oa], dfb = s_wf[warp][ob], dbb = s_wb[warp][ob];
             const int2 rma = s_room[warp][oa], rmb = s_room[warp][ob];
             const uint32_t ea = ma.x, eb = mb2.x;
