@@ -31,6 +31,17 @@ entry = {"kernel": r[col["Kernel Name"]], "dram_bytes_read": val(r, "dram__bytes
          "duration_ms_under_ncu": val(r, "gpu__time_duration.sum"), "grid": r[col["launch__grid_size"]],
          "report": os.path.basename(rep), "note": note}
 entry["dram_bytes_per_launch"] = entry["dram_bytes_read"] + entry["dram_bytes_written"]
+# executed instructions: warp-level count x average active threads = thread-instructions (the "issue" roofline)
+try:
+    wi = val(r, "smsp__inst_executed.sum")
+    tpi = val(r, "smsp__thread_inst_executed_per_inst_executed.ratio")
+    entry.update({"warp_inst_executed": wi, "threads_per_inst": tpi, "thread_inst_executed": wi * tpi,
+                  "thread_inst_per_s_under_ncu": wi * tpi / (entry["duration_ms_under_ncu"] * 1e-3),
+                  "issue_active_pct": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                  "alu_pipe_pct": val(r, "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                  "l1_data_pipe_pct": val(r, "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed")})
+except Exception as e:  # noqa: BLE001
+    entry["inst_note"] = str(e)
 path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 cur = json.load(open(path)) if os.path.exists(path) else {}
 cur[key] = entry
