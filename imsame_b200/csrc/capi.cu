@@ -1448,9 +1448,16 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
         if ((rc = pool_alloc(ctx, &d_tb, tb_elems)) || (rc = pool_alloc(ctx, &d_tboff, nb)) || (rc = pool_alloc(ctx, &d_opoff, nb)) ||
             (rc = pool_alloc(ctx, &d_str, nb)) || (rc = pool_alloc(ctx, &d_ops, op_elems)) || (rc = pool_alloc(ctx, &d_nops, nb)) ||
             (rc = pool_alloc(ctx, &d_end, 2ull * nb))) { cleanup(); return rc; }
-        cudaMemcpyAsync(d_tboff, tb_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(d_opoff, op_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
-        cudaMemcpyAsync(d_str, strides.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream);
+        {
+            cudaError_t up = cudaMemcpyAsync(d_tboff, tb_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (up == cudaSuccess) up = cudaMemcpyAsync(d_opoff, op_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
+            if (up == cudaSuccess) up = cudaMemcpyAsync(d_str, strides.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, ctx->stream);
+            if (up != cudaSuccess) {
+                ctx->cuda_err = std::string("imsame_gpu_traceback: cudaMemcpyAsync: ") + cudaGetErrorString(up);
+                cleanup();
+                return IMSAME_ECUDA;
+            }
+        }
         NwArgs a = pb.args(p->igap, p->egap);
         a.tb = d_tb;
         a.tb_off = d_tboff;

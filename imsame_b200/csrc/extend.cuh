@@ -252,6 +252,19 @@ IMS_HD void ext_step(const ExtXY *lut, uint32_t mm, int c, int &run, int &best) 
 #endif
 }
 
+// first table step of a walk that starts with a score of 9 or more (seed lengths >= 9: the forward walk starts at
+// K, the backward one at high_right >= K): the row is known, two instructions less
+IMS_HD void ext_step_row9(const ExtXY *lut, uint32_t mm, int &run, int &best) {
+#if defined(__CUDA_ARCH__)
+    const int2 e = *reinterpret_cast<const int2 *>(lut + ((mm & 0xFFu) | (9u << 8)));
+    best = __viaddmax_s32(run, e.x, best);
+    run += e.y;
+#else
+    ext_step(lut, mm, 0, run, best);
+#endif
+}
+IMS_HD void ext_step_row9(const uint32_t *lut, uint32_t mm, int &run, int &best) { ext_step(lut, mm, 0, run, best); }
+
 template <class LUT>
 IMS_HD void ext_window(ExtState &s, const LUT *lut, const uint32_t *dpk, const uint32_t *qpk, uint32_t p,
                        uint32_t e, int K = imsame::K) {
@@ -371,8 +384,11 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const LUT *lut, uint32_t mfa,
     const int k0 = K << EXT_SC_SHIFT, kb = k0 + EXT_BEST_BIAS;
     int ra = k0, ba = kb, rb = k0, bb = kb;
     mfa = ext_prep(lut, mfa); mba = ext_prep(lut, mba); mfb = ext_prep(lut, mfb); mbb = ext_prep(lut, mbb);
+    const bool top9 = K >= 9;  // both walks start in the table's "9 or more" row
+    if (top9) { ext_step_row9(lut, mfa, ra, ba); ext_step_row9(lut, mfb, rb, bb); }
+    else { ext_step(lut, mfa, 0, ra, ba); ext_step(lut, mfb, 0, rb, bb); }
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) {
+    for (int c = 8; c < 32; c += 8) {
         ext_step(lut, mfa, c, ra, ba);
         ext_step(lut, mfb, c, rb, bb);
     }
@@ -381,8 +397,10 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const LUT *lut, uint32_t mfa,
     // backward restarts from high_right (:339) with high_left = 12 (:303)
     int ra2 = (ba & ~(int)EXT_POS_MASK) - EXT_BEST_BIAS, ba2 = kb, rb2 = (bb & ~(int)EXT_POS_MASK) - EXT_BEST_BIAS, bb2 = kb;
     const int hra = ra2 >> EXT_SC_SHIFT, hrb = rb2 >> EXT_SC_SHIFT;
+    if (top9) { ext_step_row9(lut, mba, ra2, ba2); ext_step_row9(lut, mbb, rb2, bb2); }
+    else { ext_step(lut, mba, 0, ra2, ba2); ext_step(lut, mbb, 0, rb2, bb2); }
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) {
+    for (int c = 8; c < 32; c += 8) {
         ext_step(lut, mba, c, ra2, ba2);
         ext_step(lut, mbb, c, rb2, bb2);
     }
