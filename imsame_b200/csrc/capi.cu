@@ -104,6 +104,8 @@ struct imsame_ctx {
     NwLink *carry = nullptr;
     uint64_t carry_warps = 0;
     uint8_t *stage = nullptr;
+    uint32_t *tb_pin = nullptr;            // pinned host buffer of imsame_gpu_traceback (ops, counts, cells), kept across calls
+    uint64_t tb_pin_cap = 0;               // in 32-bit words
     uint8_t *pin[2] = {nullptr, nullptr};  // pinned bounce buffers (upload_pack), their copy-done events
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool pin_busy[2] = {false, false};     // a copy out of the buffer has been enqueued (wait for pin_ev before refilling)
@@ -664,6 +666,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
     dev_free(ctx->keys); dev_free(ctx->payload); dev_free(ctx->pkey); dev_free(ctx->d_bins); dev_free(ctx->carry); dev_free(ctx->stage);
+    if (ctx->tb_pin) cudaFreeHost(ctx->tb_pin);
     for (int b = 0; b < 2; b++) {
         if (ctx->pin[b]) cudaFreeHost(ctx->pin[b]);
         if (ctx->pin_ev[b]) cudaEventDestroy(ctx->pin_ev[b]);
@@ -1392,30 +1395,36 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
             winners.push_back(r);
         }
     }
-    std::vector<uint64_t> n_ops_of(nq, 0), first_op(nq, 0);
-    // the op slots of a batch (xlen + ylen + 2 words per pair, ~50 MB) come back through one pinned buffer that is
-    // reused by every batch: as a fresh std::vector per batch they cost a 1 GB zero-fill and a 1 GB pageable copy
-    // on cfg2 (519 k winners)
-    struct Pinned {
-        uint32_t *p = nullptr; uint64_t cap = 0;
-        ~Pinned() { if (p) cudaFreeHost(p); }
-        bool ensure(uint64_t n) {
-            if (n <= cap) return true;
-            if (p) cudaFreeHost(p);
-            p = nullptr; cap = 0;
-            if (cudaMallocHost((void **)&p, (size_t)n * 4) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
-            cap = n;
-            return true;
+    std::vector<uint64_t> n_ops_of(nq, 0);
+    const bool trace = getenv("IMSAME_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_prep = 0, t_upload = 0, t_gpu = 0, t_merge = 0;
+    // everything that comes back goes through ONE pinned buffer kept in the context (a cudaMallocHost per call
+    // cost more than the kernels of a 100 k-read comparison)
+    auto pinned = [&](uint64_t words) -> uint32_t * {
+        if (words > ctx->tb_pin_cap) {
+            if (ctx->tb_pin) cudaFreeHost(ctx->tb_pin);
+            ctx->tb_pin = nullptr; ctx->tb_pin_cap = 0;
+            const uint64_t cap = words + words / 4 + 1024;
+            if (cudaMallocHost((void **)&ctx->tb_pin, (size_t)cap * 4) != cudaSuccess) { cudaGetLastError(); ctx->tb_pin = nullptr; return nullptr; }
+            ctx->tb_pin_cap = cap;
         }
-    } h_ops;
+        return ctx->tb_pin;
+    };
     size_t w0 = 0;
     while (w0 < winners.size()) {
+        double t0 = now();
         // batch: as many winners as fit the table budget
         std::vector<const unsigned char *> X, Y;
         std::vector<uint32_t> xl, yl, strides;
         std::vector<uint64_t> tb_off, op_off;
         uint64_t tb_elems = 0, op_elems = 0;
         size_t w1 = w0;
+        {
+            const size_t guess = std::min<size_t>(winners.size() - w0, 1u << 20);
+            X.reserve(guess); Y.reserve(guess); xl.reserve(guess); yl.reserve(guess); strides.reserve(guess);
+            tb_off.reserve(guess); op_off.reserve(guess);
+        }
         while (w1 < winners.size()) {
             const uint64_t r = winners[w1], s = best[r].db_seq - p->db_seq_base;
             const uint64_t xe = s + 1 < db->n_seqs ? db->start_pos[s + 1] : db->total_len;
@@ -1434,20 +1443,25 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
             w1++;
         }
         const uint32_t nb = (uint32_t)(w1 - w0);
+        t_prep += now() - t0; t0 = now();
         PairBatch pb(ctx);
         int rc;
         if ((rc = pb.upload(nb, X.data(), xl.data(), Y.data(), yl.data()))) return rc;
+        t_upload += now() - t0; t0 = now();
         uint16_t *d_tb = nullptr;
         uint64_t *d_tboff = nullptr, *d_opoff = nullptr;
-        uint32_t *d_str = nullptr, *d_ops = nullptr, *d_nops = nullptr, *d_end = nullptr;
+        uint32_t *d_str = nullptr, *d_ops = nullptr, *d_nops = nullptr, *d_end = nullptr, *d_coff = nullptr, *d_tiles = nullptr,
+                 *d_cops = nullptr;
+        const uint32_t n_tiles = (nb + SCAN_TILE - 1) / SCAN_TILE;
         // recycled blocks (pool): a cudaMalloc + cudaFree of the 3 GB table per batch cost 0.1 - 3 s each
         auto cleanup = [&]() {
             pool_free(ctx, d_tb); pool_free(ctx, d_tboff); pool_free(ctx, d_opoff); pool_free(ctx, d_str); pool_free(ctx, d_ops);
-            pool_free(ctx, d_nops); pool_free(ctx, d_end);
+            pool_free(ctx, d_nops); pool_free(ctx, d_end); pool_free(ctx, d_coff); pool_free(ctx, d_tiles); pool_free(ctx, d_cops);
         };
         if ((rc = pool_alloc(ctx, &d_tb, tb_elems)) || (rc = pool_alloc(ctx, &d_tboff, nb)) || (rc = pool_alloc(ctx, &d_opoff, nb)) ||
             (rc = pool_alloc(ctx, &d_str, nb)) || (rc = pool_alloc(ctx, &d_ops, op_elems)) || (rc = pool_alloc(ctx, &d_nops, nb)) ||
-            (rc = pool_alloc(ctx, &d_end, 2ull * nb))) { cleanup(); return rc; }
+            (rc = pool_alloc(ctx, &d_end, 2ull * nb)) || (rc = pool_alloc(ctx, &d_coff, (uint64_t)nb + 1)) ||
+            (rc = pool_alloc(ctx, &d_tiles, (uint64_t)n_tiles + 1))) { cleanup(); return rc; }
         {
             cudaError_t up = cudaMemcpyAsync(d_tboff, tb_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
             if (up == cudaSuccess) up = cudaMemcpyAsync(d_opoff, op_off.data(), (size_t)nb * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -1465,30 +1479,55 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
         if (!rc) {
             tb_walk_kernel<<<std::min<uint32_t>((nb + 127) / 128, (uint32_t)ctx->n_sm * 8), 128, 0, ctx->stream>>>(
                 pb.dr, d_tb, d_tboff, d_str, nb, d_ops, d_opoff, d_nops, d_end);
-            ctx->launches++;
+            // compact offsets of the ops actually used = exclusive scan of n_ops
+            scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(d_nops, nb, d_tiles, d_coff);
+            scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(d_tiles, n_tiles);
+            scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(d_nops, nb, d_tiles, d_coff);
+            ctx->launches += 4;
         }
-        std::vector<uint32_t> h_nops(nb), h_end(2ull * nb);
-        std::vector<PairRes> h_res(nb);
+        // pinned layout: [compact offsets nb + 1 | n_ops nb | end cells 2 nb | PairRes 4 nb | compact ops ...]
+        const uint64_t fixed_words = (uint64_t)nb + 1 + nb + 2ull * nb + 4ull * nb;
         cudaError_t ce = cudaGetLastError();
-        if (!rc && ce == cudaSuccess && !h_ops.ensure(op_elems)) { cleanup(); return IMSAME_ENOMEM; }
-        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_ops.p, d_ops, op_elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_nops.data(), d_nops, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_end.data(), d_end, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_res.data(), pb.dr, (size_t)nb * sizeof(PairRes), cudaMemcpyDeviceToHost, ctx->stream);
+        uint32_t *h = (!rc && ce == cudaSuccess) ? pinned(fixed_words + op_elems / 8 + 1024) : nullptr;
+        if (!rc && ce == cudaSuccess && !h) { cleanup(); return IMSAME_ENOMEM; }
+        uint32_t *h_coff = h, *h_nops = h ? h + nb + 1 : nullptr, *h_end = h ? h_nops + nb : nullptr;
+        PairRes *h_res = h ? reinterpret_cast<PairRes *>(h_end + 2ull * nb) : nullptr;
+        static_assert(sizeof(PairRes) == 16, "PairRes is copied as four words");
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_coff, d_coff, ((size_t)nb + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_nops, d_nops, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_end, d_end, (size_t)nb * 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpyAsync(h_res, pb.dr, (size_t)nb * sizeof(PairRes), cudaMemcpyDeviceToHost, ctx->stream);
         if (!rc && ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+        if (!rc && ce == cudaSuccess) {
+            const uint64_t total_ops = h_coff[nb];
+            if ((rc = pool_alloc(ctx, &d_cops, total_ops + 1))) { cleanup(); return rc; }
+            compact_ops_kernel<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)ctx->n_sm * 8), 256, 0, ctx->stream>>>(
+                d_ops, d_opoff, d_nops, d_coff, nb, d_cops);
+            ctx->launches++;
+            ce = cudaGetLastError();
+            // the fixed part is consumed before the buffer may move
+            for (uint32_t i = 0; i < nb; i++) {
+                const uint64_t r = winners[w0 + i];
+                n_ops_of[r] = h_nops[i];
+                cell_xy[4 * r] = h_res[i].bx; cell_xy[4 * r + 1] = h_res[i].by;
+                cell_xy[4 * r + 2] = h_end[2 * i]; cell_xy[4 * r + 3] = h_end[2 * i + 1];
+            }
+            uint32_t *h_ops = pinned(total_ops + 16);
+            if (!h_ops) { cleanup(); return IMSAME_ENOMEM; }
+            if (ce == cudaSuccess && total_ops) ce = cudaMemcpyAsync(h_ops, d_cops, total_ops * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+            t_gpu += now() - t0; t0 = now();
+            if (ce == cudaSuccess) all_ops.insert(all_ops.end(), h_ops, h_ops + total_ops);  // batch order = ascending read order
+            t_merge += now() - t0;
+        }
         cleanup();
         if (rc) return rc;
         if (ce != cudaSuccess) { ctx->cuda_err = cudaGetErrorString(ce); return IMSAME_ECUDA; }
-        for (uint32_t i = 0; i < nb; i++) {
-            const uint64_t r = winners[w0 + i];
-            first_op[r] = all_ops.size();
-            n_ops_of[r] = h_nops[i];
-            all_ops.insert(all_ops.end(), h_ops.p + op_off[i], h_ops.p + op_off[i] + h_nops[i]);
-            cell_xy[4 * r] = h_res[i].bx; cell_xy[4 * r + 1] = h_res[i].by;
-            cell_xy[4 * r + 2] = h_end[2 * i]; cell_xy[4 * r + 3] = h_end[2 * i + 1];
-        }
         w0 = w1;
     }
+    if (trace)
+        fprintf(stderr, "[imsame] traceback of %zu winners: lists %.1f ms, upload + pack %.1f ms, NW + walk + D2H %.1f ms, merge %.1f ms\n",
+                winners.size(), t_prep, t_upload, t_gpu, t_merge);
     // winners were visited in ascending read order, so first_op is already monotone
     uint64_t at = 0;
     for (uint64_t r = 0; r < nq; r++) { ops_off[r] = at; at += n_ops_of[r]; }

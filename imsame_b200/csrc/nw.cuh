@@ -206,6 +206,22 @@ static __global__ void tb_walk_kernel(const PairRes *res, const uint16_t *tb, co
     }
 }
 
+// K4c: the walks leave their run-length ops in per-pair slots of xlen + ylen + 2 words of which a handful are
+// used; one warp per pair moves them to their place in the compact list (offsets = exclusive scan of n_ops), so
+// that only the ops themselves cross PCIe (cfg2: 12 MB instead of 1 GB)
+static __global__ void compact_ops_kernel(const uint32_t *__restrict__ ops, const uint64_t *__restrict__ ops_off,
+                                          const uint32_t *__restrict__ n_ops, const uint32_t *__restrict__ dst_off,
+                                          uint32_t n_pairs, uint32_t *__restrict__ dst) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n_pairs; i += n_warps) {
+        const uint32_t n = n_ops[i];
+        const uint32_t *src = ops + ops_off[i];
+        uint32_t *d = dst + dst_off[i];
+        for (uint32_t k = lane; k < n; k += 32) d[k] = src[k];
+    }
+}
+
 #endif  // __CUDACC__
 
 }  // namespace imsame
