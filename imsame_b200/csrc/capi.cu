@@ -1431,7 +1431,7 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
             const uint64_t ye = r + 1 < nq ? query->start_pos[r + 1] : query->total_len;
             const uint32_t xlen = (uint32_t)(xe - db->start_pos[s]), ylen = (uint32_t)(ye - query->start_pos[r]);
             if (xlen > IMSAME_MAX_READ_SIZE || ylen > IMSAME_MAX_READ_SIZE) return IMSAME_EREADSIZE;
-            const uint32_t stride = tb_stride(ylen, nw_class_of(ylen));
+            const uint32_t stride = tb_stride(ylen, 8);  // every pair runs in the 8-columns-per-lane kernel (16-byte code stores)
             const uint64_t need = (uint64_t)(xlen > 1 ? xlen - 1 : 1) * stride;
             if (w1 > w0 && (tb_elems + need) * 2 > TB_BUDGET) break;
             X.push_back(db->sequences + db->start_pos[s]);
@@ -1475,7 +1475,9 @@ int imsame_gpu_traceback(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame
         NwArgs a = pb.args(p->igap, p->egap);
         a.tb = d_tb;
         a.tb_off = d_tboff;
-        rc = launch_nw_classes<true>(ctx, a, pb.class_mask, pb.dsmall + 4);
+        a.check_class = 0;
+        a.work = pb.dsmall + 4;
+        rc = launch_nw<8, true>(ctx, a);
         if (!rc) {
             tb_walk_kernel<<<std::min<uint32_t>((nb + 127) / 128, (uint32_t)ctx->n_sm * 8), 128, 0, ctx->stream>>>(
                 pb.dr, d_tb, d_tboff, d_str, nb, d_ops, d_opoff, d_nops, d_end);

@@ -155,6 +155,7 @@ IMS_HD void nw_row(NwLane<S> &L, const NwRow<S> &P1, NwRow<S> &P2, const NwLink 
     int nt = in.a, np = in.ap;   // value that becomes slot c of the new row: T[i][j0-1+c]
     int t2 = in.b;               // T[i][j-2]
     int r2 = P1.g, rp2 = P1.gp;  // T[i-1][j-2]
+    uint32_t tbw[4] = {0u, 0u, 0u, 0u};  // TB, S = 8: the row's codes, two per word
 #pragma unroll
     for (int c = 0; c < S; c++) {
         const int j = j0 + c;
@@ -183,7 +184,14 @@ IMS_HD void nw_row(NwLane<S> &L, const NwRow<S> &P1, NwRow<S> &P2, const NwLink 
         const bool is_d = (m == d);
         const bool is_r = r > l;
         const int pj = is_r ? pr : pl;
-        if (TB) tbrow[c] = is_d ? TB_DIAG : (is_r ? (uint16_t)(TB_COL | L.mcx[c]) : (uint16_t)(TB_ROW | mfy));
+        if (TB) {
+            const uint32_t code = is_d ? TB_DIAG : (is_r ? (uint32_t)(TB_COL | L.mcx[c]) : (uint32_t)(TB_ROW | mfy));
+            // S = 8 (the only strip width the traceback launches): the row's eight codes leave as ONE 16-byte store
+            // (tbrow is 16-byte aligned: strips start at multiples of 8 columns, rows at multiples of 256); as eight
+            // 2-byte stores from 32 lanes on 32 different rows every store instruction touched 32 sectors
+            if (S == 8) { if (c & 1) tbw[c >> 1] |= code << 16; else tbw[c >> 1] = code; }
+            else tbrow[c] = (uint16_t)code;
+        }
         // column maximum of column j-1 absorbs T[i-2][j-1], strictly greater only (:476-480)
         const bool uc = o2 > L.mcs[c];
         L.mcs[c] = uc ? o2 : L.mcs[c];
@@ -195,6 +203,13 @@ IMS_HD void nw_row(NwLane<S> &L, const NwRow<S> &P1, NwRow<S> &P2, const NwLink 
         rp2 = P1.p[c];
         nt = m + s;
         np = is_d ? pd : pj;
+    }
+    if (TB && S == 8) {
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint4 *>(tbrow) = make_uint4(tbw[0], tbw[1], tbw[2], tbw[3]);
+#else
+        for (int c = 0; c < 8; c++) tbrow[c] = (uint16_t)(tbw[c >> 1] >> (16 * (c & 1)));
+#endif
     }
     P2.h[S] = nt;
     P2.p[S] = np;
