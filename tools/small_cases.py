@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Small end-to-end cases for `compute-sanitizer` (memcheck / racecheck / initcheck): fixed-length, ragged reads with
+"""Small end-to-end cases (each checked against the oracle; also what one would run under a memory checker -- compute-sanitizer is closed on the GPU pool): fixed-length, ragged reads with
 word breaks, a run-time seed length, device-resident samples with the device reverse complement, the explicit-pair
 NW batch and the winners' traceback.  Every case is also checked against the oracle.
-usage: compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+usage: python tools/small_cases.py"""
 import os
 import sys
 
@@ -52,4 +52,4 @@ for s_ in (S_db, S_q, S_r):
 xs, ys = sc.random_pairs(4, 120, max_len=280, long_every=40)
 got, _ = ctx.nw_batch(xs, ys)
 ctx.close()
-print("sanitize_small: all cases equal the oracle")
+print("small_cases: all cases equal the oracle")
