@@ -252,12 +252,6 @@ IMS_HD void ext_step(const ExtXY *lut, uint32_t mm, int c, int &run, int &best) 
 #endif
 }
 
-// A walk whose score has reached 0 only reads the absorbing row 0 of the table from then on, whatever the mask says.
-// Zeroing the mask makes all finished walks of a warp read the SAME entry (a broadcast) instead of up to 32 different
-// ones: by the third and fourth step of a first window 20 % and 55 % of the random hits are finished, and the table
-// lookups are what keeps the shared-memory pipe busy.
-IMS_HD uint32_t ext_dead_mask(int run, uint32_t mm) { return run < (1 << EXT_SC_SHIFT) ? 0u : mm; }
-
 // first table step of a walk that starts with a score of 9 or more (seed lengths >= 9: the forward walk starts at
 // K, the backward one at high_right >= K): the row is known, two instructions less
 IMS_HD void ext_step_row9(const ExtXY *lut, uint32_t mm, int &run, int &best) {
@@ -395,7 +389,6 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const LUT *lut, uint32_t mfa,
     else { ext_step(lut, mfa, 0, ra, ba); ext_step(lut, mfb, 0, rb, bb); }
 #pragma unroll
     for (int c = 8; c < 32; c += 8) {
-        if (c >= 16) { mfa = ext_dead_mask(ra, mfa); mfb = ext_dead_mask(rb, mfb); }
         ext_step(lut, mfa, c, ra, ba);
         ext_step(lut, mfb, c, rb, bb);
     }
@@ -408,7 +401,6 @@ IMS_HD void ext_first2(ExtState &sa, ExtState &sb, const LUT *lut, uint32_t mfa,
     else { ext_step(lut, mba, 0, ra2, ba2); ext_step(lut, mbb, 0, rb2, bb2); }
 #pragma unroll
     for (int c = 8; c < 32; c += 8) {
-        if (c >= 16) { mba = ext_dead_mask(ra2, mba); mbb = ext_dead_mask(rb2, mbb); }
         ext_step(lut, mba, c, ra2, ba2);
         ext_step(lut, mbb, c, rb2, bb2);
     }
