@@ -488,9 +488,7 @@ def run_ours(args):
             else:
                 # the same public calls a sharded caller makes: upload + pack + query table, upload + pack
                 # of the shard, band-stepped run with the key exchange, owner's payload, records to the host
-                ctx2.set_query((q_pin.array, qs), params)
-                ctx2.set_db((db_pin.array, ds))
-                st = ctx2.run_sharded(params, keys.data_ptr(), payload.data_ptr())
+                st = ctx2.align_shard((db_pin.array, ds), (q_pin.array, qs), params, keys.data_ptr(), payload.data_ptr())
                 out = ctx2.fetch(keys.data_ptr(), payload.data_ptr())
                 st["h2d_bytes"] = int(nd * L + nq * L)
                 st["d2h_bytes"] = int(16 * nq)
@@ -508,8 +506,8 @@ def run_ours(args):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(te.item()) * 1e3,
                "what": ("imsame_gpu_align(): pinned host ASCII reads -> H2D -> pack -> query table -> scan -> NW -> D2H records"
                         if world == 1 else
-                        "per rank: set_query + set_db (pinned host ASCII reads -> H2D -> pack -> query table) -> imsame_gpu_run_sharded "
-                        "(band-stepped run, ncclMin key reductions and the owner's payload inside the library) -> D2H records"),
+                        "per rank: imsame_gpu_align_shard (pinned host ASCII reads -> H2D one segment ahead of the scan -> pack -> query "
+                        "table -> band-stepped run, ncclMin key reductions and the owner's payload inside the library) -> D2H records"),
                "device_phases_ms": e2e_phases}
 
     # ---- cfg3 as BASELINE.json states it: the SAME 80 M-read database cut over N GPUs (strong scaling) --------

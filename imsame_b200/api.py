@@ -63,7 +63,7 @@ SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "im
            "imsame_gpu_run_scan", "imsame_gpu_run_band", "imsame_gpu_run_select", "imsame_gpu_run_end",
            "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode",
            "imsame_gpu_set_kmer", "imsame_gpu_comm_id", "imsame_gpu_comm_init", "imsame_gpu_comm_free",
-           "imsame_gpu_run_sharded", "imsame_gpu_align_sharded",
+           "imsame_gpu_run_sharded", "imsame_gpu_align_shard", "imsame_gpu_align_sharded",
            "imsame_gpu_sample_create", "imsame_gpu_sample_revcomp", "imsame_gpu_sample_free", "imsame_gpu_align_samples",
            "imsame_gpu_traceback", "imsame_gpu_free", "imsame_gpu_host_alloc", "imsame_gpu_host_free"]
 
@@ -116,6 +116,7 @@ def lib():
         l.imsame_gpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
         l.imsame_gpu_comm_free.argtypes = [vp]
         l.imsame_gpu_run_sharded.argtypes = [vp, C.POINTER(Params), vp, vp, C.c_int, C.POINTER(Stats)]
+        l.imsame_gpu_align_shard.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(SeqInfo), C.POINTER(Params), vp, vp, C.POINTER(Stats)]
         l.imsame_gpu_align_sharded.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(SeqInfo), C.POINTER(SeqInfo),
                                                C.POINTER(Params), vp, C.POINTER(Stats)]
         l.imsame_gpu_sample_create.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(vp)]
@@ -326,6 +327,17 @@ class Imsame:
         st = Stats()
         self._check(lib().imsame_gpu_run_sharded(self._h, C.byref(params), C.c_void_p(d_keys), C.c_void_p(d_payload),
                                                  int(exchange_every), C.byref(st)))
+        return st.as_dict()
+
+    def align_shard(self, shard, query, params, d_keys=0, d_payload=0, db_breaks=None):
+        """collective, host buffers in: query + this rank's shard uploaded (segments one ahead of their scan), then as
+        run_sharded.  The reduced result stays on the device (d_keys / d_payload or the context's own): fetch() it."""
+        d, k1 = _seqinfo(shard[0], shard[1], db_breaks)
+        q, k2 = _seqinfo(query[0], query[1])
+        st = Stats()
+        self._check(lib().imsame_gpu_align_shard(self._h, C.byref(d), C.byref(q), C.byref(params), C.c_void_p(d_keys),
+                                                 C.c_void_p(d_payload), C.byref(st)))
+        self.nq = int(q.n_seqs)
         return st.as_dict()
 
     def n_segments(self):

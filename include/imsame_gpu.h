@@ -177,6 +177,13 @@ int imsame_gpu_comm_free(imsame_ctx *ctx);
  * REDUCED result on every rank; imsame_gpu_fetch decodes it.  Collective: every rank must call it. */
 int imsame_gpu_run_sharded(imsame_ctx *ctx, const imsame_params *params, uint64_t *d_keys,
                            uint64_t *d_payload, int exchange_every, imsame_stats *stats);
+/* The whole per-rank job in one collective call, like imsame_gpu_align: uploads the query (+ its word table) and
+ * THIS rank's shard from host buffers -- the shard's segments one ahead of their scan, on a copy stream -- then
+ * continues like imsame_gpu_run_sharded.  `shard` = this rank's contiguous read range with local start_pos;
+ * params->db_total_len_global / db_pos_base / db_seq_base place it in the whole database. */
+int imsame_gpu_align_shard(imsame_ctx *ctx, const imsame_seqinfo *shard, const imsame_seqinfo *query,
+                           const imsame_params *params, uint64_t *d_keys, uint64_t *d_payload,
+                           imsame_stats *stats);
 /* One process, n GPUs: cut `db` into n contiguous read ranges, upload, build the query table on every
  * GPU, run sharded, decode into out (nq entries).  ctxs[i] must sit on n different devices; stats: n
  * entries or NULL.  The communicator is created on first use and kept in the contexts. */

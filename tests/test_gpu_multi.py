@@ -37,12 +37,20 @@ def _worker(rank, world, port, tmpdir):
     ctx = api.Imsame(rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     p = api.make_params(n_threads=4, db_total_len_global=len(db), db_pos_base=b0, db_seq_base=lo)
-    ctx.set_query((q, qs), p)
-    ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
+    mode = os.environ.get("IMSAME_TEST_STEPPED", "1")
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")
     payload = torch.empty(nq, dtype=torch.int64, device="cuda")
-    mode = os.environ.get("IMSAME_TEST_STEPPED", "1")
-    if mode == "nccl_in_library":
+    if mode != "align_shard":
+        ctx.set_query((q, qs), p)
+        ctx.set_db((db[b0:b1], ds[lo:hi + 1] - ds[lo]))
+    if mode == "align_shard":
+        # the whole per-rank job in one collective call: uploads (a segment ahead of the scan) + table + sharded run
+        box = [api.comm_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], world, rank)
+        st = ctx.align_shard((db[b0:b1], ds[lo:hi + 1] - ds[lo]), (q, qs), p, keys.data_ptr(), payload.data_ptr())
+        assert st["ms_comm"] > 0 and st["h2d_bytes"] >= (b1 - b0) + len(q)
+    elif mode == "nccl_in_library":
         # the product path: the library's own communicator (ncclCommInitRank from 128 bytes handed around by
         # torch.distributed) and its band-stepped run with ncclMin / ncclMax reductions inside
         box = [api.comm_id() if rank == 0 else None]
@@ -70,7 +78,7 @@ def _worker(rank, world, port, tmpdir):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("stepped", ["nccl_in_library", "1", "0"])
+@pytest.mark.parametrize("stepped", ["nccl_in_library", "align_shard", "1", "0"])
 def test_nccl_sharded_equals_single_gpu(gpu, tmp_path, stepped):
     import torch.multiprocessing as mp
     from imsame_b200 import api
