@@ -208,24 +208,25 @@ def reference_cpu_run(args, w, steps, warmup):
             "ms_align_phase": al * 1e3, "ms_process": wall * 1e3}, None
 
 
-def same_config_cfg1(ctx, api, H, np):
-    """BASELINE.json configs[0] at FULL size -- the one configuration the reference itself can run -- through both
-    implementations on this box: the unmodified reference binary on all host threads (whole process and alignment
-    phase) and imsame_gpu_align() from host buffers.  The two record sets must be identical."""
-    import shutil
-    ref = os.path.join(ROOT, "oracle", "_ref", "IMSAME")
-    if not os.path.exists(ref):
-        return {"unavailable": "oracle/_ref/IMSAME missing"}
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers as hp
-    cores = os.cpu_count() or 1
+def cfg1_inputs(H, np):
+    """BASELINE.json configs[0] at full size: 10k x 150bp query reads vs a 100k-read database (seed 1001, 20 genomes)"""
     L, nd, nq = 150, 100_000, 10_000
     pool = H.SynthPool(1001, 20, 500_000)
     db = pool.db_reads(0, nd, L)
     q = pool.query_reads(0, nq, L, 0.03)
     pool.close()
-    ds = np.arange(nd + 1, dtype=np.uint64) * L
-    qs = np.arange(nq + 1, dtype=np.uint64) * L
+    return db, np.arange(nd + 1, dtype=np.uint64) * L, q, np.arange(nq + 1, dtype=np.uint64) * L, L, nd, nq
+
+
+def reference_cfg1(H, np, keep_out=None):
+    """the unmodified reference binary on configs[0] at full size, all host threads, best of 2: whole process and
+    alignment phase (process wall - its single-threaded load / index phases, whose clock() prints are wall time)"""
+    import shutil
+    ref = os.path.join(ROOT, "oracle", "_ref", "IMSAME")
+    if not os.path.exists(ref):
+        return None
+    cores = os.cpu_count() or 1
+    db, ds, q, qs, L, nd, nq = cfg1_inputs(H, np)
     tmp = tempfile.mkdtemp(prefix="imsame_cfg1_")
     dbf, qf, outf = (os.path.join(tmp, n) for n in ("db.fa", "q.fa", "ref.align"))
     H.write_fasta(dbf, db, nd, L, "d")
@@ -236,7 +237,7 @@ def same_config_cfg1(ctx, api, H, np):
         txt = subprocess.run([ref, "-query", qf, "-db", dbf, "-out", outf, "-n_threads", str(cores)],
                              capture_output=True, text=True, check=True).stdout
         wall = time.perf_counter() - t0
-        load = 0.0  # single-threaded phases: the reference's clock() prints are wall time there
+        load = 0.0
         for line in txt.splitlines():
             for key in ("Initialization took", "Hash table building took", "Took"):
                 if key in line:
@@ -246,26 +247,43 @@ def same_config_cfg1(ctx, api, H, np):
                         pass
         runs.append((wall, max(wall - load, 1e-9)))
     wall, al = min(r[0] for r in runs), min(r[1] for r in runs)
-    want = hp.parse_align_headers(outf)
-    params = api.make_params(n_threads=cores)
+    headers = None
+    if keep_out is not None:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as hp
+        headers = hp.parse_align_headers(outf)
+    shutil.rmtree(tmp, ignore_errors=True)
+    return {"workload": "cfg1 at full size: 10k x 150bp query reads vs 100k-read database, defaults, -n_threads = host cores",
+            "cores": cores, "reference_whole_process_reads_per_s": nq / wall, "reference_whole_process_s": wall,
+            "reference_align_phase_reads_per_s": nq / al, "reference_align_phase_s": al,
+            "reference_what": "oracle/_ref/IMSAME (unmodified reference) on FASTA files, best of 2; alignment phase = process wall "
+                              "- its single-threaded load/index phases", "_headers": headers}
+
+
+def same_config_cfg1(ctx, api, H, np):
+    """BASELINE.json configs[0] at FULL size -- the one configuration the reference itself can run -- through both
+    implementations on this box: the unmodified reference binary on all host threads (whole process and alignment
+    phase) and imsame_gpu_align() from host buffers.  The two record sets must be identical."""
+    r = reference_cfg1(H, np, keep_out=True)
+    if r is None:
+        return {"unavailable": "oracle/_ref/IMSAME missing"}
+    want = r.pop("_headers")
+    db, ds, q, qs, L, nd, nq = cfg1_inputs(H, np)
+    params = api.make_params(n_threads=r["cores"])
     ctx.align((db, ds), (q, qs), params)
     ts = []
     for _ in range(3):
         t0 = time.perf_counter()
         out, st = ctx.align((db, ds), (q, qs), params)
         ts.append(time.perf_counter() - t0)
-    got = sorted(api.header_fields(r, o, L) for r, o in enumerate(out) if o["accepted"])
-    shutil.rmtree(tmp, ignore_errors=True)
+    got = sorted(api.header_fields(i, o, L) for i, o in enumerate(out) if o["accepted"])
     t = min(ts)
-    return {"workload": "cfg1 at full size: 10k x 150bp query reads vs 100k-read database, defaults, -n_threads = host cores",
-            "cores": cores, "records": len(want), "records_identical_to_reference": got == want,
-            "gpu_e2e_reads_per_s": nq / t, "gpu_e2e_ms": t * 1e3,
-            "gpu_what": "imsame_gpu_align() from pageable host buffers: H2D, packing, query table, scan, NW, D2H (best of 3)",
-            "reference_whole_process_reads_per_s": nq / wall, "reference_whole_process_s": wall,
-            "reference_align_phase_reads_per_s": nq / al, "reference_align_phase_s": al,
-            "reference_what": "oracle/_ref/IMSAME (unmodified reference) on the same FASTA, best of 2; alignment phase = process wall "
-                              "- its single-threaded load/index phases",
-            "speedup_vs_align_phase": (nq / t) / (nq / al), "speedup_vs_whole_process": (nq / t) / (nq / wall)}
+    r.update({"records": len(want), "records_identical_to_reference": got == want,
+              "gpu_e2e_reads_per_s": nq / t, "gpu_e2e_ms": t * 1e3,
+              "gpu_what": "imsame_gpu_align() from pageable host buffers: H2D, packing, query table, scan, NW, D2H (best of 3)",
+              "speedup_vs_align_phase": (nq / t) / r["reference_align_phase_reads_per_s"],
+              "speedup_vs_whole_process": (nq / t) / r["reference_whole_process_reads_per_s"]})
+    return r
 
 
 def run_reference_arm(args):
@@ -292,7 +310,19 @@ def run_reference_arm(args):
             "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "what": "alignment phase of the reference (src/IMSAME.c:409-467) on all host threads",
                     "reads_per_s_index_plus_align": r["reads_per_s_index_plus_align"]}}
+    if not args.no_same_config:
+        # the one configuration the reference can run at FULL size, for a same-config pair with our arm's `same_config`
+        import numpy as np
+        c1 = reference_cfg1(H_mod(), np)
+        if c1:
+            c1.pop("_headers", None)
+            line["same_config"] = c1
     OUT.emit(json.dumps(line))
+
+
+def H_mod():
+    from imsame_b200 import hostlib as H
+    return H
 
 
 # ------------------------------------------------------------------------------------------

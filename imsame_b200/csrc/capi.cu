@@ -981,45 +981,47 @@ static int scan_launch(imsame_ctx *ctx, int seg) {
 static int scan_finish(imsame_ctx *ctx, int seg) {
     const SeqMap qm = query_map(ctx);
     int rc;
-    for (int attempt = 0;; attempt++) {
-        int overflow = 0;
-        CK(cudaMemcpyAsync(&overflow, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (!overflow) break;
-        if (ctx->hcap >= (1u << 30) || attempt == 7) return IMSAME_ELIMIT;
-        if ((rc = ensure_work_buffers(ctx, ctx->hcap * 2))) return rc;  // reallocates + clears the table
-        if ((rc = scan_launch(ctx, seg))) return rc;
-    }
     uint32_t *bins = ctx->d_bins + (size_t)seg * BINS_STRIDE;
     uint32_t *bin_count = bins, *bin_off = bins + NW_NBINS, *launch_range = bins + 4 * NW_NBINS + 4;
     uint64_t base = 0;
     for (int k = 0; k < seg; k++) base += ctx->seg_pair_count[k];
     if (base >= 0xFFFFFFFFull) return IMSAME_ELIMIT;
     BinArgs b;
-    b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.q = qm;
+    b.q = qm;
     b.band_width = (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS;
-    b.bin_count = bin_count; b.bin_off = bin_off; b.pairs = ctx->pairs;
-    const int g = std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS),
-                                     (uint32_t)ctx->n_sm * 8);
+    b.bin_count = bin_count; b.bin_off = bin_off;
     uint32_t n_seg_pairs = 0;
-    {
-        PhaseScope ps(ctx, PH_K2B);
-        add_counters_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->d_counters + 8, 4);
-        CK(cudaMemsetAsync(bins, 0, BINS_STRIDE * sizeof(uint32_t), ctx->stream));
-        bin_kernel<0><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
-        bin_offsets_kernel<<<1, 32, 0, ctx->stream>>>(bin_count, bin_off, launch_range, ctx->d_small,
-                                                    (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u, (uint32_t)base);
-        ctx->launches += 3;
+    int g = 0;
+    // ONE host synchronisation per segment: the counting pass over the pair table is queued behind the scan right
+    // away (it only reads the table), and the overflow flag comes back together with the number of candidates
+    for (int attempt = 0;; attempt++) {
+        b.hkeys = ctx->hkeys; b.hvals = ctx->hvals; b.n_slots = ctx->hcap; b.pairs = ctx->pairs;
+        g = (int)std::min<uint32_t>((ctx->hcap + BIN_THREADS * BIN_ITEMS - 1) / (BIN_THREADS * BIN_ITEMS), (uint32_t)ctx->n_sm * 8);
+        {
+            PhaseScope ps(ctx, PH_K2B);
+            CK(cudaMemsetAsync(bins, 0, BINS_STRIDE * sizeof(uint32_t), ctx->stream));
+            bin_kernel<0><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
+            bin_offsets_kernel<<<1, 32, 0, ctx->stream>>>(bin_count, bin_off, launch_range, ctx->d_small,
+                                                        (uint32_t)max_nw_grid(ctx) * NW_WARPS * 8u, (uint32_t)base);
+            ctx->launches += 2;
+        }
+        int overflow = 0;
+        CK(cudaMemcpyAsync(&overflow, ctx->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(&n_seg_pairs, ctx->d_small, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!overflow) break;
+        if (ctx->hcap >= (1u << 30) || attempt == 7) return IMSAME_ELIMIT;
+        if ((rc = ensure_work_buffers(ctx, ctx->hcap * 2))) return rc;  // reallocates + clears the table
+        if ((rc = scan_launch(ctx, seg))) return rc;
     }
-    CK(cudaMemcpyAsync(&n_seg_pairs, ctx->d_small, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     if (base + n_seg_pairs >= 0xFFFFFFFFull) return IMSAME_ELIMIT;
     if ((rc = ensure_pairs(ctx, base + n_seg_pairs))) return rc;
     b.pairs = ctx->pairs;
     {
         PhaseScope ps(ctx, PH_K2B);
+        add_counters_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_counters, ctx->d_counters + 8, 4);  // the attempt that counted
         bin_kernel<1><<<g, BIN_THREADS, 0, ctx->stream>>>(b);
-        ctx->launches++;
+        ctx->launches += 2;
     }
     ctx->seg_pair_base[seg] = base;
     ctx->seg_pair_count[seg] = n_seg_pairs;
