@@ -915,6 +915,10 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     // segment and grow on overflow (run_scan)
     uint32_t cap = 1u << 20;
     while (cap < 64ull * nq && cap < (1u << 28)) cap <<= 1;
+    if (const char *e = getenv("IMSAME_TEST_PAIR_SLOTS")) {  // test hook: start small so that the growth path runs
+        cap = 1u << 8;
+        while (cap < (uint32_t)atoi(e)) cap <<= 1;
+    }
     cap = std::max(cap, ctx->hcap);
     if ((rc = ensure_carry(ctx, ctx->q_maxlen))) return rc;
     if ((rc = ensure_work_buffers(ctx, cap))) return rc;

@@ -93,6 +93,26 @@ def test_read_longer_than_the_scan_limit_is_refused(gpu):
     assert int(out["accepted"].sum()) == 1  # the context is still usable
 
 
+def test_pair_table_growth_gives_the_same_records(monkeypatch):
+    """the candidate pair table overflows and is grown (the segment is scanned again) until it holds every
+    (read, database read) pair: a fresh context starts at 256 slots through the test hook IMSAME_TEST_PAIR_SLOTS"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(23, 3, 40000, 150, 6000, 800, 0.04)
+    want, _ = oracle_records(db, ds, q, qs, 4)
+    monkeypatch.setenv("IMSAME_TEST_PAIR_SLOTS", "256")
+    ctx = api.Imsame(0)
+    try:
+        out, st = ctx.align((db, ds), (q, qs), api.make_params(n_threads=4))
+        assert st["k2_launches"] >= 3 and st["n_pairs"] > 2000  # 256 -> ... slots: several scans of the one segment
+        assert gpu_records(out) == want and len(want) > 300
+        monkeypatch.delenv("IMSAME_TEST_PAIR_SLOTS")
+        out2, st2 = ctx.align((db, ds), (q, qs), api.make_params(n_threads=4))
+        assert st2["k2_launches"] == 1 and gpu_records(out2) == want
+        assert (st2["n_hits"], st2["n_evalue_pass"], st2["n_pairs"]) == (st["n_hits"], st["n_evalue_pass"], st["n_pairs"])
+    finally:
+        ctx.close()
+
+
 def _oracle_rc(db, ds, q, qs, n_threads):
     """orc_align_sequential's return code (-5 = "Read size reached for gapped alignment.") and records"""
     odb, oq = hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs)
