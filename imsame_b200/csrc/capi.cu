@@ -408,6 +408,7 @@ int ensure_pairs(imsame_ctx *ctx, uint64_t need) {
     if (ctx->pairs && ctx->pairs_cap)
         CK(cudaMemcpyAsync(np, ctx->pairs, ctx->pairs_cap * sizeof(PairRec), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));  // (segment-major experiment: NW launches may run there)
     dev_free(ctx->pairs); dev_free(ctx->res);
     ctx->pairs = np; ctx->res = nr; ctx->pairs_cap = cap;
     return IMSAME_OK;
@@ -1121,11 +1122,45 @@ extern "C" int imsame_gpu_run_end(imsame_ctx *ctx, imsame_stats *st) {
     return IMSAME_OK;
 }
 
+// EXPERIMENT (IMSAME_SEGMENT_MAJOR = 1 | 2, measured in DESIGN.md 9.2, not the default): the NW launches of segment s
+// run right after its scan -- 2: on the copy stream, i.e. concurrently with the scan of segment s + 1.  Segment-major
+// order gives up the pruning across segments of the band-major order below; results are the same.  (The candidate
+// buffers must have reached their final size: run once in the default order first.)
+static int run_segment_major(imsame_ctx *ctx, imsame_stats *st, bool concurrent) {
+    int rc;
+    const int nseg = (int)ctx->segs.size();
+    cudaEvent_t ev = nullptr;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return IMSAME_ECUDA;
+    cudaStream_t main_stream = ctx->stream;
+    for (int seg = 0; seg < nseg; seg++) {
+        if ((rc = imsame_gpu_run_scan(ctx, seg))) break;
+        if (concurrent) {
+            cudaEventRecord(ev, main_stream);
+            cudaStreamWaitEvent(ctx->copy_stream, ev, 0);
+            ctx->stream = ctx->copy_stream;
+        }
+        for (int band = 0; band < NW_BANDS && !rc; band++) rc = imsame_gpu_run_band(ctx, seg, band);
+        ctx->stream = main_stream;
+        if (rc) break;
+    }
+    if (concurrent) {
+        cudaEventRecord(ev, ctx->copy_stream);
+        cudaStreamWaitEvent(main_stream, ev, 0);
+    }
+    cudaEventDestroy(ev);
+    if (rc) return rc;
+    for (int seg = 0; seg < nseg; seg++)
+        if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
+    return imsame_gpu_run_end(ctx, st);
+}
+
 static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
                     imsame_stats *st) {
     int rc;
     if ((rc = imsame_gpu_run_begin(ctx, p, d_keys, d_payload))) return rc;
     const int nseg = (int)ctx->segs.size();
+    if (const char *e = getenv("IMSAME_SEGMENT_MAJOR"))
+        if (atoi(e) > 0 && !ctx->in_align) return run_segment_major(ctx, st, atoi(e) == 2);
     for (int seg = 0; seg < nseg; seg++)
         if ((rc = imsame_gpu_run_scan(ctx, seg))) return rc;
     // ascending bands over ALL segments: an accepted early candidate prunes the read's later ones
