@@ -60,8 +60,6 @@ struct imsame_ctx {
     uint32_t class_mask = 0;
     std::vector<uint32_t> q_start_host;
     uint32_t *off = nullptr, *cursor = nullptr, *tile_sums = nullptr;
-    uint32_t *d_part = nullptr;   // partition cursors of the two-level table build (qtable.cuh)
-    QRec *k1_tmp = nullptr;       // its intermediate records: given back to the pool at the next host synchronisation
     uint32_t *off_own = nullptr;  // the context's own offsets table (`off` may point into a resident sample instead)
     QEntry *qtab = nullptr;  // query word table entries, bucket by bucket (qtable.cuh)
     bool q_borrowed = false;  // the query buffers and its word table belong to an imsame_sample
@@ -247,7 +245,6 @@ void pool_destroy(imsame_ctx *ctx) {
 }
 
 void free_query(imsame_ctx *ctx) {
-    if (ctx->k1_tmp) { cudaStreamSynchronize(ctx->stream); pool_free(ctx, ctx->k1_tmp); }
     if (ctx->q_borrowed) {
         ctx->q_pk = ctx->q_start = ctx->q_blk = nullptr;
         ctx->qtab = nullptr;
@@ -602,28 +599,12 @@ static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_o
         return rc;
     }
     {
-        // entries: level 1 into `tmp` by partition, level 2 from there into the buckets (qtable.cuh)
-        if (!ctx->d_part && (rc = dev_alloc(ctx, &ctx->d_part, QPARTS))) return rc;
-        if (ctx->k1_tmp) { CK(cudaStreamSynchronize(ctx->stream)); pool_free(ctx, ctx->k1_tmp); }
-        QRec *tmp = nullptr;
-        if ((rc = pool_alloc(ctx, &tmp, (uint64_t)n_words + 1))) return rc;
-        ctx->k1_tmp = tmp;
         PhaseScope ps(ctx, PH_K1);
         CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
         a.qtab = ctx->qtab;
-        a.tmp = tmp;
-        a.part_cursor = ctx->d_part;
-        a.off = ctx->off;
-        a.part_shift = std::max(0, 2 * ctx->k - 8);
-        a.n_words = n_words;
-        qpart_init_kernel<<<1, QPARTS, 0, ctx->stream>>>(ctx->off, a.part_shift, ctx->d_part);
-        const uint32_t tiles = (total + QPART_THREADS * QPART_ITEMS - 1) / (QPART_THREADS * QPART_ITEMS);
-        qpart_kernel<<<std::max(1u, std::min<uint32_t>(tiles, (uint32_t)ctx->n_sm * 8)), QPART_THREADS, 0, ctx->stream>>>(a);
-        const uint32_t chunks = (n_words + QFILL_THREADS * QFILL_ITEMS - 1) / (QFILL_THREADS * QFILL_ITEMS);
-        qfill_kernel<<<std::max(1u, chunks), QFILL_THREADS, 0, ctx->stream>>>(a);
-        ctx->launches += 3;
-        cudaError_t ce = cudaGetLastError();
-        if (ce != cudaSuccess) { ctx->cuda_err = std::string("query table kernels: ") + cudaGetErrorString(ce); return IMSAME_ECUDA; }
+        qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
     }
     ctx->q_k = ctx->k;
     ctx->have_query = true;
@@ -681,7 +662,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     free_query(ctx);
     free_db(ctx);
     pool_destroy(ctx);
-    dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums); dev_free(ctx->d_part);
+    dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
     dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
@@ -968,7 +949,6 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
         CK(cudaMemsetAsync(ctx->run_payload, 0, (size_t)nq * 8, ctx->stream));
     }
     CK(cudaStreamSynchronize(ctx->stream));  // the host tables go out of scope
-    pool_free(ctx, ctx->k1_tmp);             // the table build that used it has finished (other streams may reuse the block)
     ctx->run_active = true;
     ctx->run_masked = false;
     return IMSAME_OK;

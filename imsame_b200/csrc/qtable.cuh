@@ -68,26 +68,12 @@ static_assert(sizeof(QEntry) == 24, "QEntry is read as three 8-byte words");
 // of 505 ms per cfg2 step (profiles/r02_ncu_scan_v12_full_summary.txt vs ..._v11_...).  The three loads of a lane
 // hit the same sectors, so the first one brings them into L1 (hit rate 58 % of the ideal 67 %).
 
-// Intermediate record of the two-level table build: an entry plus its word
-struct QRec {
-    QEntry ent;
-    uint32_t code, pad;
-};
-static_assert(sizeof(QRec) == 32, "QRec is moved as two 16-byte words");
-constexpr int QPARTS = 256;  // level-1 partitions: the top 8 bits of the word
-
 struct QTableArgs {
     SeqMap q;
     uint32_t per, n_threads;  // chunking of src/IMSAME.c:414,433
-    uint32_t *cnt;            // histogram pass: counters; fill pass: bucket cursors
+    uint32_t *cnt;            // pass 0: histogram ; pass 1: bucket cursors
     QEntry *qtab;
     int k;                    // seed length (the reference: FIXED_K = 12, src/structs.h:15)
-    // two-level build: words -> QPARTS partitions of `tmp` (by the top bits of the word) -> buckets of qtab
-    QRec *tmp;
-    uint32_t *part_cursor;    // QPARTS
-    const uint32_t *off;      // bucket offsets (after the scan)
-    int part_shift;           // word >> part_shift = partition
-    uint32_t n_words;
 };
 
 // does a query word end at base e, and which word?  
@@ -116,78 +102,6 @@ __global__ void qtable_kernel(QTableArgs a) {
             dst[0] = make_uint2(h.f_lo, h.f_hi);
             dst[1] = make_uint2(h.b_lo, h.b_hi);
             dst[2] = make_uint2(e, (uint32_t)h.froom | ((uint32_t)(h.broom + 1) << 16));  // reads <= 32767 bases
-        }
-    }
-}
-
-// ---- two-level scatter of the table entries --------------------------------------------------------------
-// A direct scatter (qtable_kernel<1>: every query position writes its 24-byte entry to a random bucket of a 5.7 GB
-// table) costs 22-38 ms on cfg2 although the histogram pass, with as many atomics, takes 1.7 ms: the price is 2.4e8
-// isolated partial-sector writes.  Instead, in two passes that both keep their writes together:
-//   level 1 (qpart_kernel): a block takes a tile of consecutive query positions, builds their entries (the packed
-//     query is read sequentially), counts them per partition (top 8 bits of the word) in shared memory, reserves one
-//     contiguous range per partition with ONE global atomic each and stores the records there, 32 bytes = one
-//     full sector each;
-//   level 2 (qfill_kernel): the records are read back in order -- so the blocks in flight work on one or two
-//     partitions = a few tens of MB of the table, which the L2 holds -- and every record takes its slot in its
-//     bucket (atomic cursor) and stores its entry; the table leaves the L2 as whole lines.
-constexpr int QPART_THREADS = 256;
-constexpr int QPART_ITEMS = 8;  // query positions per thread and tile
-
-__global__ void qpart_init_kernel(const uint32_t *__restrict__ off, int part_shift, uint32_t *__restrict__ part_cursor) {
-    if (threadIdx.x < QPARTS) part_cursor[threadIdx.x] = off[(uint64_t)threadIdx.x << part_shift];
-}
-
-__global__ void __launch_bounds__(QPART_THREADS) qpart_kernel(QTableArgs a) {
-    __shared__ uint32_t s_cnt[QPARTS], s_base[QPARTS];
-    const uint32_t tile = QPART_THREADS * QPART_ITEMS;
-    const uint32_t n_tiles = (a.q.total + tile - 1) / tile;
-    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        for (int i = threadIdx.x; i < QPARTS; i += QPART_THREADS) s_cnt[i] = 0;
-        __syncthreads();
-        uint32_t code[QPART_ITEMS], rank[QPART_ITEMS], ys[QPART_ITEMS], yend[QPART_ITEMS];
-        bool ok[QPART_ITEMS];
-#pragma unroll
-        for (int i = 0; i < QPART_ITEMS; i++) {
-            const uint32_t e = t * tile + i * QPART_THREADS + threadIdx.x;
-            ok[i] = e < a.q.total && query_word_at(a, e, code[i], ys[i], yend[i]);
-            if (ok[i]) rank[i] = atomicAdd(&s_cnt[code[i] >> a.part_shift], 1u);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < QPARTS; i += QPART_THREADS)
-            s_base[i] = s_cnt[i] ? atomicAdd(&a.part_cursor[i], s_cnt[i]) : 0u;
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < QPART_ITEMS; i++) {
-            if (!ok[i]) continue;
-            const uint32_t e = t * tile + i * QPART_THREADS + threadIdx.x;
-            const HitHalf h = query_half(a.q.pk, e, ys[i], yend[i], a.k);
-            uint4 *dst = reinterpret_cast<uint4 *>(a.tmp + (s_base[code[i] >> a.part_shift] + rank[i]));
-            dst[0] = make_uint4(h.f_lo, h.f_hi, h.b_lo, h.b_hi);
-            dst[1] = make_uint4(e, (uint32_t)h.froom | ((uint32_t)(h.broom + 1) << 16), code[i], 0u);  // reads <= 32767 bases
-        }
-        __syncthreads();
-    }
-}
-
-constexpr int QFILL_THREADS = 256;
-constexpr int QFILL_ITEMS = 4;  // records per thread: a block works on 1024 consecutive records
-
-__global__ void __launch_bounds__(QFILL_THREADS) qfill_kernel(QTableArgs a) {
-    const uint32_t chunk = QFILL_THREADS * QFILL_ITEMS;
-    const uint32_t n_chunks = (a.n_words + chunk - 1) / chunk;
-    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-#pragma unroll
-        for (int i = 0; i < QFILL_ITEMS; i++) {
-            const uint32_t r = c * chunk + i * QFILL_THREADS + threadIdx.x;
-            if (r >= a.n_words) continue;
-            const uint4 *src = reinterpret_cast<const uint4 *>(a.tmp + r);
-            const uint4 w0 = __ldcs(src), w1 = __ldcs(src + 1);
-            const uint32_t slot = atomicAdd(&a.cnt[w1.z], 1u);
-            uint2 *dst = reinterpret_cast<uint2 *>(a.qtab + slot);
-            dst[0] = make_uint2(w0.x, w0.y);
-            dst[1] = make_uint2(w0.z, w0.w);
-            dst[2] = make_uint2(w1.x, w1.y);
         }
     }
 }
