@@ -110,14 +110,19 @@ const char *imsame_gpu_last_cuda_error(const imsame_ctx *ctx);
 int imsame_gpu_set_stream(imsame_ctx *ctx, void *cuda_stream);
 
 /* ---- one call = src/IMSAME.c:232-281 + :409-467 ------------------------ */
-/* Host buffers in, host records out (nq entries, caller-owned). */
+/* Host buffers in, host records out (nq entries, caller-owned).  The database is uploaded on an internal copy
+ * stream one segment (2^29 bases) ahead of its scan; nothing of the caller's buffers is in flight when the call
+ * returns, whatever its result.  IMSAME_EREADSIZE exactly where the reference stops with "Read size reached for
+ * gapped alignment.": an e-value-passing hit with a read of more than IMSAME_MAX_READ_SIZE bases that its query
+ * read reaches before being accepted. */
 int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,
                      const imsame_params *params, imsame_best *out, imsame_stats *stats);
 
 /* ---- staged form (device-resident inputs; used for sharded databases) --- */
 /* upload + 2-bit pack + build the query word table (K1) */
 int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *query, const imsame_params *params);
-/* upload + 2-bit pack one database shard; stays resident until replaced */
+/* upload + 2-bit pack one database shard; stays resident until replaced.  Synchronous: the host buffers (pinned
+ * or pageable) may be refilled or freed as soon as it returns; the same holds for imsame_gpu_set_query. */
 int imsame_gpu_set_db(imsame_ctx *ctx, const imsame_seqinfo *db);
 /* scan + extension + NW + filter over the resident shard. Results stay on the
  * device as one packed key per read (smaller = earlier in the reference's scan
