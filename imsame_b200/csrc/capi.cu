@@ -27,7 +27,7 @@ constexpr uint64_t SEG_MAX_BASES = 1ull << 29;    // database segment size (posi
 constexpr uint64_t STAGE_BYTES = 256ull << 20;    // ASCII staging buffer on the device
 constexpr uint64_t PIN_BYTES = 32ull << 20;       // pinned bounce buffers for pageable host input (two of them)
 constexpr uint32_t PAD_WORDS = 16;                // zero words after every packed array
-constexpr uint32_t BINS_STRIDE = 6 * NW_NBINS + 8;
+constexpr uint32_t BINS_STRIDE = 7 * NW_NBINS + 8;
 
 struct Seg {
     uint64_t pos_base = 0, seq_base = 0;  // offsets inside the shard handed to set_db
@@ -95,6 +95,7 @@ struct imsame_ctx {
     int comm_rank = 0, comm_size = 1;
     unsigned long long *comm_flag = nullptr;  // one device word for status / read-size reductions
     bool table_dirty = false;  // the pair table may hold entries of a run that failed before they were binned
+    // (after the launch ranges: NBINS more work heads, for the second kernel of a mixed run)
     // per segment (stride BINS_STRIDE): [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors |
     // NBINS work heads | 2*NBINS launch ranges
     uint32_t *d_bins = nullptr;
@@ -472,14 +473,19 @@ bool use_packed(const imsame_ctx *ctx, uint32_t xmax, uint32_t ymax, int igap, i
 
 // unsorted explicit pairs: every class kernel walks the whole list and skips the other classes
 template <bool TB>
-int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 9 zeroed */,
-                      bool packed = false) {
+int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 18 zeroed */,
+                      bool packed = false, bool mixed = false) {
     int rc = IMSAME_OK;
     a.check_class = 1;
+    a.mixed = (mixed && !packed && !TB) ? 1 : 0;
     for (int c = 1; c <= 8 && !rc; c++) {
         if (!(class_mask & (1u << c))) continue;
         a.work = work_heads + c;
-        rc = (packed && !TB) ? launch_nwp_class(ctx, a, c) : launch_nw_class<TB>(ctx, a, c);
+        if ((packed || a.mixed) && !TB) rc = launch_nwp_class(ctx, a, c);
+        if (!rc && (!packed || TB)) {
+            if (a.mixed) a.work = work_heads + 9 + c;
+            rc = launch_nw_class<TB>(ctx, a, c);
+        }
     }
     return rc;
 }
@@ -1058,12 +1064,20 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
     a.tb = nullptr; a.tb_off = nullptr; a.check_class = 0;
     int rc;
     const bool packed = use_packed(ctx, ctx->db_maxlen, ctx->q_maxlen, p->igap, p->egap);
+    // some reads too long for packed words: the two kernels share every bin, pair by pair (NwArgs.mixed)
+    const bool mixed = !packed && ctx->nw_mode != 1 && p->igap <= 0 && p->egap <= 0;
+    uint32_t *bin_work2 = bins + 6 * NW_NBINS + 8;
+    a.mixed = mixed ? 1 : 0;
     for (int c = 1; c <= 8; c++) {
         if (!(ctx->class_mask & (1u << c))) continue;
         const int bin = c * NW_BANDS + band;
         a.range = launch_range + 2 * bin;
         a.work = bin_work + bin;
-        if ((rc = packed ? launch_nwp_class(ctx, a, c) : launch_nw_class<false>(ctx, a, c))) return rc;
+        if (packed || mixed) { if ((rc = launch_nwp_class(ctx, a, c))) return rc; }
+        if (!packed) {
+            if (mixed) a.work = bin_work2 + bin;
+            if ((rc = launch_nw_class<false>(ctx, a, c))) return rc;
+        }
     }
     return IMSAME_OK;
 }
@@ -1344,7 +1358,7 @@ struct PairBatch {
         const uint64_t xw = (xt + 15) / 16 + PAD_WORDS, yw = (yt + 15) / 16 + PAD_WORDS;
         if ((rc = pool_alloc(ctx, &xpk, xw)) || (rc = pool_alloc(ctx, &ypk, yw)) ||
             (rc = pool_alloc(ctx, &dxs, (uint64_t)n + 1)) || (rc = pool_alloc(ctx, &dys, (uint64_t)n + 1)) ||
-            (rc = pool_alloc(ctx, &dsmall, 16)) || (rc = pool_alloc(ctx, &dp, n)) || (rc = pool_alloc(ctx, &dr, n)) ||
+            (rc = pool_alloc(ctx, &dsmall, 32)) || (rc = pool_alloc(ctx, &dp, n)) || (rc = pool_alloc(ctx, &dr, n)) ||
             (rc = pool_alloc(ctx, &dz, 2 * IMSAME_MAX_READ_SIZE + 1)) || (rc = pool_alloc(ctx, &dcells, 4)))
             return rc;
         CK(cudaMemsetAsync(xpk, 0, xw * 4, ctx->stream));
@@ -1356,7 +1370,7 @@ struct PairBatch {
         if ((rc = upload_pack(ctx, ya.data(), yt, ypk, PH_PACKQ))) return rc;
         std::vector<PairRec> hp(n);
         for (uint32_t i = 0; i < n; i++) { hp[i].r = i; hp[i].s = i; hp[i].key = 0; }
-        uint32_t small[16] = {0};
+        uint32_t small[32] = {0};
         small[1] = n;  // range = [0, n); small[4..] = per-class work heads
         CK(cudaMemcpyAsync(dxs, xs.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(dys, ys.data(), ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1373,6 +1387,7 @@ struct PairBatch {
         a.lmin = dz; a.imin = dz; a.best = nullptr; a.cells = dcells; a.carry = ctx->carry; a.s_class = 0;
         a.tb = nullptr; a.tb_off = nullptr;
         a.check_class = 1;
+        a.mixed = 0;
         return a;
     }
 };
@@ -1396,7 +1411,8 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
-    rc = launch_nw_classes<false>(ctx, a, pb.class_mask, pb.dsmall + 4, use_packed(ctx, pb.xmax, pb.ymax, igap, egap));
+    rc = launch_nw_classes<false>(ctx, a, pb.class_mask, pb.dsmall + 4, use_packed(ctx, pb.xmax, pb.ymax, igap, egap),
+                                  ctx->nw_mode != 1 && igap <= 0 && egap <= 0);
     cudaEventRecord(e1, ctx->stream);
     std::vector<PairRes> hr(n_pairs);
     if (!rc) {

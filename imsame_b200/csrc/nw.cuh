@@ -7,6 +7,7 @@
 // Integer ALU work only: no tensor cores (irregular max/select recurrence).
 #pragma once
 #include "nw_core.cuh"
+#include "nwp_core.cuh"  // pw_pair_eligible: which pairs the packed-word kernel takes in a mixed run
 #include "traceback.cuh"
 
 namespace imsame {
@@ -44,6 +45,10 @@ struct NwArgs {
     const uint32_t *range;
     int check_class;  // 1: unsorted explicit pairs (nw_batch / traceback): skip other classes here
     int one;          // 1, as a run-time value (nwp_core.cuh: pw_row)
+    // 1: the work range is shared between the two kernels (a run whose longest reads do not fit packed words):
+    // nwp_kernel takes the pairs that do (pw_eligible on the pair's own lengths), nw_kernel the others; each kernel
+    // walks the whole range with its own work-queue head and skips the other's pairs without touching them
+    int mixed;
     // TB = true only (K4, winners-only traceback): back-pointer codes per cell
     uint16_t *tb;              // codes of pair idx start at tb + tb_off[idx]
     const uint64_t *tb_off;
@@ -86,6 +91,11 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
         const uint32_t ys = read_start(a.q, pr.r);
         const uint32_t ylen = (a.q.fixed_len ? a.q.fixed_len : a.q.start[pr.r + 1] - ys);
         if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
+        if (a.mixed) {  // the packed-word kernel's pair?
+            const uint32_t xs_ = read_start(a.db, pr.s);
+            const uint32_t xlen_ = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs_);
+            if (pw_pair_eligible(xlen_, ylen, a.igap, a.egap)) continue;
+        }
         // an earlier hit of this read is already accepted?  best[] is lowered by other warps meanwhile: one lane
         // reads it, so that the whole warp takes the same branch
         int pruned_w = 0;

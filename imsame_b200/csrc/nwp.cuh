@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(NWP_THREADS, 2) nwp_kernel(NwArgs a) {
             if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
             xs = read_start(a.db, pr.s);
             xlen = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs);
+            if (a.mixed && !pw_pair_eligible(xlen, ylen, a.igap, a.egap)) continue;  // the generic kernel's pair
             // an earlier hit of this read is accepted?  best[] is lowered by other warps meanwhile: one lane of
             // the half reads it, so that all 16 lanes take the same branch
             int pruned_h = 0;

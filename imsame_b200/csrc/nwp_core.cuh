@@ -95,6 +95,11 @@ IMS_HD bool pw_eligible(uint32_t xmax, uint32_t ymax, int igap, int egap) {
     return true;
 }
 
+// the same test on ONE pair's own lengths (mixed runs: NwArgs.mixed)
+IMS_HD bool pw_pair_eligible(uint32_t xlen, uint32_t ylen, int igap, int egap) {
+    return xlen >= 2 && ylen >= 2 && pw_eligible(xlen, ylen, igap, egap);
+}
+
 struct PwLink {
     int a;    // T'[i][j0-1]
     int b;    // T'[i][j0-2]

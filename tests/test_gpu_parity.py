@@ -93,6 +93,31 @@ def test_read_longer_than_the_scan_limit_is_refused(gpu):
     assert int(out["accepted"].sum()) == 1  # the context is still usable
 
 
+def test_mixed_run_shares_the_bins_between_both_nw_kernels(gpu):
+    """a run in which SOME reads are too long for packed words (here: query reads of 20..400 bases, database reads up
+    to 600): pair by pair, the packed-word kernel takes what fits (<= 257 query / 512 database bases) and the generic
+    kernel the rest -- records equal the oracle's, and equal the all-generic run"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.ragged_case(808, 3, 60000, 6000, 900, 0.04, lo=20, hi=400)
+    # stretch a few database reads beyond 512 bases by merging neighbours
+    keep = np.ones(len(ds), dtype=bool)
+    keep[np.arange(5, len(ds) - 1, 37)] = False
+    ds2 = ds[keep]
+    assert int(np.diff(ds2).max()) > 512
+    p = api.make_params(n_threads=4)
+    want, _ = oracle_records(db, ds2, q, qs, 4)
+    out, st = gpu.align((db, ds2), (q, qs), p)
+    assert 0 < st["k3_packed_launches"] < st["k3_launches"]
+    assert gpu_records(out) == want and len(want) > 200
+    gpu.set_nw_mode(1)
+    try:
+        out_g, st_g = gpu.align((db, ds2), (q, qs), p)
+    finally:
+        gpu.set_nw_mode(0)
+    assert st_g["k3_packed_launches"] == 0 and gpu_records(out_g) == want
+    assert st_g["n_cells"] == st["n_cells"] and st_g["n_pairs_dp"] == st["n_pairs_dp"]
+
+
 def test_pair_table_growth_gives_the_same_records(monkeypatch):
     """the candidate pair table overflows and is grown (the segment is scanned again) until it holds every
     (read, database read) pair: a fresh context starts at 256 slots through the test hook IMSAME_TEST_PAIR_SLOTS"""
