@@ -202,10 +202,10 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
                         const uint32_t *xlen, const unsigned char *const *Y, const uint32_t *ylen,
                         int igap, int egap, int32_t *out5, float *ms_kernel);
 
-/* Which K3 kernel evaluates the pairs: 0 (default) = the packed-word kernel whenever every read
- * of the run is short enough for it (<= 257 query / 512 database bases, non-positive gap scores;
- * nwp_core.cuh: pw_eligible), the generic kernel otherwise; 1 = always the generic kernel.  Both
- * give identical results; the switch exists so tests and benchmarks can compare them. */
+/* Which K3 kernel evaluates the pairs: 0 (default) = the packed-word kernel for every pair that fits it
+ * (<= 257 query / 512 database bases, non-positive gap scores; nwp_core.cuh: pw_eligible) and the generic
+ * kernel for the others, pair by pair; 1 = always the generic kernel.  Both give identical results; the
+ * switch exists so tests and benchmarks can compare them. */
 int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode);
 
 /* Seed length k.  The reference has exactly one: FIXED_K = 12 (src/structs.h:15),
