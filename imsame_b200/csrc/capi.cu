@@ -110,8 +110,8 @@ struct imsame_ctx {
     uint8_t *pin[2] = {nullptr, nullptr};  // pinned bounce buffers (upload_pack), their copy-done events
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     bool pin_busy[2] = {false, false};     // a copy out of the buffer has been enqueued (wait for pin_ev before refilling)
-    int nw_grid[9] = {0};
-    int nwp_grid[9] = {0};
+    int nw_grid[9] = {0};                 // by columns per lane (1..8)
+    int nwp_grid[NW_CLASSES + 1] = {0};   // by NW class
     bool in_align = false;  // imsame_gpu_align: upload phases belong to the same stats
     int nw_mode = 0;  // 0: packed-word kernel where pw_eligible() holds, 1: generic kernel only
     int k = K;        // seed length (imsame_gpu_set_kmer); k_tables = the length off/cursor/tile_sums are sized for
@@ -422,7 +422,7 @@ int launch_nw(imsame_ctx *ctx, NwArgs a) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<S, false>, NW_THREADS, 0));
         ctx->nw_grid[S] = std::max(1, per_sm) * ctx->n_sm;
     }
-    a.s_class = S;
+    if (!a.s_class) a.s_class = S;
     nw_kernel<S, TB><<<ctx->nw_grid[S], NW_THREADS, 0, ctx->stream>>>(a);
     ctx->launches++;
     ctx->k3_launches++;
@@ -431,10 +431,11 @@ int launch_nw(imsame_ctx *ctx, NwArgs a) {
 }
 
 template <bool TB>
-int launch_nw_class(imsame_ctx *ctx, const NwArgs &a, int c) {
+int launch_nw_class(imsame_ctx *ctx, NwArgs a, int c) {
     int rc = IMSAME_OK;
     {
-        switch (c) {
+        a.s_class = c;
+        switch (nw_class_cols(c)) {  // columns per lane of the class (classes 9 and 10: two passes of 5)
             case 1: rc = launch_nw<1, TB>(ctx, a); break;
             case 2: rc = launch_nw<2, TB>(ctx, a); break;
             case 3: rc = launch_nw<3, TB>(ctx, a); break;
@@ -451,7 +452,7 @@ int launch_nw_class(imsame_ctx *ctx, const NwArgs &a, int c) {
 // packed-word kernel (nwp.cuh) of NW class c; its ~150 instantiations live in their own translation unit
 // (nwp_launch.cu) so that the two halves of the library compile side by side
 int launch_nwp_class(imsame_ctx *ctx, NwArgs a, int c) {
-    c = c < 1 ? 1 : (c > 8 ? 8 : c);
+    c = c < 1 ? 1 : (c > NW_CLASSES ? NW_CLASSES : c);
     if (!ctx->nwp_grid[c]) {
         const int per_sm = nwp_blocks_per_sm(c);
         if (per_sm < 0) { ctx->cuda_err = "cudaOccupancyMaxActiveBlocksPerMultiprocessor(nwp_kernel)"; return IMSAME_ECUDA; }
@@ -473,17 +474,17 @@ bool use_packed(const imsame_ctx *ctx, uint32_t xmax, uint32_t ymax, int igap, i
 
 // unsorted explicit pairs: every class kernel walks the whole list and skips the other classes
 template <bool TB>
-int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 18 zeroed */,
+int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 2 * (NW_CLASSES + 1) zeroed */,
                       bool packed = false, bool mixed = false) {
     int rc = IMSAME_OK;
     a.check_class = 1;
     a.mixed = (mixed && !packed && !TB) ? 1 : 0;
-    for (int c = 1; c <= 8 && !rc; c++) {
+    for (int c = 1; c <= NW_CLASSES && !rc; c++) {
         if (!(class_mask & (1u << c))) continue;
         a.work = work_heads + c;
         if ((packed || a.mixed) && !TB) rc = launch_nwp_class(ctx, a, c);
         if (!rc && (!packed || TB)) {
-            if (a.mixed) a.work = work_heads + 9 + c;
+            if (a.mixed) a.work = work_heads + NW_CLASSES + 1 + c;
             rc = launch_nw_class<TB>(ctx, a, c);
         }
     }
@@ -492,19 +493,35 @@ int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *
 
 int max_nw_grid(imsame_ctx *ctx) {
     int g = 0;
-    for (int c = 1; c <= 8; c++) g = std::max(g, std::max(ctx->nw_grid[c], 2 * ctx->nwp_grid[c]));
+    for (int c = 1; c <= 8; c++) g = std::max(g, ctx->nw_grid[c]);
+    for (int c = 1; c <= NW_CLASSES; c++) g = std::max(g, 2 * ctx->nwp_grid[c]);
     return g ? g : ctx->n_sm * 8;
 }
 
 int ensure_carry(imsame_ctx *ctx, uint32_t max_ylen) {
     if (max_ylen <= 32 * 8 + 1) return IMSAME_OK;
-    // the S = 8 kernel is the only one that runs multi-pass
+    // the kernels with 5..8 columns per lane run multi-pass (nw_class_of: balanced passes)
+    if (!ctx->nw_grid[5]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<5, false>, NW_THREADS, 0));
+        ctx->nw_grid[5] = std::max(1, per_sm) * ctx->n_sm;
+    }
+    if (!ctx->nw_grid[6]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<6, false>, NW_THREADS, 0));
+        ctx->nw_grid[6] = std::max(1, per_sm) * ctx->n_sm;
+    }
+    if (!ctx->nw_grid[7]) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<7, false>, NW_THREADS, 0));
+        ctx->nw_grid[7] = std::max(1, per_sm) * ctx->n_sm;
+    }
     if (!ctx->nw_grid[8]) {
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_kernel<8, false>, NW_THREADS, 0));
         ctx->nw_grid[8] = std::max(1, per_sm) * ctx->n_sm;
     }
-    const uint64_t warps = (uint64_t)ctx->nw_grid[8] * NW_WARPS;
+    const uint64_t warps = (uint64_t)std::max(std::max(ctx->nw_grid[5], ctx->nw_grid[6]), std::max(ctx->nw_grid[7], ctx->nw_grid[8])) * NW_WARPS;
     if (warps > ctx->carry_warps) {
         dev_free(ctx->carry);
         int rc = dev_alloc(ctx, &ctx->carry, warps * 2 * MAX_READ);
@@ -1068,7 +1085,7 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
     const bool mixed = !packed && ctx->nw_mode != 1 && p->igap <= 0 && p->egap <= 0;
     uint32_t *bin_work2 = bins + 6 * NW_NBINS + 8;
     a.mixed = mixed ? 1 : 0;
-    for (int c = 1; c <= 8; c++) {
+    for (int c = 1; c <= NW_CLASSES; c++) {
         if (!(ctx->class_mask & (1u << c))) continue;
         const int bin = c * NW_BANDS + band;
         a.range = launch_range + 2 * bin;

@@ -36,7 +36,7 @@ struct NwArgs {
     unsigned long long *best;  // per read scan-order key (atomicMin); may be null (nw_batch)
     unsigned long long *cells;  // [0] cells, [2] pairs evaluated
     NwLink *carry;             // 2 * MAX_READ links per warp of the grid, or null
-    int s_class;               // pairs with min(ceil((ylen-1)/32), 8) != s_class are skipped
+    int s_class;               // check_class: pairs with nw_class_of(ylen) != s_class are skipped
     // Work range: pairs[range[0] .. range[1]) (device-resident offsets written by the binning
     // kernels).  The scan orders candidates into (NW class, k-mer-end band) bins and the bins of
     // a class are launched in ascending band order: the reference stops at a read's first
@@ -54,10 +54,24 @@ struct NwArgs {
     const uint64_t *tb_off;
 };
 
+// NW class of a query read = the bin its candidates are sorted into and the kernel instantiation that aligns them.
+//   1..8   Y1 = ylen - 1 <= 255 columns: c = ceil(Y1 / 32); generic kernel c columns per lane, packed 2c per lane
+//   9, 10  Y1 <= 288 / 320: packed-word kernel with 18 / 20 columns per lane (nwp_core.cuh, "wide reads"); pairs
+//          it cannot take run in the generic kernel in two balanced passes of 5 columns per lane
+//   longer reads: P = ceil(Y1 / 256) passes of the generic kernel, columns per lane chosen so that the passes are
+//          balanced (class = ceil(Y1 / 32P) = 6..8).  With 8 columns per lane whatever the length, a 300-base
+//          query read ran one full pass and one pass on 6 lanes of 32: 55 % of the lane-steps did work, now 85 %
+constexpr int NW_CLASSES = 10;
 IMS_HD int nw_class_of(uint32_t ylen) {
-    int c = ((int)ylen - 1 + 31) / 32;
-    return c < 1 ? 1 : (c > 8 ? 8 : c);
+    const int y1 = (int)ylen - 1;
+    if (y1 <= 255) { const int c = (y1 + 31) / 32; return c < 1 ? 1 : c; }
+    if (y1 <= 288) return 9;
+    if (y1 <= 320) return 10;
+    const int passes = (y1 + 255) / 256;
+    return (y1 + 32 * passes - 1) / (32 * passes);
 }
+// columns per lane of the generic kernel that aligns class c
+IMS_HD int nw_class_cols(int c) { return c <= 8 ? c : 5; }
 
 #if defined(__CUDACC__)
 

@@ -38,6 +38,23 @@
 // scores incl. the transient gap candidates inside 12 bits.  Everything else
 // runs through nw_core.cuh.  Tested bit for bit against the oracle on the CPU
 // (tests/emul/nwp_emul.cpp) and on the GPU (tests/test_gpu_parity.py).
+//
+// Wide reads (query reads of 257..321 bases, e.g. 2 x 300 sequencing: NW classes
+// 9 and 10, 18 / 20 columns per lane).  Score (12 bits), priority (2) and length
+// (10) still fit, the identities can reach 320 and would need a 33rd bit.  They
+// do not get one: the statistics never decide a comparison (see above), so the
+// low 18 bits are simply the integer V = 256 * length + identities carried along
+// the chosen path, exact as long as V < 2^18, and the only question is how V
+// splits at the end.  identities < 512 leaves two readings, (V >> 8, V & 255)
+// and (V >> 8) - 1, (V & 255) + 256).  pw_split_stats() rules one out from the
+// geometry of the path that ends in the best cell (identities are diagonal
+// steps: at most min(bi, bj), at most the columns, and a path with d diagonal
+// steps into (bi, bj) has at most bi + bj - d columns), which settles every
+// pair with fewer than 256 identities whose second reading would need more
+// diagonal steps than the matrix has -- all random pairs.  What stays open
+// (near-complete overlaps: 256 or more identities) is run once more with the
+// length unit set to 0 (pw_consts(..., lenu = 0)): the same path, the low bits
+// now the identities alone; the length follows from V.
 #pragma once
 #include "nw_core.cuh"
 
@@ -50,9 +67,11 @@ constexpr int PW_LOW = PW_SC1 - 1;   // id | len | prio
 constexpr int PW_SMASK = ~PW_LOW;    // score field
 constexpr int PW_PRMASK = 3 * PW_PR1;
 constexpr int PW_LANES = 16;         // lanes per pair (half a warp)
-constexpr int PW_MAX_S = 16;         // columns per lane
-constexpr int PW_MAX_Y = PW_LANES * PW_MAX_S + 1;  // 257: Y1 <= 256 columns in one pass
+constexpr int PW_MAX_S = 20;         // columns per lane (17..20: wide reads, see above)
+constexpr int PW_MAX_Y = PW_LANES * PW_MAX_S + 1;  // 321: Y1 <= 320 columns in one pass
+constexpr int PW_NARROW_Y1 = 255;    // up to here min(X1, Y1) <= 255 whatever the database read: 8-bit identities
 constexpr int PW_MAX_X = 512;
+constexpr uint32_t PW_VMASK = (1u << 18) - 1u;  // V = 256 * length + identities
 
 // per-run constants (functions of igap / egap only)
 struct PwK {
@@ -66,15 +85,17 @@ struct PwK {
     int one;      // 1, opaque to the compiler on the device (pw_row: diagonal add as IMAD)
 };
 
-IMS_HD PwK pw_consts(int igap, int egap, int one = 1) {
+// lenu: what one alignment column adds to the statistics bits (PW_LEN1; 0 = carry the identities alone, the
+// second run of a wide pair whose statistics did not split)
+IMS_HD PwK pw_consts(int igap, int egap, int one = 1, int lenu = PW_LEN1) {
     PwK k;
     k.one = one;
-    k.B = (igap + egap) * PW_SC1 + 2 * PW_LEN1 + PW_PR1;
-    k.step = egap * PW_SC1 + PW_LEN1;
+    k.B = (igap + egap) * PW_SC1 + 2 * lenu + PW_PR1;
+    k.step = egap * PW_SC1 + lenu;
     k.negz = -2046 * PW_SC1;
     k.negb = -2047 * PW_SC1;
     k.negl = -1900 * PW_SC1;
-    k.ds_mis = PW_LEN1 + 2 * PW_PR1 - k.B;
+    k.ds_mis = lenu + 2 * PW_PR1 - k.B;
     k.sb_mis = -NW_POINT * PW_SC1 + k.B;
     return k;
 }
@@ -86,8 +107,10 @@ IMS_HD bool pw_eligible(uint32_t xmax, uint32_t ymax, int igap, int egap) {
     if (ymax > (uint32_t)PW_MAX_Y || xmax > (uint32_t)PW_MAX_X) return false;
     const int X1 = (int)xmax - 1, Y1 = (int)ymax - 1;
     const int mn = X1 < Y1 ? X1 : Y1, mx = X1 < Y1 ? Y1 : X1;
-    if (mn > 255) return false;                          // identities <= diagonal steps <= min(X1, Y1)
-    if (X1 + Y1 + 2 > 1023) return false;                // columns on a path <= X1 + Y1, + 2 of bias
+    // identities <= diagonal steps <= min(X1, Y1): 8 bits up to Y1 = 255 (the classes 1..8 kernels split V
+    // as it is), one carry into the length field beyond (classes 9, 10: pw_split_stats)
+    if (mn > 511) return false;
+    if (X1 + Y1 + 3 > 1023) return false;                // columns on a path <= X1 + Y1, + 2 of bias, + 1 carry
     // |T| <= 4 (min(i,j) + 1); gap candidates fall at most |igap| + |egap| (mx + 3) below that
     const long lo = 4L * (mn + 1) + (long)(-igap) + (long)(-egap) * (mx + 3) + 24;
     if (lo > 1890) return false;                         // stays above negl (and its one STEP)
@@ -95,6 +118,8 @@ IMS_HD bool pw_eligible(uint32_t xmax, uint32_t ymax, int igap, int egap) {
     return true;
 }
 
+// (the bound is monotone in both lengths and Y1 <= 255 implies min(X1, Y1) <= 255: a run whose longest reads
+// pass consists of pairs that pass, each in the kernel of its own class)
 // the same test on ONE pair's own lengths (mixed runs: NwArgs.mixed)
 IMS_HD bool pw_pair_eligible(uint32_t xlen, uint32_t ylen, int igap, int egap) {
     return xlen >= 2 && ylen >= 2 && pw_eligible(xlen, ylen, igap, egap);
@@ -234,6 +259,7 @@ IMS_HD void pw_row(PwLane<S> &L, const PwRow<S> &P1, PwRow<S> &P2, const PwLink 
 #define IMS_CASE(C) case C: if (C < S) lt = P2.h[(C < S ? C : 0) + 1]; break;
             IMS_CASE(0) IMS_CASE(1) IMS_CASE(2) IMS_CASE(3) IMS_CASE(4) IMS_CASE(5) IMS_CASE(6) IMS_CASE(7)
             IMS_CASE(8) IMS_CASE(9) IMS_CASE(10) IMS_CASE(11) IMS_CASE(12) IMS_CASE(13) IMS_CASE(14)
+            IMS_CASE(15) IMS_CASE(16) IMS_CASE(17) IMS_CASE(18)
 #undef IMS_CASE
             default: break;
         }
@@ -257,5 +283,19 @@ IMS_HD void pw_last_row(PwLane<S> &L, const PwRow<S> &row, int j0, int X1, int Y
 IMS_HD int pw_score(const PwK &k, int w) { return (w - k.B) >> 20; }
 IMS_HD uint32_t pw_len(const PwK &k, int w) { return ((uint32_t)(w - k.B) >> 8) & 1023u; }
 IMS_HD uint32_t pw_ids(const PwK &k, int w) { return (uint32_t)(w - k.B) & 255u; }
+IMS_HD uint32_t pw_stats(const PwK &k, int w) { return (uint32_t)(w - k.B) & PW_VMASK; }  // V (or, lenu = 0, the identities)
+
+// Wide reads: V = 256 * length + identities of the path into the best cell (bi, bj), identities < 512.
+// Returns false with the one split the path's geometry admits, true when both readings are possible (the
+// pair is then run again with lenu = 0).
+IMS_HD bool pw_split_stats(uint32_t V, int bi, int bj, uint32_t *len, uint32_t *id) {
+    const uint32_t f = V >> 8, id0 = V & 255u, id1 = id0 + 256u;
+    const uint32_t m = (uint32_t)(bi < bj ? bi : bj), span = (uint32_t)(bi + bj);
+    const bool can0 = id0 <= m && id0 <= f && f + id0 <= span;
+    const bool can1 = f >= 1 && id1 <= m && id1 <= f - 1 && (f - 1) + id1 <= span;
+    if (can1 && !can0) { *len = f - 1; *id = id1; return false; }
+    *len = f; *id = id0;
+    return can0 && can1;
+}
 
 }  // namespace imsame

@@ -1,6 +1,6 @@
-// nwp_launch.cu -- instantiations of nwp_kernel<S, CL> (nwp.cuh): S = 2 * class columns per lane, CL = register
-// slot of the last query column (or -1: decided at run time).  A translation unit of its own: these ~150 kernels
-// are most of the library's compile time.
+// nwp_launch.cu -- instantiations of nwp_kernel<S, CL> (nwp.cuh): S columns per lane (2 * class for the classes
+// 1..8, 18 and 20 for the wide classes 9 and 10), CL = register slot of the last query column (or -1: decided at
+// run time).  A translation unit of its own: these ~190 kernels are most of the library's compile time.
 #include "nwp_launch.h"
 #include "nwp.cuh"
 
@@ -8,28 +8,32 @@ namespace imsame {
 
 namespace {
 
-template <int C, int CL>
+constexpr int cols_of_class(int c) { return 2 * c; }  // 2, 4, .. 16 and 18, 20 (wide)
+
+template <int S, int CL>
 void launch_variant(int grid, cudaStream_t stream, const NwArgs &a, int cl) {
     if (cl == CL) {
-        nwp_kernel<2 * C, CL><<<grid, NWP_THREADS, 0, stream>>>(a);
+        nwp_kernel<S, CL><<<grid, nwp_threads(S), 0, stream>>>(a);
         return;
     }
-    if constexpr (CL + 1 < 2 * C) launch_variant<C, CL + 1>(grid, stream, a, cl);
-    else nwp_kernel<2 * C, -1><<<grid, NWP_THREADS, 0, stream>>>(a);
+    if constexpr (CL + 1 < S) launch_variant<S, CL + 1>(grid, stream, a, cl);
+    else nwp_kernel<S, -1><<<grid, nwp_threads(S), 0, stream>>>(a);
 }
 
 template <int C>
 void launch_class(int grid, cudaStream_t stream, const NwArgs &a) {
+    constexpr int S = cols_of_class(C);
     int cl = -1;
-    if (a.q.fixed_len >= 2 && !a.check_class && nw_class_of(a.q.fixed_len) == C) cl = (int)((a.q.fixed_len - 2) % (2 * C));
-    if (cl >= 0) launch_variant<C, 0>(grid, stream, a, cl);
-    else nwp_kernel<2 * C, -1><<<grid, NWP_THREADS, 0, stream>>>(a);
+    if (a.q.fixed_len >= 2 && !a.check_class && nw_class_of(a.q.fixed_len) == C) cl = (int)((a.q.fixed_len - 2) % S);
+    if (cl >= 0) launch_variant<S, 0>(grid, stream, a, cl);
+    else nwp_kernel<S, -1><<<grid, nwp_threads(S), 0, stream>>>(a);
 }
 
 template <int C>
 int blocks_per_sm() {
+    constexpr int S = cols_of_class(C);
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nwp_kernel<2 * C, -1>, NWP_THREADS, 0) != cudaSuccess) return -1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nwp_kernel<S, -1>, nwp_threads(S), 0) != cudaSuccess) return -1;
     return per_sm;
 }
 
@@ -44,7 +48,9 @@ int nwp_blocks_per_sm(int c) {
         case 5: return blocks_per_sm<5>();
         case 6: return blocks_per_sm<6>();
         case 7: return blocks_per_sm<7>();
-        default: return blocks_per_sm<8>();
+        case 8: return blocks_per_sm<8>();
+        case 9: return blocks_per_sm<9>();
+        default: return blocks_per_sm<10>();
     }
 }
 
@@ -57,7 +63,9 @@ void nwp_launch(int c, int grid, cudaStream_t stream, const NwArgs &a) {
         case 5: launch_class<5>(grid, stream, a); break;
         case 6: launch_class<6>(grid, stream, a); break;
         case 7: launch_class<7>(grid, stream, a); break;
-        default: launch_class<8>(grid, stream, a); break;
+        case 8: launch_class<8>(grid, stream, a); break;
+        case 9: launch_class<9>(grid, stream, a); break;
+        default: launch_class<10>(grid, stream, a); break;
     }
 }
 

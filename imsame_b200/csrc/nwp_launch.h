@@ -6,7 +6,7 @@
 
 namespace imsame {
 
-// resident blocks per SM of the class-c kernel (16 lanes x 2c columns per pair), < 0 on a CUDA error
+// resident blocks per SM of the class-c kernel (16 lanes x 2c columns per pair; c = 1..NW_CLASSES), < 0 on a CUDA error
 int nwp_blocks_per_sm(int c);
 // launch the class-c kernel; when every query read of the run has the same length (a.q.fixed_len) the
 // variant with the last column's register slot compiled in is chosen

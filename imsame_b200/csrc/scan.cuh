@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
 // histogram of the occupied slots per bin, exclusive scan of the NBINS counters, scatter with
 // block-aggregated atomics (one global atomic per bin per block); the scatter also resets the table.
 constexpr int NW_BANDS = 32;
-constexpr int NW_NBINS = 9 * NW_BANDS;  // classes 1..8
+constexpr int NW_NBINS = (NW_CLASSES + 1) * NW_BANDS;  // classes 1..NW_CLASSES (nw_class_of)
 constexpr int BIN_THREADS = 256;
 constexpr int BIN_ITEMS = 16;  // slots per thread
 
@@ -407,7 +407,7 @@ __global__ void bin_offsets_kernel(const uint32_t *bin_count, uint32_t *bin_off,
         uint32_t launches = (acc - base) / (min_per_launch ? min_per_launch : 1u);
         launches = launches < 1u ? 1u : (launches > (uint32_t)NW_BANDS ? (uint32_t)NW_BANDS : launches);
         const uint32_t merge = ((uint32_t)NW_BANDS + launches - 1) / launches;  // bands per launch
-        for (int c = 0; c < 9; c++)
+        for (int c = 0; c <= NW_CLASSES; c++)
             for (uint32_t b = 0; b < (uint32_t)NW_BANDS; b++) {
                 const uint32_t lo = b * merge, hi = (b + 1) * merge;
                 const uint32_t b0 = lo < (uint32_t)NW_BANDS ? lo : (uint32_t)NW_BANDS;

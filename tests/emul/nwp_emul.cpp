@@ -2,7 +2,10 @@
 // stepped in lockstep, neighbour hand-over = value of the previous step.  Checks
 // imsame::pw_row / pw_lane_init against the oracle's forward NW, bit for bit, on every pair
 // that pw_eligible admits (and checks that the eligibility bound is what keeps it exact by
-// also running pairs at the edge of the admitted range).
+// also running pairs at the edge of the admitted range).  Wide reads (query reads of 257..321 bases,
+// 18 / 20 columns per lane): the statistics word V = 256 * length + identities is split by
+// pw_split_stats and, where both splits are possible, the pair is run again with length unit 0 --
+// the kernel's epilogue, step for step.
 //   usage: nwp_emul <n_cases> <seed>
 #include <cstdio>
 #include <cstdlib>
@@ -21,16 +24,19 @@ static inline uint32_t code(unsigned char c) { return (c >> 1) & 3; }
 struct Res { int s, i, j; uint32_t len, id; };
 
 struct HostEW {
-    const PwK *k; uint32_t mm;
+    const PwK *k; uint64_t mm;
     PwE4 operator()(int g) const { return pw_e4(*k, (mm >> (8 * g)) & 0xFFu); }
 };
 
+static int n_again = 0, n_wide = 0;
+
+struct Raw { bool have; int bw, bi, bj; };
+
 template <int S>
-static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
+static Raw run_raw(const unsigned char *X, int xlen, const unsigned char *Y, int ylen, const PwK &k) {
     const int X1 = xlen - 1, Y1 = ylen - 1;
-    const PwK k = pw_consts(igap, egap);
-    Res best; best.s = NW_NEG * 2; best.i = best.j = 0; best.len = best.id = 0;
-    if (X1 < 1 || Y1 < 1) return best;
+    Raw raw; raw.have = false; raw.bw = raw.bi = raw.bj = 0;
+    if (X1 < 1 || Y1 < 1) return raw;
     const int nl = (Y1 + S - 1) / S;
     if (nl > PW_LANES) { fprintf(stderr, "bad S\n"); exit(2); }
     PwLane<S> lanes[PW_LANES]; PwLink outs[PW_LANES];
@@ -46,8 +52,8 @@ static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, in
             if (i < 1 || i > X1) continue;
             int j0 = l * S + 1;
             PwLink in = (l == 0) ? pw_first_link(k, code(X[i]), code(Y[0])) : outs[l - 1];
-            uint32_t mm = 0;
-            for (int c = 0; c < S; c++) { int j = j0 + c; uint32_t y = j < ylen ? code(Y[j]) : (uint32_t)(rnd() & 3); if (y != code(X[i])) mm |= 1u << (2 * c); }
+            uint64_t mm = 0;
+            for (int c = 0; c < S; c++) { int j = j0 + c; uint32_t y = j < ylen ? code(Y[j]) : (uint32_t)(rnd() & 3); if (y != code(X[i])) mm |= 1ull << (2 * c); }
             HostEW ew{&k, mm};
             PwLink out;
             const int cl = (Y1 - 1) % S; const bool owns = Y1 >= j0 && Y1 < j0 + S;
@@ -67,14 +73,36 @@ static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, in
         bool better = !have || L.bz > bz || (L.bz == bz && (L.bi > bi || (L.bi == bi && L.bj > bj)));
         if (better) { have = true; bz = L.bz; bw = L.bw; bi = L.bi; bj = L.bj; }
     }
-    if (have) { best.s = pw_score(k, bw); best.i = bi; best.j = bj; best.len = pw_len(k, bw); best.id = pw_ids(k, bw); }
+    raw.have = have; raw.bw = bw; raw.bi = bi; raw.bj = bj;
+    return raw;
+}
+
+// the epilogue of nwp_kernel<S, CL>
+template <int S>
+static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
+    const PwK k = pw_consts(igap, egap);
+    Res best; best.s = NW_NEG * 2; best.i = best.j = 0; best.len = best.id = 0;
+    if (xlen < 2 || ylen < 2) return best;
+    const Raw r = run_raw<S>(X, xlen, Y, ylen, k);
+    if (!r.have) return best;
+    best.s = pw_score(k, r.bw); best.i = r.bi; best.j = r.bj;
+    if (S <= 16) { best.len = pw_len(k, r.bw); best.id = pw_ids(k, r.bw); return best; }
+    n_wide++;
+    const uint32_t v = pw_stats(k, r.bw);
+    if (!pw_split_stats(v, r.bi, r.bj, &best.len, &best.id)) return best;
+    n_again++;
+    const PwK k_id = pw_consts(igap, egap, 1, 0);
+    const Raw r2 = run_raw<S>(X, xlen, Y, ylen, k_id);
+    if (r2.bi != r.bi || r2.bj != r.bj || pw_score(k_id, r2.bw) != best.s) { fprintf(stderr, "second run took another path\n"); exit(3); }
+    best.id = pw_stats(k_id, r2.bw);
+    best.len = (v - best.id) >> 8;
     return best;
 }
 
 template <int S>
 static Res dispatch(int s, const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
     if (s == S) return run_pair<S>(X, xlen, Y, ylen, igap, egap);
-    if constexpr (S < 16) return dispatch<S + 1>(s, X, xlen, Y, ylen, igap, egap);
+    if constexpr (S < PW_MAX_S) return dispatch<S + 1>(s, X, xlen, Y, ylen, igap, egap);
     fprintf(stderr, "bad S\n"); exit(2);
 }
 
@@ -84,9 +112,14 @@ int main(int argc, char **argv) {
     int bad = 0, skipped = 0;
     for (int it = 0; it < n; it++) {
         int xlen = 2 + rnd() % (it % 7 == 0 ? 510 : 255), ylen = 2 + rnd() % 256;
+        const bool wide = (it % 3 == 1);
+        if (wide) { ylen = 257 + rnd() % 65; xlen = (it % 4 == 0) ? 2 + rnd() % 511 : 230 + rnd() % 100; }
         if (it % 11 == 0) { xlen = 250; ylen = 250; }
         if (it % 19 == 0) { xlen = 256; ylen = 257; }
         if (it % 23 == 0) { xlen = 512; ylen = 256; }
+        if (it % 41 == 0) { xlen = 300; ylen = 300; }
+        if (it % 43 == 0) { xlen = 309; ylen = 309; }
+        if (it % 47 == 0) { xlen = 260 + rnd() % 50; ylen = 321; }
         if (it % 13 == 0) { xlen = 2 + rnd() % 6; }
         if (it % 17 == 0) { ylen = 2 + rnd() % 6; }
         std::vector<unsigned char> X(xlen), Y(ylen);
@@ -97,6 +130,7 @@ int main(int argc, char **argv) {
         else {
             int off = (int)(rnd() % (xlen)) - xlen / 3; double pe = (mode == 1) ? 0.03 : (mode == 2 ? 0.15 : 0.30);
             if (it % 5 == 0) off = 0;
+            if (wide && it % 2 == 0) { off = (int)(rnd() % 40) - 20; pe = (rnd() % 3 == 0) ? 0.0 : 0.02; }  // near-complete overlaps: 256 and more identities
             int src = off;
             for (int j = 0; j < ylen; j++) {
                 double u = (rnd() >> 11) * (1.0 / 9007199254740992.0);
@@ -108,7 +142,7 @@ int main(int argc, char **argv) {
             }
         }
         int igap = -(int)(rnd() % 8), egap = -(int)(rnd() % 4);
-        if (it % 3 == 0) { igap = -5; egap = -2; }
+        if (it % 3 == 0 || (wide && it % 2 == 0)) { igap = -5; egap = -2; }
         if (it % 31 == 0) { igap = 0; egap = 0; }
         if (it % 37 == 0) { igap = -(int)(rnd() % 40); egap = -(int)(rnd() % 7); }
         if (!pw_eligible(xlen, ylen, igap, egap)) { skipped++; continue; }
@@ -116,7 +150,8 @@ int main(int argc, char **argv) {
         orc_nw_forward(X.data(), xlen, Y.data(), ylen, igap, egap, &os, &obx, &oby, &olen, &oid);
         const int smin = (ylen - 1 + PW_LANES - 1) / PW_LANES;
         int s = smin < 1 ? 1 : smin;
-        if (it % 2 == 0) { s = 2 * ((ylen - 1 + 31) / 32); if (s < 2) s = 2; }  // what the kernel uses: 2 * class
+        if (ylen - 1 > PW_NARROW_Y1) s = ylen - 1 <= 288 ? (it % 5 == 2 && smin <= 17 ? 17 + (int)(rnd() % 4) : 18) : (it % 5 == 2 && smin <= 19 ? 19 : 20);  // classes 9 and 10 (sometimes another width)
+        else if (it % 2 == 0) { s = 2 * ((ylen - 1 + 31) / 32); if (s < 2) s = 2; }  // what the kernel uses: 2 * class
         else if (s < 16 && (it % 4 == 1)) s += rnd() % (17 - s);
         Res b = dispatch<1>(s, X.data(), xlen, Y.data(), ylen, igap, egap);
         bool ok;
@@ -128,6 +163,6 @@ int main(int argc, char **argv) {
                                  b.s, b.i, b.j, b.len, b.id, os, obx, oby, olen, oid);
         }
     }
-    printf("%d cases, %d skipped (not eligible), %d mismatches\n", n, skipped, bad);
+    printf("%d cases, %d skipped (not eligible), %d mismatches; %d wide pairs, %d of them run twice\n", n, skipped, bad, n_wide, n_again);
     return bad != 0;
 }

@@ -122,6 +122,41 @@ def test_align_sharded_in_one_process_equals_oracle(gpu):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_align_sharded_read_size_error_is_a_property_of_the_whole_database(gpu):
+    """"Read size reached for gapped alignment." (src/alignmentFunctions.c:155) in a sharded run: the long contig
+    lies in ONE shard; every shard must come back with the same answer (the flag is reduced with the payload), and a
+    later, normal database read that the scan order reaches first -- in the OTHER shard -- must still suppress it"""
+    from imsame_b200 import api
+    db, ds, q, qs = sc.fixed_case(71, 3, 50000, 200, 4000, 300, 0.03)
+    rng = np.random.default_rng(3)
+    contig = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=5000)]
+    cut = 1000 * 200  # the contig sits in the first shard
+    db_a = np.concatenate([db[:cut], contig, db[cut:]])
+    ds_a = np.concatenate([ds[:1001], ds[1000:] + 5000]).astype(np.uint64)
+    q_b = q.copy()
+    q_b[40 * 200:41 * 200] = contig[1000:1200]
+    p = api.make_params(n_threads=4)
+    ctxs = [gpu, api.Imsame(1)]
+    try:
+        with pytest.raises(api.ImsameError) as e:
+            api.align_sharded(ctxs, (db_a, ds_a), (q_b, qs), p)
+        assert e.value.code == -5
+        # the same piece in a normal read of the SECOND shard, later in the database: reached first, accepted
+        db_c = db_a.copy()
+        s_late = 3500
+        lo = int(ds_a[s_late])
+        db_c[lo:lo + 200] = contig[1000:1200]
+        out, _ = api.align_sharded(ctxs, (db_c, ds_a), (q_b, qs), p)
+        assert int(out[40]["accepted"]) == 1 and int(out[40]["db_seq"]) == s_late
+        whole, _ = gpu.align((db_c, ds_a), (q_b, qs), p)
+        for f in ("accepted", "db_seq", "qpos_end", "db_pos", "length", "identities"):
+            assert np.array_equal(out[f], whole[f]), f
+    finally:
+        ctxs[1].close()
+        gpu.comm_free()
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
 def test_cli_two_gpus_equals_one(gpu, tmp_path):
     from imsame_b200 import hostlib as H
     pool = H.SynthPool(606, 3, 60000)

@@ -76,6 +76,77 @@ def test_nw_batch_packed_kernel_matches_oracle_and_generic(gpu):
             assert tuple(int(v) for v in got[i]) == _oracle_nw(lib, xs[i], ys[i], igap, egap), (i, len(xs[i]), len(ys[i]), igap, egap)
 
 
+def test_nw_batch_wide_reads_in_packed_words(gpu):
+    """query reads of 257..321 bases (NW classes 9 and 10: 18 / 20 columns per lane): the identities no longer fit their
+    8 bits, the statistics word is split by the path's geometry and near-complete overlaps (256 and more identities)
+    are run a second time with the identities alone -- bit for bit the oracle's and the generic kernel's 5-tuples,
+    incl. identical reads, the largest admitted sizes and database reads of up to 512 bases"""
+    lib = hp.oracle()
+    rng = np.random.default_rng(303)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    xs, ys = [], []
+    sizes = [(300, 300), (301, 301), (309, 309), (257, 257), (256, 257), (290, 289), (289, 290), (250, 321), (321, 321),
+             (512, 300), (400, 321), (2, 300), (300, 2 + 256), (150, 310), (310, 150)]
+    for xl, yl in sizes:
+        for rep in range(10):
+            x = B[rng.integers(0, 4 if rep < 8 else 2, size=xl)]
+            if rep % 5 == 0:  # a copy (identical up to the shorter length): every identity counts
+                y = np.resize(x, yl).copy()
+            elif rep % 5 == 1:  # a noisy, slightly shifted copy: 256 and more identities, a few gaps
+                off = int(rng.integers(0, 12))
+                y = np.resize(np.roll(x, -off), yl).copy()
+                hit = rng.random(yl) < 0.02
+                y[hit] = B[rng.integers(0, 4, size=int(hit.sum()))]
+            elif rep % 5 == 2:  # short overlap at one corner
+                y = B[rng.integers(0, 4, size=yl)]
+                n = min(40, xl, yl)
+                y[:n] = x[xl - n:]
+            else:
+                y = B[rng.integers(0, 4 if rep < 8 else 2, size=yl)]
+            xs.append(np.ascontiguousarray(x)); ys.append(np.ascontiguousarray(y))
+    x2, y2 = sc.random_pairs(21, 600, max_len=322)
+    xs += x2; ys += y2
+    for igap, egap in ((5, 2), (0, 0), (8, 1), (1, 0)):
+        gpu.set_nw_mode(0)
+        got, _ = gpu.nw_batch(xs, ys, igap=igap, egap=egap)
+        gpu.set_nw_mode(1)
+        gen, _ = gpu.nw_batch(xs, ys, igap=igap, egap=egap)
+        gpu.set_nw_mode(0)
+        assert np.array_equal(np.asarray(got), np.asarray(gen)), (igap, egap)
+        n_big = 0
+        for i in range(0, len(xs), 1 if (igap, egap) == (5, 2) else 5):
+            if len(xs[i]) < 2 or len(ys[i]) < 2:
+                continue
+            want = _oracle_nw(lib, xs[i], ys[i], igap, egap)
+            assert tuple(int(v) for v in got[i]) == want, (i, len(xs[i]), len(ys[i]), igap, egap)
+            n_big += want[4] >= 256
+        assert n_big >= 10  # pairs whose identities overflow the 8-bit field were among them
+
+
+def test_align_wide_reads_matches_oracle(gpu):
+    """the whole path on 300-base reads (2 x 300 sequencing) and on ragged reads of 240..308 bases (with the default gap
+    scores packed words hold pairs of up to 309 x 309 bases): every candidate pair fits the packed-word kernels, no
+    generic launch is left, records == oracle == all-generic run"""
+    from imsame_b200 import api
+    p = api.make_params(n_threads=4)
+    for case in ("fixed", "ragged"):
+        if case == "fixed":
+            db, ds, q, qs = sc.fixed_case(3001, 3, 60000, 300, 5000, 800, 0.03)
+        else:
+            db, ds, q, qs = sc.ragged_case(3002, 3, 60000, 5000, 800, 0.04, lo=240, hi=308)
+        want, _ = oracle_records(db, ds, q, qs, 4)
+        out, st = gpu.align((db, ds), (q, qs), p)
+        assert st["k3_launches"] > 0 and st["k3_packed_launches"] == st["k3_launches"], case
+        assert gpu_records(out) == want and len(want) > 100, case
+        assert max(v[4] for v in want.values()) >= 256, case  # records whose identities took the second run
+        gpu.set_nw_mode(1)
+        try:
+            out_g, st_g = gpu.align((db, ds), (q, qs), p)
+        finally:
+            gpu.set_nw_mode(0)
+        assert st_g["k3_packed_launches"] == 0 and gpu_records(out_g) == want, case
+
+
 def test_read_longer_than_the_scan_limit_is_refused(gpu):
     """documented implementation limit: a read of more than 32 767 bases -> IMSAME_ELIMIT, not a wrong answer"""
     from imsame_b200 import api
