@@ -469,7 +469,7 @@ int launch_nwp_class(imsame_ctx *ctx, NwArgs a, int c) {
 }
 
 bool use_packed(const imsame_ctx *ctx, uint32_t xmax, uint32_t ymax, int igap, int egap) {
-    return ctx->nw_mode != 1 && pw_eligible(xmax, ymax, igap, egap);
+    return ctx->nw_mode != 1 && pw_eligible(xmax, ymax, igap, egap, pw_bias(xmax, ymax, igap, egap));
 }
 
 // unsorted explicit pairs: every class kernel walks the whole list and skips the other classes
@@ -499,7 +499,7 @@ int max_nw_grid(imsame_ctx *ctx) {
 }
 
 int ensure_carry(imsame_ctx *ctx, uint32_t max_ylen) {
-    if (max_ylen <= 32 * 8 + 1) return IMSAME_OK;
+    if (max_ylen <= 256) return IMSAME_OK;  // Y1 <= 255: classes 1..8, one pass (nw_class_of)
     // the kernels with 5..8 columns per lane run multi-pass (nw_class_of: balanced passes)
     if (!ctx->nw_grid[5]) {
         int per_sm = 0;
@@ -1085,6 +1085,7 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
     const bool mixed = !packed && ctx->nw_mode != 1 && p->igap <= 0 && p->egap <= 0;
     uint32_t *bin_work2 = bins + 6 * NW_NBINS + 8;
     a.mixed = mixed ? 1 : 0;
+    a.pw_bias = pw_bias(ctx->db_maxlen, ctx->q_maxlen, p->igap, p->egap);
     for (int c = 1; c <= NW_CLASSES; c++) {
         if (!(ctx->class_mask & (1u << c))) continue;
         const int bin = c * NW_BANDS + band;
@@ -1405,6 +1406,7 @@ struct PairBatch {
         a.tb = nullptr; a.tb_off = nullptr;
         a.check_class = 1;
         a.mixed = 0;
+        a.pw_bias = pw_bias(xmax, ymax, igap, egap);
         return a;
     }
 };

@@ -49,6 +49,7 @@ struct NwArgs {
     // nwp_kernel takes the pairs that do (pw_eligible on the pair's own lengths), nw_kernel the others; each kernel
     // walks the whole range with its own work-queue head and skips the other's pairs without touching them
     int mixed;
+    int pw_bias;      // score offset of the packed words of this run (nwp_core.cuh: pw_bias)
     // TB = true only (K4, winners-only traceback): back-pointer codes per cell
     uint16_t *tb;              // codes of pair idx start at tb + tb_off[idx]
     const uint64_t *tb_off;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(NW_THREADS) nw_kernel(NwArgs a) {
         if (a.mixed) {  // the packed-word kernel's pair?
             const uint32_t xs_ = read_start(a.db, pr.s);
             const uint32_t xlen_ = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs_);
-            if (pw_pair_eligible(xlen_, ylen, a.igap, a.egap)) continue;
+            if (pw_pair_eligible(xlen_, ylen, a.igap, a.egap, a.pw_bias)) continue;
         }
         // an earlier hit of this read is already accepted?  best[] is lowered by other warps meanwhile: one lane
         // reads it, so that the whole warp takes the same branch

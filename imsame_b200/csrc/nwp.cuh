@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(nwp_threads(S), nwp_min_blocks(S)) nwp_kernel(
     const unsigned hmask = 0xFFFFu << (16 * half);
     uint8_t *sx = sx_all[warp * 2 + half];
     const uint32_t r_begin = a.range[0], r_end = a.range[1];
-    const PwK k = pw_consts(a.igap, a.egap, a.one);
-    const PwK k_id = pw_consts(a.igap, a.egap, a.one, 0);  // wide reads, second run: identities alone
+    const PwK k = pw_consts(a.igap, a.egap, a.one, PW_LEN1, a.pw_bias);
+    const PwK k_id = pw_consts(a.igap, a.egap, a.one, 0, a.pw_bias);  // wide reads, second run: identities alone
     for (int e = threadIdx.x; e < NWP_TBL * (ROW / 4); e += THREADS) {
         // entry e: table index e / (ROW / 4), then (wide) 8 copies for k followed by 8 copies for k_id
         const bool second = WIDE && ((e >> 3) & 1);
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(nwp_threads(S), nwp_min_blocks(S)) nwp_kernel(
             if (a.check_class && nw_class_of(ylen) != a.s_class) continue;
             xs = read_start(a.db, pr.s);
             xlen = (a.db.fixed_len ? a.db.fixed_len : a.db.start[pr.s + 1] - xs);
-            if (a.mixed && !pw_pair_eligible(xlen, ylen, a.igap, a.egap)) continue;  // the generic kernel's pair
+            if (a.mixed && !pw_pair_eligible(xlen, ylen, a.igap, a.egap, a.pw_bias)) continue;  // the generic kernel's pair
             // an earlier hit of this read is accepted?  best[] is lowered by other warps meanwhile: one lane of
             // the half reads it, so that all 16 lanes take the same branch
             int pruned_h = 0;

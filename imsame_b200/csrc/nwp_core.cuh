@@ -86,43 +86,73 @@ struct PwK {
 };
 
 // lenu: what one alignment column adds to the statistics bits (PW_LEN1; 0 = carry the identities alone, the
-// second run of a wide pair whose statistics did not split)
-IMS_HD PwK pw_consts(int igap, int egap, int one = 1, int lenu = PW_LEN1) {
+// second run of a wide pair whose statistics did not split).  bias: score offset of the run (pw_bias): every
+// word that carries a score is derived from a stored cell by adding constants, and scores are only ever
+// compared with each other, so adding `bias` to the stored cells (through B) moves the 12-bit window from
+// [-2048, 2047] to [-2048 - bias, 2047 - bias] -- scores reach 4 (min + 1) upwards but, with the gap
+// candidates, 4 (min + 1) + |igap| + |egap| (max + 3) downwards.
+IMS_HD PwK pw_consts(int igap, int egap, int one = 1, int lenu = PW_LEN1, int bias = 0) {
     PwK k;
     k.one = one;
-    k.B = (igap + egap) * PW_SC1 + 2 * lenu + PW_PR1;
+    const int b0 = (igap + egap) * PW_SC1 + 2 * lenu + PW_PR1;  // a stored word is the L candidate it would install
+    k.B = b0 + bias * PW_SC1;
     k.step = egap * PW_SC1 + lenu;
     k.negz = -2046 * PW_SC1;
     k.negb = -2047 * PW_SC1;
     k.negl = -1900 * PW_SC1;
-    k.ds_mis = lenu + 2 * PW_PR1 - k.B;
-    k.sb_mis = -NW_POINT * PW_SC1 + k.B;
+    k.ds_mis = lenu + 2 * PW_PR1 - b0;    // candidates keep the offset of the cell they come from
+    k.sb_mis = -NW_POINT * PW_SC1 + b0;
     return k;
 }
 
-// Can every pair with xlen <= xmax, ylen <= ymax run in packed words?
-IMS_HD bool pw_eligible(uint32_t xmax, uint32_t ymax, int igap, int egap) {
+// how far below zero a score can fall for reads of up to xmax x ymax bases: |T| <= 4 (min(i,j) + 1); gap
+// candidates fall at most |igap| + |egap| (mx + 3) below that
+IMS_HD long pw_depth(uint32_t xmax, uint32_t ymax, int igap, int egap) {
+    const int X1 = (int)xmax - 1, Y1 = (int)ymax - 1;
+    const int mn = X1 < Y1 ? X1 : Y1, mx = X1 < Y1 ? Y1 : X1;
+    return 4L * (mn + 1) + (long)(-igap) + (long)(-egap) * (mx + 3) + 24;
+}
+constexpr long PW_DEPTH0 = 1890;  // depth that fits without a bias: stays above negl (and its one STEP)
+constexpr long PW_TOP = 2040;     // 4 (min + 1) + bias stays below this
+
+// Score offset of a run whose longest reads have xmax / ymax bases (lengths beyond what packed words take are
+// clamped: in a mixed run the generic kernel has those pairs).  0 for everything that fits without one (reads
+// of 250 bases with the default gap scores: depth 1533).
+IMS_HD int pw_bias(uint32_t xmax, uint32_t ymax, int igap, int egap) {
+    if (igap > 0 || egap > 0) return 0;
+    if (xmax > (uint32_t)PW_MAX_X) xmax = PW_MAX_X;
+    if (ymax > (uint32_t)PW_MAX_Y) ymax = PW_MAX_Y;
+    if (xmax < 2 || ymax < 2) return 0;
+    const long d = pw_depth(xmax, ymax, igap, egap);
+    if (d <= PW_DEPTH0) return 0;
+    const int mn = (int)(xmax < ymax ? xmax : ymax) - 1;
+    // no offset holds the longest pairs (very negative gap scores): none, as many short pairs as possible stay packed
+    if (4L * (mn + 1) + (d - PW_DEPTH0) > PW_TOP) return 0;
+    return (int)(d - PW_DEPTH0);
+}
+
+// Can every pair with xlen <= xmax, ylen <= ymax run in packed words (in a run with this score offset)?
+IMS_HD bool pw_eligible(uint32_t xmax, uint32_t ymax, int igap, int egap, int bias) {
     if (igap > 0 || egap > 0) return false;             // the row-1 R candidate must lose to D (see pw_lane_init)
     if (xmax < 2 || ymax < 2) return true;              // no cells at all
     if (ymax > (uint32_t)PW_MAX_Y || xmax > (uint32_t)PW_MAX_X) return false;
     const int X1 = (int)xmax - 1, Y1 = (int)ymax - 1;
-    const int mn = X1 < Y1 ? X1 : Y1, mx = X1 < Y1 ? Y1 : X1;
+    const int mn = X1 < Y1 ? X1 : Y1;
     // identities <= diagonal steps <= min(X1, Y1): 8 bits up to Y1 = 255 (the classes 1..8 kernels split V
     // as it is), one carry into the length field beyond (classes 9, 10: pw_split_stats)
     if (mn > 511) return false;
     if (X1 + Y1 + 3 > 1023) return false;                // columns on a path <= X1 + Y1, + 2 of bias, + 1 carry
-    // |T| <= 4 (min(i,j) + 1); gap candidates fall at most |igap| + |egap| (mx + 3) below that
-    const long lo = 4L * (mn + 1) + (long)(-igap) + (long)(-egap) * (mx + 3) + 24;
-    if (lo > 1890) return false;                         // stays above negl (and its one STEP)
+    if (pw_depth(xmax, ymax, igap, egap) - bias > PW_DEPTH0) return false;
+    if (4L * (mn + 1) + bias > PW_TOP) return false;
     if (-egap > 100) return false;
     return true;
 }
 
-// (the bound is monotone in both lengths and Y1 <= 255 implies min(X1, Y1) <= 255: a run whose longest reads
+// (both bounds are monotone in both lengths and Y1 <= 255 implies min(X1, Y1) <= 255: a run whose longest reads
 // pass consists of pairs that pass, each in the kernel of its own class)
 // the same test on ONE pair's own lengths (mixed runs: NwArgs.mixed)
-IMS_HD bool pw_pair_eligible(uint32_t xlen, uint32_t ylen, int igap, int egap) {
-    return xlen >= 2 && ylen >= 2 && pw_eligible(xlen, ylen, igap, egap);
+IMS_HD bool pw_pair_eligible(uint32_t xlen, uint32_t ylen, int igap, int egap, int bias) {
+    return xlen >= 2 && ylen >= 2 && pw_eligible(xlen, ylen, igap, egap, bias);
 }
 
 struct PwLink {

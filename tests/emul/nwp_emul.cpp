@@ -28,7 +28,7 @@ struct HostEW {
     PwE4 operator()(int g) const { return pw_e4(*k, (mm >> (8 * g)) & 0xFFu); }
 };
 
-static int n_again = 0, n_wide = 0;
+static int n_again = 0, n_wide = 0, n_biased = 0;
 
 struct Raw { bool have; int bw, bi, bj; };
 
@@ -79,8 +79,8 @@ static Raw run_raw(const unsigned char *X, int xlen, const unsigned char *Y, int
 
 // the epilogue of nwp_kernel<S, CL>
 template <int S>
-static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
-    const PwK k = pw_consts(igap, egap);
+static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap, int bias) {
+    const PwK k = pw_consts(igap, egap, 1, PW_LEN1, bias);
     Res best; best.s = NW_NEG * 2; best.i = best.j = 0; best.len = best.id = 0;
     if (xlen < 2 || ylen < 2) return best;
     const Raw r = run_raw<S>(X, xlen, Y, ylen, k);
@@ -91,7 +91,7 @@ static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, in
     const uint32_t v = pw_stats(k, r.bw);
     if (!pw_split_stats(v, r.bi, r.bj, &best.len, &best.id)) return best;
     n_again++;
-    const PwK k_id = pw_consts(igap, egap, 1, 0);
+    const PwK k_id = pw_consts(igap, egap, 1, 0, bias);
     const Raw r2 = run_raw<S>(X, xlen, Y, ylen, k_id);
     if (r2.bi != r.bi || r2.bj != r.bj || pw_score(k_id, r2.bw) != best.s) { fprintf(stderr, "second run took another path\n"); exit(3); }
     best.id = pw_stats(k_id, r2.bw);
@@ -100,9 +100,9 @@ static Res run_pair(const unsigned char *X, int xlen, const unsigned char *Y, in
 }
 
 template <int S>
-static Res dispatch(int s, const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap) {
-    if (s == S) return run_pair<S>(X, xlen, Y, ylen, igap, egap);
-    if constexpr (S < PW_MAX_S) return dispatch<S + 1>(s, X, xlen, Y, ylen, igap, egap);
+static Res dispatch(int s, const unsigned char *X, int xlen, const unsigned char *Y, int ylen, int igap, int egap, int bias) {
+    if (s == S) return run_pair<S>(X, xlen, Y, ylen, igap, egap, bias);
+    if constexpr (S < PW_MAX_S) return dispatch<S + 1>(s, X, xlen, Y, ylen, igap, egap, bias);
     fprintf(stderr, "bad S\n"); exit(2);
 }
 
@@ -120,6 +120,8 @@ int main(int argc, char **argv) {
         if (it % 41 == 0) { xlen = 300; ylen = 300; }
         if (it % 43 == 0) { xlen = 309; ylen = 309; }
         if (it % 47 == 0) { xlen = 260 + rnd() % 50; ylen = 321; }
+        if (it % 53 == 0) { xlen = 321; ylen = 321; }
+        if (it % 59 == 0) { xlen = 512; ylen = 321; }
         if (it % 13 == 0) { xlen = 2 + rnd() % 6; }
         if (it % 17 == 0) { ylen = 2 + rnd() % 6; }
         std::vector<unsigned char> X(xlen), Y(ylen);
@@ -145,7 +147,13 @@ int main(int argc, char **argv) {
         if (it % 3 == 0 || (wide && it % 2 == 0)) { igap = -5; egap = -2; }
         if (it % 31 == 0) { igap = 0; egap = 0; }
         if (it % 37 == 0) { igap = -(int)(rnd() % 40); egap = -(int)(rnd() % 7); }
-        if (!pw_eligible(xlen, ylen, igap, egap)) { skipped++; continue; }
+        // the score offset is a property of the RUN (its longest reads): the pair's own, that of a run with longer
+        // reads, or that of a run with reads beyond what packed words take (clamped to 512 x 321)
+        int bias = pw_bias(xlen, ylen, igap, egap);
+        if (it % 4 == 1) bias = pw_bias(xlen + rnd() % 200, ylen + rnd() % 60, igap, egap);
+        if (it % 4 == 2) bias = pw_bias(3000, 3000, igap, egap);
+        if (bias) n_biased++;
+        if (!pw_eligible(xlen, ylen, igap, egap, bias)) { skipped++; continue; }
         int32_t os; uint32_t obx, oby, olen, oid;
         orc_nw_forward(X.data(), xlen, Y.data(), ylen, igap, egap, &os, &obx, &oby, &olen, &oid);
         const int smin = (ylen - 1 + PW_LANES - 1) / PW_LANES;
@@ -153,7 +161,7 @@ int main(int argc, char **argv) {
         if (ylen - 1 > PW_NARROW_Y1) s = ylen - 1 <= 288 ? (it % 5 == 2 && smin <= 17 ? 17 + (int)(rnd() % 4) : 18) : (it % 5 == 2 && smin <= 19 ? 19 : 20);  // classes 9 and 10 (sometimes another width)
         else if (it % 2 == 0) { s = 2 * ((ylen - 1 + 31) / 32); if (s < 2) s = 2; }  // what the kernel uses: 2 * class
         else if (s < 16 && (it % 4 == 1)) s += rnd() % (17 - s);
-        Res b = dispatch<1>(s, X.data(), xlen, Y.data(), ylen, igap, egap);
+        Res b = dispatch<1>(s, X.data(), xlen, Y.data(), ylen, igap, egap, bias);
         bool ok;
         if (xlen < 2 || ylen < 2) ok = true;
         else ok = b.s == os && (uint32_t)b.i == obx && (uint32_t)b.j == oby && b.len == olen && b.id == oid;
@@ -163,6 +171,6 @@ int main(int argc, char **argv) {
                                  b.s, b.i, b.j, b.len, b.id, os, obx, oby, olen, oid);
         }
     }
-    printf("%d cases, %d skipped (not eligible), %d mismatches; %d wide pairs, %d of them run twice\n", n, skipped, bad, n_wide, n_again);
+    printf("%d cases, %d skipped (not eligible), %d mismatches; %d wide pairs, %d of them run twice; %d cases with a score offset\n", n, skipped, bad, n_wide, n_again, n_biased);
     return bad != 0;
 }

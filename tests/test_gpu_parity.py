@@ -86,7 +86,7 @@ def test_nw_batch_wide_reads_in_packed_words(gpu):
     B = np.frombuffer(b"ACGT", dtype=np.uint8)
     xs, ys = [], []
     sizes = [(300, 300), (301, 301), (309, 309), (257, 257), (256, 257), (290, 289), (289, 290), (250, 321), (321, 321),
-             (512, 300), (400, 321), (2, 300), (300, 2 + 256), (150, 310), (310, 150)]
+             (512, 300), (400, 321), (512, 321), (2, 300), (300, 2 + 256), (150, 310), (310, 150)]
     for xl, yl in sizes:
         for rep in range(10):
             x = B[rng.integers(0, 4 if rep < 8 else 2, size=xl)]
@@ -106,7 +106,9 @@ def test_nw_batch_wide_reads_in_packed_words(gpu):
             xs.append(np.ascontiguousarray(x)); ys.append(np.ascontiguousarray(y))
     x2, y2 = sc.random_pairs(21, 600, max_len=322)
     xs += x2; ys += y2
-    for igap, egap in ((5, 2), (0, 0), (8, 1), (1, 0)):
+    # (the batch's longest reads, 512 x 321, give every pair of it a score offset: 451 with the default gap scores;
+    # with (12, 4) the offset no longer fits and the two kernels share the batch pair by pair)
+    for igap, egap in ((5, 2), (0, 0), (8, 1), (1, 0), (12, 4)):
         gpu.set_nw_mode(0)
         got, _ = gpu.nw_batch(xs, ys, igap=igap, egap=egap)
         gpu.set_nw_mode(1)
@@ -124,16 +126,16 @@ def test_nw_batch_wide_reads_in_packed_words(gpu):
 
 
 def test_align_wide_reads_matches_oracle(gpu):
-    """the whole path on 300-base reads (2 x 300 sequencing) and on ragged reads of 240..308 bases (with the default gap
-    scores packed words hold pairs of up to 309 x 309 bases): every candidate pair fits the packed-word kernels, no
-    generic launch is left, records == oracle == all-generic run"""
+    """the whole path on 300-base reads (2 x 300 sequencing) and on ragged reads of 240..321 bases (the longest of them
+    need the run's score offset, nwp_core.cuh: pw_bias): every candidate pair fits the packed-word kernels, no generic
+    launch is left, records == oracle == all-generic run"""
     from imsame_b200 import api
     p = api.make_params(n_threads=4)
     for case in ("fixed", "ragged"):
         if case == "fixed":
             db, ds, q, qs = sc.fixed_case(3001, 3, 60000, 300, 5000, 800, 0.03)
         else:
-            db, ds, q, qs = sc.ragged_case(3002, 3, 60000, 5000, 800, 0.04, lo=240, hi=308)
+            db, ds, q, qs = sc.ragged_case(3002, 3, 60000, 5000, 800, 0.04, lo=240, hi=321)
         want, _ = oracle_records(db, ds, q, qs, 4)
         out, st = gpu.align((db, ds), (q, qs), p)
         assert st["k3_launches"] > 0 and st["k3_packed_launches"] == st["k3_launches"], case
