@@ -451,7 +451,7 @@ int launch_nw_class(imsame_ctx *ctx, NwArgs a, int c) {
 
 // packed-word kernel (nwp.cuh) of NW class c; its ~150 instantiations live in their own translation unit
 // (nwp_launch.cu) so that the two halves of the library compile side by side
-int launch_nwp_class(imsame_ctx *ctx, NwArgs a, int c) {
+int launch_nwp_class(imsame_ctx *ctx, NwArgs a, int c, uint32_t ymax) {
     c = c < 1 ? 1 : (c > NW_CLASSES ? NW_CLASSES : c);
     if (!ctx->nwp_grid[c]) {
         const int per_sm = nwp_blocks_per_sm(c);
@@ -460,7 +460,7 @@ int launch_nwp_class(imsame_ctx *ctx, NwArgs a, int c) {
     }
     a.s_class = c;
     a.one = 1;
-    nwp_launch(c, ctx->nwp_grid[c], ctx->stream, a);
+    nwp_launch(c, ctx->nwp_grid[c], ctx->stream, a, ymax);
     ctx->launches++;
     ctx->k3_launches++;
     ctx->k3_packed++;
@@ -475,14 +475,14 @@ bool use_packed(const imsame_ctx *ctx, uint32_t xmax, uint32_t ymax, int igap, i
 // unsorted explicit pairs: every class kernel walks the whole list and skips the other classes
 template <bool TB>
 int launch_nw_classes(imsame_ctx *ctx, NwArgs a, uint32_t class_mask, uint32_t *work_heads /* >= 2 * (NW_CLASSES + 1) zeroed */,
-                      bool packed = false, bool mixed = false) {
+                      bool packed = false, bool mixed = false, uint32_t ymax = IMSAME_MAX_READ_SIZE) {
     int rc = IMSAME_OK;
     a.check_class = 1;
     a.mixed = (mixed && !packed && !TB) ? 1 : 0;
     for (int c = 1; c <= NW_CLASSES && !rc; c++) {
         if (!(class_mask & (1u << c))) continue;
         a.work = work_heads + c;
-        if ((packed || a.mixed) && !TB) rc = launch_nwp_class(ctx, a, c);
+        if ((packed || a.mixed) && !TB) rc = launch_nwp_class(ctx, a, c, ymax);
         if (!rc && (!packed || TB)) {
             if (a.mixed) a.work = work_heads + NW_CLASSES + 1 + c;
             rc = launch_nw_class<TB>(ctx, a, c);
@@ -1091,7 +1091,7 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
         const int bin = c * NW_BANDS + band;
         a.range = launch_range + 2 * bin;
         a.work = bin_work + bin;
-        if (packed || mixed) { if ((rc = launch_nwp_class(ctx, a, c))) return rc; }
+        if (packed || mixed) { if ((rc = launch_nwp_class(ctx, a, c, ctx->q_maxlen))) return rc; }
         if (!packed) {
             if (mixed) a.work = bin_work2 + bin;
             if ((rc = launch_nw_class<false>(ctx, a, c))) return rc;
@@ -1431,7 +1431,7 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
     cudaEventCreate(&e1);
     cudaEventRecord(e0, ctx->stream);
     rc = launch_nw_classes<false>(ctx, a, pb.class_mask, pb.dsmall + 4, use_packed(ctx, pb.xmax, pb.ymax, igap, egap),
-                                  ctx->nw_mode != 1 && igap <= 0 && egap <= 0);
+                                  ctx->nw_mode != 1 && igap <= 0 && egap <= 0, pb.ymax);
     cudaEventRecord(e1, ctx->stream);
     std::vector<PairRes> hr(n_pairs);
     if (!rc) {

@@ -19,7 +19,10 @@ namespace imsame {
 constexpr int NWP_TBL = 0x56;  // table index = mismatch bits of 4 cells at bits 0,2,4,6
 IMS_HD constexpr bool nwp_wide(int S) { return S > 16; }
 IMS_HD constexpr int nwp_threads(int S) { return nwp_wide(S) ? 128 : 256; }
-IMS_HD constexpr int nwp_min_blocks(int S) { return nwp_wide(S) ? 3 : 2; }
+#ifndef NWP_WIDE_MIN_BLOCKS
+#define NWP_WIDE_MIN_BLOCKS 3  // x 128 threads: 168 registers per thread
+#endif
+IMS_HD constexpr int nwp_min_blocks(int S) { return nwp_wide(S) ? NWP_WIDE_MIN_BLOCKS : 2; }
 
 #if defined(__CUDACC__)
 

@@ -1,6 +1,7 @@
 // nwp_launch.cu -- instantiations of nwp_kernel<S, CL> (nwp.cuh): S columns per lane (2 * class for the classes
-// 1..8, 18 and 20 for the wide classes 9 and 10), CL = register slot of the last query column (or -1: decided at
-// run time).  A translation unit of its own: these ~190 kernels are most of the library's compile time.
+// 1..8; 18 and 20 for the wide classes 9 and 10, or 17 and 19 when the run's longest query read fits them: 300-base
+// reads fill 299 of 304 columns instead of 299 of 320), CL = register slot of the last query column (or -1: decided
+// at run time).  A translation unit of its own: these ~160 kernels are most of the library's compile time.
 #include "nwp_launch.h"
 #include "nwp.cuh"
 
@@ -20,9 +21,8 @@ void launch_variant(int grid, cudaStream_t stream, const NwArgs &a, int cl) {
     else nwp_kernel<S, -1><<<grid, nwp_threads(S), 0, stream>>>(a);
 }
 
-template <int C>
+template <int C, int S = cols_of_class(C)>
 void launch_class(int grid, cudaStream_t stream, const NwArgs &a) {
-    constexpr int S = cols_of_class(C);
     int cl = -1;
     if (a.q.fixed_len >= 2 && !a.check_class && nw_class_of(a.q.fixed_len) == C) cl = (int)((a.q.fixed_len - 2) % S);
     if (cl >= 0) launch_variant<S, 0>(grid, stream, a, cl);
@@ -54,7 +54,10 @@ int nwp_blocks_per_sm(int c) {
     }
 }
 
-void nwp_launch(int c, int grid, cudaStream_t stream, const NwArgs &a) {
+void nwp_launch(int c, int grid, cudaStream_t stream, const NwArgs &a, uint32_t ymax) {
+    // the wide classes with one column per lane less when no query read of the run needs it
+    if (c == 9 && ymax <= (uint32_t)(PW_LANES * 17 + 1)) { launch_class<9, 17>(grid, stream, a); return; }
+    if (c == 10 && ymax <= (uint32_t)(PW_LANES * 19 + 1)) { launch_class<10, 19>(grid, stream, a); return; }
     switch (c) {
         case 1: launch_class<1>(grid, stream, a); break;
         case 2: launch_class<2>(grid, stream, a); break;
