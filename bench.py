@@ -25,6 +25,8 @@ After the timed region (never inside it):
   same_config     N = 1: configs[0] at full size through the unmodified reference binary (whole process and alignment
                   phase, all host threads) and through imsame_gpu_align, record sets compared
   cpu_baseline    the reference binary on a bounded sample of the workload (its index cannot hold configs[1])
+  k3_by_read_len  N = 1: cell rate of the packed-word and the generic NW kernel on explicit random pairs of 250 and of
+                  300 bases (2 x 300 sequencing: the wide packed-word kernel), results compared
 """
 import argparse
 import json
@@ -318,6 +320,39 @@ def run_reference_arm(args):
             c1.pop("_headers", None)
             line["same_config"] = c1
     OUT.emit(json.dumps(line))
+
+
+def k3_by_read_len(ctx, np, lens=(250, 300), pairs_at_250=60000):
+    """cell rate of the two NW kernels on explicit random pairs (imsame_gpu_nw_batch, kernel time = the library's CUDA
+    events), per read length: 250 = the bench's own, 300 = 2 x 300 sequencing (NW class 10, the wide packed-word
+    kernel with 19 columns per lane); one pair in 50 is a noisy copy (an accepted pair).  Outside the timed region."""
+    rng = np.random.default_rng(1)
+    B = np.frombuffer(b"ACGT", dtype=np.uint8)
+    rows = []
+    for L in lens:
+        n = int(pairs_at_250 * (250.0 / L) ** 2)
+        X = B[rng.integers(0, 4, size=(n, L))]
+        Y = B[rng.integers(0, 4, size=(n, L))]
+        for i in range(0, n, 50):
+            Y[i] = X[i]
+            hit = rng.random(L) < 0.03
+            Y[i, hit] = B[rng.integers(0, 4, size=int(hit.sum()))]
+        xs, ys = [X[i] for i in range(n)], [Y[i] for i in range(n)]
+        cells = float(n) * (L - 1) * (L - 1)
+        row = {"read_len": L, "pairs": n}
+        res = {}
+        for mode, name in ((0, "packed"), (1, "generic")):
+            ctx.set_nw_mode(mode)
+            best = None
+            for _ in range(2):
+                got, ms = ctx.nw_batch(xs, ys)
+                best = ms if best is None or ms < best else best
+            res[name] = np.asarray(got)
+            row[name + "_gcups"] = round(cells / best / 1e6, 1)
+        ctx.set_nw_mode(0)
+        row["identical"] = bool(np.array_equal(res["packed"], res["generic"]))
+        rows.append(row)
+    return rows
 
 
 def H_mod():
@@ -660,6 +695,8 @@ def run_ours(args):
         }
         if not args.no_same_config and world == 1 and args.scale == 1.0 and not args.cfg3:
             line["same_config"] = same_config_cfg1(ctx, api, H, np)
+        if world == 1 and not args.cfg3 and args.nw_mode == 0:
+            line["k3_by_read_len"] = k3_by_read_len(ctx, np)
         if not args.no_cpu_baseline and world == 1:
             r, err = reference_cpu_run(args, w, 1, 0)
             if r:
