@@ -50,7 +50,7 @@ class Stats(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("ms_total", C.c_float),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("k2_launches", C.c_uint32), ("k3_launches", C.c_uint32), ("total_launches", C.c_uint32),
-                ("k3_packed_launches", C.c_uint32), ("ms_comm", C.c_float), ("reserved", C.c_uint32)]
+                ("k3_packed_launches", C.c_uint32), ("ms_comm", C.c_float), ("scan_passes", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -61,7 +61,7 @@ SYMBOLS = ["imsame_gpu_create", "imsame_gpu_destroy", "imsame_gpu_strerror", "im
            "imsame_gpu_set_stream", "imsame_gpu_align", "imsame_gpu_set_query", "imsame_gpu_set_db",
            "imsame_gpu_run", "imsame_gpu_n_segments", "imsame_gpu_n_bands", "imsame_gpu_run_begin",
            "imsame_gpu_run_scan", "imsame_gpu_run_band", "imsame_gpu_run_select", "imsame_gpu_run_end",
-           "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode",
+           "imsame_gpu_mask_payload", "imsame_gpu_fetch", "imsame_gpu_nw_batch", "imsame_gpu_set_nw_mode", "imsame_gpu_set_passes",
            "imsame_gpu_set_kmer", "imsame_gpu_comm_id", "imsame_gpu_comm_init", "imsame_gpu_comm_free",
            "imsame_gpu_run_sharded", "imsame_gpu_align_shard", "imsame_gpu_align_sharded",
            "imsame_gpu_sample_create", "imsame_gpu_sample_revcomp", "imsame_gpu_sample_free", "imsame_gpu_align_samples",
@@ -111,6 +111,7 @@ def lib():
         l.imsame_gpu_traceback.argtypes = [vp, C.POINTER(SeqInfo), C.POINTER(SeqInfo), C.POINTER(Params), vp, vp,
                                            C.POINTER(C.POINTER(C.c_uint32)), vp]
         l.imsame_gpu_set_nw_mode.argtypes = [vp, C.c_int]
+        l.imsame_gpu_set_passes.argtypes = [vp, C.c_int]
         l.imsame_gpu_set_kmer.argtypes = [vp, C.c_int]
         l.imsame_gpu_comm_id.argtypes = [vp]
         l.imsame_gpu_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
@@ -235,6 +236,10 @@ class Imsame:
     def set_nw_mode(self, mode):
         """0 = packed-word K3 where eligible (default), 1 = generic K3 only"""
         self._check(lib().imsame_gpu_set_nw_mode(self._h, int(mode)))
+
+    def set_passes(self, mode):
+        """0 = decide per run (default), 1 = one scan with every word, 2 = early words first (two scans)"""
+        self._check(lib().imsame_gpu_set_passes(self._h, int(mode)))
 
     def set_kmer(self, k):
         """seed length, 4..16 (default 12 = the reference's FIXED_K); call before set_query / align"""

@@ -63,6 +63,17 @@ struct imsame_ctx {
     uint32_t *off_own = nullptr;  // the context's own offsets table (`off` may point into a resident sample instead)
     QEntry *qtab = nullptr;  // query word table entries, bucket by bucket (qtable.cuh)
     bool q_borrowed = false;  // the query buffers and its word table belong to an imsame_sample
+    // "Early words first" (two-pass runs, see run_plan): the words that end inside the first early_bands k-mer-end
+    // bands of their read have a table of their own (built once per query), the later words of the reads that are
+    // still without an accepted hit after those bands a second one (built in the middle of every run)
+    bool tab_full = false, tab_early = false;  // off/qtab resp. off_early/qtab_early hold this query's words
+    uint32_t tab_early_split = 0;
+    uint32_t *off_early = nullptr, *off_late = nullptr;
+    QEntry *qtab_early = nullptr, *qtab_late = nullptr;
+    uint64_t n_words_early = 0, n_words_late = 0;
+    int passes_mode = 0;     // imsame_gpu_set_passes: 0 = decide per run, 1 = one pass, 2 = early words first
+    int run_passes = 1;      // of the run in progress
+    int run_early_bands = 0; // two passes: NW launches [0, run_early_bands) belong to the first
     uint64_t n_qwords = 0;
     uint64_t q_threads = 0;
     bool have_query = false;
@@ -94,6 +105,7 @@ struct imsame_ctx {
     void *comm = nullptr;
     int comm_rank = 0, comm_size = 1;
     unsigned long long *comm_flag = nullptr;  // one device word for status / read-size reductions
+    unsigned long long *comm_flag3 = nullptr; // three more: comm_status
     bool table_dirty = false;  // the pair table may hold entries of a run that failed before they were binned
     // (after the launch ranges: NBINS more work heads, for the second kernel of a mixed run)
     // per segment (stride BINS_STRIDE): [0,NBINS) counts | [NBINS, 3*NBINS+1) offsets + cursors |
@@ -255,6 +267,8 @@ void free_query(imsame_ctx *ctx) {
         pool_free(ctx, ctx->q_pk); pool_free(ctx, ctx->q_start); pool_free(ctx, ctx->q_blk);
         pool_free(ctx, ctx->qtab);
     }
+    pool_free(ctx, ctx->qtab_early); pool_free(ctx, ctx->qtab_late);
+    ctx->tab_full = ctx->tab_early = false;
     ctx->have_query = false;
 }
 void free_db(imsame_ctx *ctx) {
@@ -565,7 +579,8 @@ void fill_stats(imsame_ctx *ctx, imsame_stats *st, const unsigned long long *cnt
     st->h2d_bytes = ctx->h2d_bytes; st->d2h_bytes = ctx->d2h_bytes;
     st->k2_launches = ctx->k2_launches; st->k3_launches = ctx->k3_launches; st->total_launches = ctx->launches;
     st->k3_packed_launches = ctx->k3_packed;
-    st->n_query_kmers = ctx->n_qwords;
+    st->n_query_kmers = ctx->run_passes == 2 ? ctx->n_words_early + ctx->n_words_late : ctx->n_qwords;
+    st->scan_passes = (uint32_t)ctx->run_passes;
     if (cnt) {
         st->n_db_kmers = cnt[0]; st->n_hits = cnt[1]; st->n_evalue_pass = cnt[2];
         st->n_cells = cnt[4]; st->n_pairs = cnt[5]; st->n_pairs_dp = cnt[6]; st->n_accepted = cnt[7];
@@ -575,23 +590,37 @@ void fill_stats(imsame_ctx *ctx, imsame_stats *st, const unsigned long long *cnt
 }  // namespace
 
 // K1 over the resident packed query (ctx->q_pk ...): histogram of the words, exclusive scan, scatter of the
-// table entries.  off_dst / qtab_out: build into a resident sample's own offsets table and hand the entries
-// (plain allocation) to the caller; nullptr: the context's own table and the recycled pool.
-static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_out) {
+// table entries.  part 0 = every word: off_dst / qtab_out: build into a resident sample's own offsets table and
+// hand the entries (plain allocation) to the caller; nullptr: the context's own table and the recycled pool.
+// part 1 / 2 = the early / the late words of a two-pass run (qtable.cuh: QTableArgs.part) into off_early /
+// qtab_early resp. off_late / qtab_late.
+static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_out, int part = 0, uint32_t e_split = 0) {
     int rc;
     const uint32_t nq = ctx->nq, total = ctx->q_total;
     const uint64_t ncodes = ncodes_of(ctx->k);
     const uint32_t n_tiles = (uint32_t)((ncodes + SCAN_TILE - 1) / SCAN_TILE);
     if (ctx->k_tables != ctx->k) {
-        dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
-        ctx->off_own = ctx->cursor = ctx->tile_sums = nullptr;
+        dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums); dev_free(ctx->off_early); dev_free(ctx->off_late);
+        ctx->off_own = ctx->cursor = ctx->tile_sums = ctx->off_early = ctx->off_late = nullptr;
         ctx->k_tables = 0;
         if ((rc = dev_alloc(ctx, &ctx->off_own, (uint64_t)ncodes + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->cursor, (uint64_t)ncodes + 1))) return rc;
         if ((rc = dev_alloc(ctx, &ctx->tile_sums, (uint64_t)n_tiles + 1))) return rc;
         ctx->k_tables = ctx->k;
     }
-    ctx->off = off_dst ? off_dst : ctx->off_own;
+    uint32_t *off = nullptr;
+    QEntry **slot = nullptr;
+    if (part == 0) {
+        off = off_dst ? off_dst : ctx->off_own;
+        ctx->off = off;
+        slot = &ctx->qtab;
+    } else {
+        uint32_t **o = part == 1 ? &ctx->off_early : &ctx->off_late;
+        if (!*o && (rc = dev_alloc(ctx, o, (uint64_t)ncodes + 1))) return rc;
+        off = *o;
+        slot = part == 1 ? &ctx->qtab_early : &ctx->qtab_late;
+        pool_free(ctx, *slot);  // (the table of the previous run / query)
+    }
     QTableArgs a;
     a.k = ctx->k;
     a.q.pk = ctx->q_pk; a.q.start = ctx->q_start; a.q.blk = ctx->q_blk; a.q.n = nq; a.q.total = total;
@@ -600,37 +629,38 @@ static int build_query_table(imsame_ctx *ctx, uint32_t *off_dst, QEntry **qtab_o
     a.per = (uint32_t)(nq / ctx->q_threads);  // floorl(n_seqs / n_threads), src/IMSAME.c:414
     a.cnt = ctx->cursor;
     a.qtab = nullptr;
+    a.part = part; a.e_split = e_split; a.best = ctx->run_keys;
     const int grid = (int)std::min<uint64_t>(((uint64_t)total + 255) / 256, (uint64_t)ctx->n_sm * 32);
     uint32_t n_words = 0;
     {
         PhaseScope ps(ctx, PH_K1);
         CK(cudaMemsetAsync(ctx->cursor, 0, ((size_t)ncodes + 1) * 4, ctx->stream));
         qtable_kernel<0><<<grid, 256, 0, ctx->stream>>>(a);
-        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
+        scan_tiles_kernel<0><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, off);
         scan_sums_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->tile_sums, n_tiles);
-        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, ctx->off);
+        scan_tiles_kernel<2><<<n_tiles, SCAN_THREADS, 0, ctx->stream>>>(ctx->cursor, ncodes, ctx->tile_sums, off);
         ctx->launches += 4;
         CK(cudaGetLastError());
     }
-    CK(cudaMemcpyAsync(&n_words, ctx->off + ncodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&n_words, off + ncodes, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->n_qwords = n_words;
-    if (qtab_out) {
-        if ((rc = dev_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) return rc;
-        *qtab_out = ctx->qtab;
-    } else if ((rc = pool_alloc(ctx, &ctx->qtab, (uint64_t)n_words + 1))) {
+    if (part == 0 && qtab_out) {
+        if ((rc = dev_alloc(ctx, slot, (uint64_t)n_words + 1))) return rc;
+        *qtab_out = *slot;
+    } else if ((rc = pool_alloc(ctx, slot, (uint64_t)n_words + 1))) {
         return rc;
     }
     {
         PhaseScope ps(ctx, PH_K1);
-        CK(cudaMemcpyAsync(ctx->cursor, ctx->off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-        a.qtab = ctx->qtab;
+        CK(cudaMemcpyAsync(ctx->cursor, off, ((size_t)ncodes + 1) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        a.qtab = *slot;
         qtable_kernel<1><<<grid, 256, 0, ctx->stream>>>(a);
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    ctx->q_k = ctx->k;
-    ctx->have_query = true;
+    if (part == 0) { ctx->n_qwords = n_words; ctx->q_k = ctx->k; ctx->tab_full = true; }
+    else if (part == 1) { ctx->n_words_early = n_words; ctx->q_k = ctx->k; ctx->tab_early = true; ctx->tab_early_split = e_split; }
+    else ctx->n_words_late = n_words;
     return IMSAME_OK;
 }
 
@@ -685,7 +715,7 @@ void imsame_gpu_destroy(imsame_ctx *ctx) {
     free_query(ctx);
     free_db(ctx);
     pool_destroy(ctx);
-    dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums);
+    dev_free(ctx->off_own); dev_free(ctx->cursor); dev_free(ctx->tile_sums); dev_free(ctx->off_early); dev_free(ctx->off_late);
     dev_free(ctx->d_nmin); dev_free(ctx->d_lmin); dev_free(ctx->d_imin); dev_free(ctx->d_lut);
     dev_free(ctx->hkeys); dev_free(ctx->hvals); dev_free(ctx->pairs); dev_free(ctx->res);
     dev_free(ctx->d_small); dev_free(ctx->d_counters); dev_free(ctx->d_overflow);
@@ -771,7 +801,11 @@ int imsame_gpu_set_query(imsame_ctx *ctx, const imsame_seqinfo *q, const imsame_
         blk_kernel<<<std::min<uint32_t>((nq + 255) / 256, ctx->n_sm * 16), 256, 0, ctx->stream>>>(ctx->q_start, nq, ctx->q_blk);
         ctx->launches++;
     }
-    return build_query_table(ctx, nullptr, nullptr);
+    // the word table(s) are built by the first run on this query, which knows whether it runs in one pass (every
+    // word: build_query_table part 0) or early words first (run_plan)
+    ctx->q_k = ctx->k;
+    ctx->have_query = true;
+    return IMSAME_OK;
 }
 
 // ---- database shard: upload + pack in segments of < 2^31 bases -------------------------------
@@ -903,7 +937,56 @@ SeqMap seg_map(const Seg &s) {
 extern "C" int imsame_gpu_n_segments(const imsame_ctx *ctx) { return ctx ? (int)ctx->segs.size() : 0; }
 extern "C" int imsame_gpu_n_bands(void) { return NW_BANDS; }
 
+namespace {
+
+constexpr int EARLY_BANDS = 6;         // of NW_BANDS = 32: the words that end inside the first 3/16 of their read
+constexpr double TWO_PASS_HITS = 4e9;  // expected seed hits per GPU from which a run is made in two passes
+
+inline uint32_t band_width_of(const imsame_ctx *ctx) { return (ctx->q_maxlen + 1 + NW_BANDS - 1) / NW_BANDS; }
+// logical segments of a run: database segment (ls % nseg) scanned in pass (ls / nseg)
+inline int n_lsegs(const imsame_ctx *ctx) { return (int)ctx->segs.size() * ctx->run_passes; }
+
+// "Early words first".  The reference walks the words of a query read left to right and stops at the read's first
+// accepted hit (src/alignmentFunctions.c:172,189).  The band-ordered NW launches already use that (a later candidate
+// of an accepted read is pruned, not aligned), but the SCAN still extended every seed hit of every word: a read that
+// is in the database is usually accepted on one of its first words (76 % of the accepted reads of a 2.5x-coverage
+// database within the first 32 bases, 90 % within 64), and all the hits of its ~200 later words -- a third of the
+// scan's work on config 2 -- are looked at for nothing.  A two-pass run scans the database with the table of the
+// EARLY words only (k-mer end inside the first EARLY_BANDS bands of the read), aligns their bands, then builds the
+// table of the LATE words of the reads that are still without an accepted hit and scans again.  Exact: a read
+// accepted in the first pass has a key that every later word's key exceeds (make_key: k-mer end first), and a read
+// that is not is scanned with all its words.  In a sharded run the keys are reduced between the passes, so a read
+// accepted in ANY shard drops out of the second pass of every shard; the decision below only uses quantities
+// that are the same on every rank.
+void run_plan(imsame_ctx *ctx, const imsame_params *p, bool allow_two) {
+    ctx->run_passes = 1;
+    ctx->run_early_bands = 0;
+    if (!allow_two || ctx->q_borrowed) return;  // a resident sample brings its table of every word along
+    int mode = ctx->passes_mode;
+    if (!mode)
+        if (const char *e = getenv("IMSAME_PASSES")) mode = atoi(e);
+    if (mode == 1) return;
+    int nb = EARLY_BANDS;
+    if (const char *e = getenv("IMSAME_EARLY_BANDS")) nb = atoi(e);  // tuning knob
+    if (nb < 1 || nb >= NW_BANDS || (uint64_t)nb * band_width_of(ctx) <= (uint64_t)ctx->q_k) return;  // no early word at all
+    if (mode != 2) {
+        const double db_bases = ctx->comm_size > 1 ? (double)p->db_total_len_global / ctx->comm_size : (double)ctx->db_total;
+        if ((double)ctx->q_total * db_bases / (double)ncodes_of(ctx->q_k) < TWO_PASS_HITS) return;
+    }
+    ctx->run_passes = 2;
+    ctx->run_early_bands = nb;
+}
+
+}  // namespace
+
+static int run_begin_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload, bool allow_two);
+
+// (the caller steps through scans and bands itself: one pass over the table of every word)
 extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload) {
+    return run_begin_impl(ctx, p, d_keys, d_payload, false);
+}
+
+static int run_begin_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload, bool allow_two) {
     if (!ctx || !p) return IMSAME_EARG;
     if (!ctx->have_query || !ctx->have_db) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
@@ -920,7 +1003,15 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
         if ((rc = dev_alloc(ctx, &ctx->pkey, nq))) return rc;
         ctx->keys_cap = nq;
     }
-    const uint32_t nseg = (uint32_t)ctx->segs.size();
+    run_plan(ctx, p, allow_two);
+    // the table of the first (or only) pass; the k the query was set with decides, not a later set_kmer
+    if (ctx->run_passes == 2) {
+        const uint32_t split = (uint32_t)ctx->run_early_bands * band_width_of(ctx);
+        if ((!ctx->tab_early || ctx->tab_early_split != split) && (rc = build_query_table(ctx, nullptr, nullptr, 1, split))) return rc;
+    } else if (!ctx->q_borrowed && !ctx->tab_full) {
+        if ((rc = build_query_table(ctx, nullptr, nullptr))) return rc;
+    }
+    const uint32_t nseg = (uint32_t)n_lsegs(ctx);
     if (ctx->bins_segs < nseg) {
         dev_free(ctx->d_bins);
         if ((rc = dev_alloc(ctx, &ctx->d_bins, (uint64_t)nseg * BINS_STRIDE))) return rc;
@@ -977,9 +1068,11 @@ extern "C" int imsame_gpu_run_begin(imsame_ctx *ctx, const imsame_params *p, uin
     return IMSAME_OK;
 }
 
-// K2 for one segment, asynchronously: scan, extend, collect the candidates in the pair table
+// K2 for one (logical) segment, asynchronously: scan, extend, collect the candidates in the pair table
 static int scan_launch(imsame_ctx *ctx, int seg) {
-    Seg &s = ctx->segs[(size_t)seg];
+    const int n_db_segs = (int)ctx->segs.size();
+    const bool late = seg >= n_db_segs;  // second pass of a two-pass run (run_plan)
+    Seg &s = ctx->segs[(size_t)(seg % n_db_segs)];
     const imsame_params *p = &ctx->run_params;
     ctx->table_dirty = true;  // until bin_kernel<1> has emptied the table again (run_begin clears it otherwise)
     if (s.wait_ready) {       // the segment was uploaded on another stream (imsame_gpu_align)
@@ -992,7 +1085,10 @@ static int scan_launch(imsame_ctx *ctx, int seg) {
     CK(cudaMemsetAsync(ctx->d_counters + 8, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PhaseScope ps(ctx, PH_K2);
     ScanArgs a;
-    a.db = seg_map(s); a.q = query_map(ctx); a.off = ctx->off; a.qtab = ctx->qtab; a.brk = s.brk; a.n_brk = s.n_brk;
+    a.db = seg_map(s); a.q = query_map(ctx); a.brk = s.brk; a.n_brk = s.n_brk;
+    if (ctx->run_passes == 2) { a.off = late ? ctx->off_late : ctx->off_early; a.qtab = late ? ctx->qtab_late : ctx->qtab_early; }
+    else { a.off = ctx->off; a.qtab = ctx->qtab; }
+    a.count_words = late ? 0 : 1;  // the database words are the same in both passes
     a.nmin = ctx->d_nmin; a.lut = ctx->d_lut; a.seg_pos_base = p->db_pos_base + s.pos_base;
     a.hkeys = ctx->hkeys; a.hvals = ctx->hvals; a.hmask = ctx->hcap - 1; a.best = ctx->run_keys;
     a.counters = ctx->d_counters + 8; a.overflow = ctx->d_overflow;
@@ -1059,7 +1155,7 @@ static int scan_finish(imsame_ctx *ctx, int seg) {
 }
 
 extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
-    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= n_lsegs(ctx)) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     int rc = scan_launch(ctx, seg);
     return rc ? rc : scan_finish(ctx, seg);
@@ -1067,15 +1163,16 @@ extern "C" int imsame_gpu_run_scan(imsame_ctx *ctx, int seg) {
 
 // K3 for one band of one segment (every NW class present in the query)
 extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
-    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size() || band < 0 || band >= NW_BANDS)
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= n_lsegs(ctx) || band < 0 || band >= NW_BANDS)
         return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
     const imsame_params *p = &ctx->run_params;
+    const Seg &dbseg = ctx->segs[(size_t)seg % ctx->segs.size()];
     uint32_t *bins = ctx->d_bins + (size_t)seg * BINS_STRIDE;
     uint32_t *bin_work = bins + 3 * NW_NBINS + 4, *launch_range = bins + 4 * NW_NBINS + 4;
     PhaseScope ps(ctx, PH_K3);
     NwArgs a;
-    a.db = seg_map(ctx->segs[seg]); a.q = query_map(ctx); a.pairs = ctx->pairs; a.res = ctx->res;
+    a.db = seg_map(dbseg); a.q = query_map(ctx); a.pairs = ctx->pairs; a.res = ctx->res;
     a.igap = p->igap; a.egap = p->egap; a.lmin = ctx->d_lmin; a.imin = ctx->d_imin;
     a.best = ctx->run_keys; a.cells = ctx->d_counters + 4; a.carry = ctx->carry; a.s_class = 0;
     a.tb = nullptr; a.tb_off = nullptr; a.check_class = 0;
@@ -1102,20 +1199,21 @@ extern "C" int imsame_gpu_run_band(imsame_ctx *ctx, int seg, int band) {
 
 // record fields of the pairs of this segment that currently own their read's key
 extern "C" int imsame_gpu_run_select(imsame_ctx *ctx, int seg) {
-    if (!ctx || !ctx->run_active || seg < 0 || seg >= (int)ctx->segs.size()) return IMSAME_ESTATE;
+    if (!ctx || !ctx->run_active || seg < 0 || seg >= n_lsegs(ctx)) return IMSAME_ESTATE;
     cudaSetDevice(ctx->device);
+    const Seg &dbseg = ctx->segs[(size_t)seg % ctx->segs.size()];
     PhaseScope ps(ctx, PH_SELECT);
     select_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->pairs + ctx->seg_pair_base[seg],
                                                         ctx->res + ctx->seg_pair_base[seg],
                                                         (uint32_t)ctx->seg_pair_count[seg], ctx->run_keys,
                                                         ctx->run_payload, ctx->pkey,
-                                                        ctx->run_params.db_seq_base + ctx->segs[seg].seq_base,
+                                                        ctx->run_params.db_seq_base + dbseg.seq_base,
                                                         ctx->d_counters + 5);
     ctx->launches++;
     if (ctx->db_maxlen > IMSAME_MAX_READ_SIZE || ctx->q_maxlen > IMSAME_MAX_READ_SIZE) {
         // the keys are final here (all bands done, and exchanged between shards in a stepped run)
         readsize_kernel<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(ctx->pairs + ctx->seg_pair_base[seg],
-                                                              (uint32_t)ctx->seg_pair_count[seg], seg_map(ctx->segs[seg]),
+                                                              (uint32_t)ctx->seg_pair_count[seg], seg_map(dbseg),
                                                               query_map(ctx), ctx->run_keys, ctx->d_counters + 12);
         ctx->launches++;
     }
@@ -1186,22 +1284,51 @@ static int run_segment_major(imsame_ctx *ctx, imsame_stats *st, bool concurrent)
     return imsame_gpu_run_end(ctx, st);
 }
 
+// second pass of a two-pass run (run_plan), after the NW launches of the early bands: the table of the late words
+// of the reads that have no accepted hit yet (their keys are in run_keys; reduced over the shards by then in a
+// sharded run), and the scans of every database segment against it (logical segments nseg .. 2 nseg - 1)
+static int late_pass_scans(imsame_ctx *ctx) {
+    int rc;
+    const int nseg = (int)ctx->segs.size();
+    if ((rc = build_query_table(ctx, nullptr, nullptr, 2, (uint32_t)ctx->run_early_bands * band_width_of(ctx)))) return rc;
+    for (int seg = 0; seg < nseg; seg++)
+        if ((rc = imsame_gpu_run_scan(ctx, nseg + seg))) return rc;
+    return IMSAME_OK;
+}
+
+// everything after the scans of the first (or only) pass: NW launches in ascending band order over ALL segments (an
+// accepted early candidate prunes the read's later ones), in a two-pass run with the second scan after the early
+// bands; the candidates of the first pass all lie in the early bands, those of the second pass in the later ones
+// (bands merged into one launch for want of candidates start at launch 0: every launch is issued for them)
+static int run_bands_and_finish(imsame_ctx *ctx, imsame_stats *st) {
+    int rc;
+    const int nseg = (int)ctx->segs.size();
+    const bool two = ctx->run_passes == 2;
+    for (int band = 0; band < (two ? ctx->run_early_bands : NW_BANDS); band++)
+        for (int seg = 0; seg < nseg; seg++)
+            if ((rc = imsame_gpu_run_band(ctx, seg, band))) return rc;
+    if (two) {
+        if ((rc = late_pass_scans(ctx))) return rc;
+        for (int band = 0; band < NW_BANDS; band++)
+            for (int seg = 0; seg < nseg; seg++)
+                if ((rc = imsame_gpu_run_band(ctx, nseg + seg, band))) return rc;
+    }
+    for (int seg = 0; seg < n_lsegs(ctx); seg++)
+        if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
+    return imsame_gpu_run_end(ctx, st);
+}
+
 static int run_impl(imsame_ctx *ctx, const imsame_params *p, uint64_t *d_keys, uint64_t *d_payload,
                     imsame_stats *st) {
     int rc;
-    if ((rc = imsame_gpu_run_begin(ctx, p, d_keys, d_payload))) return rc;
+    const char *sm = getenv("IMSAME_SEGMENT_MAJOR");
+    const bool segment_major = sm && atoi(sm) > 0 && !ctx->in_align;
+    if ((rc = run_begin_impl(ctx, p, d_keys, d_payload, !segment_major))) return rc;
     const int nseg = (int)ctx->segs.size();
-    if (const char *e = getenv("IMSAME_SEGMENT_MAJOR"))
-        if (atoi(e) > 0 && !ctx->in_align) return run_segment_major(ctx, st, atoi(e) == 2);
+    if (segment_major) return run_segment_major(ctx, st, atoi(sm) == 2);
     for (int seg = 0; seg < nseg; seg++)
         if ((rc = imsame_gpu_run_scan(ctx, seg))) return rc;
-    // ascending bands over ALL segments: an accepted early candidate prunes the read's later ones
-    for (int band = 0; band < NW_BANDS; band++)
-        for (int seg = 0; seg < nseg; seg++)
-            if ((rc = imsame_gpu_run_band(ctx, seg, band))) return rc;
-    for (int seg = 0; seg < nseg; seg++)
-        if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
-    return imsame_gpu_run_end(ctx, st);
+    return run_bands_and_finish(ctx, st);
 }
 
 extern "C" {
@@ -1217,6 +1344,13 @@ int imsame_gpu_set_kmer(imsame_ctx *ctx, int k) {
     if (ctx->run_active) return IMSAME_ESTATE;
     if (k != ctx->k) ctx->have_query = false;  // the resident word table belongs to the old length
     ctx->k = k;
+    return IMSAME_OK;
+}
+
+int imsame_gpu_set_passes(imsame_ctx *ctx, int mode) {
+    if (!ctx || mode < 0 || mode > 2) return IMSAME_EARG;
+    if (ctx->run_active) return IMSAME_ESTATE;
+    ctx->passes_mode = mode;
     return IMSAME_OK;
 }
 
@@ -1278,7 +1412,7 @@ static int align_pipelined(imsame_ctx *ctx, const imsame_seqinfo *db, const imsa
     int rc;
     if ((rc = imsame_gpu_set_query(ctx, query, p))) return rc;
     if ((rc = db_layout(ctx, db))) return rc;
-    if ((rc = imsame_gpu_run_begin(ctx, p, nullptr, nullptr))) return rc;
+    if ((rc = run_begin_impl(ctx, p, nullptr, nullptr, true))) return rc;
     const int nseg = (int)ctx->segs.size();
     if ((rc = db_upload_seg(ctx, db, 0))) return rc;
     for (int seg = 0; seg < nseg; seg++) {
@@ -1287,12 +1421,7 @@ static int align_pipelined(imsame_ctx *ctx, const imsame_seqinfo *db, const imsa
         if (seg + 1 < nseg && (rc = db_upload_seg(ctx, db, seg + 1))) return rc;
         if ((rc = scan_finish(ctx, seg))) return rc;
     }
-    for (int band = 0; band < NW_BANDS; band++)
-        for (int seg = 0; seg < nseg; seg++)
-            if ((rc = imsame_gpu_run_band(ctx, seg, band))) return rc;
-    for (int seg = 0; seg < nseg; seg++)
-        if ((rc = imsame_gpu_run_select(ctx, seg))) return rc;
-    return imsame_gpu_run_end(ctx, local);
+    return run_bands_and_finish(ctx, local);
 }
 
 int imsame_gpu_align(imsame_ctx *ctx, const imsame_seqinfo *db, const imsame_seqinfo *query,

@@ -74,6 +74,15 @@ struct QTableArgs {
     uint32_t *cnt;            // pass 0: histogram ; pass 1: bucket cursors
     QEntry *qtab;
     int k;                    // seed length (the reference: FIXED_K = 12, src/structs.h:15)
+    // Which of the words go into this table (capi.cu: "early words first").  The reference walks a read's words
+    // left to right and stops at the first accepted hit (src/alignmentFunctions.c:172,189), so once the words that
+    // end before position e_split of their read have been scanned and aligned, the later words of every read that
+    // has an accepted hit by then can never matter: the second table simply does not contain them.
+    //   0: every word   1: words with e_rel < e_split   2: words with e_rel >= e_split of reads without a key
+    // e_rel = e - ys + 1, the k-mer end inside the read as the scan-order key counts it (common.cuh: make_key)
+    int part;
+    uint32_t e_split;
+    const unsigned long long *best;  // part 2: per read scan-order key after the early bands (KEY_NONE = none)
 };
 
 // does a query word end at base e, and which word?  
@@ -86,6 +95,10 @@ __device__ __forceinline__ bool query_word_at(const QTableArgs &a, uint32_t e, u
     const uint32_t hi = (r == a.q.n - 1) ? a.q.total - 1 : yend - 2;
     const uint32_t k1 = (uint32_t)a.k - 1u;
     if (e < lo + k1 || e > hi || yend < 2 + ys) return false;
+    if (a.part) {
+        const uint32_t e_rel = e - ys + 1;
+        if (a.part == 1 ? e_rel >= a.e_split : (e_rel < a.e_split || a.best[r] != KEY_NONE)) return false;
+    }
     code = fetch16(a.q.pk, (uint64_t)e - k1) & kmask_of(a.k);
     return true;
 }

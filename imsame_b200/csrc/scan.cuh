@@ -36,6 +36,7 @@ struct ScanArgs {
     unsigned long long *counters;    // [0] db words, [1] hits, [2] e-value passes, [3] anomalies
     int *overflow;
     int k;  // seed length when the kernel is not specialised on it (scan_kernel<0>)
+    int count_words;  // 0: counters[0] has the database words already (second pass of a two-pass run)
 };
 
 IMS_HD uint64_t pair_hash(uint64_t k) {
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(SCAN_THREADS_K2) scan_kernel(ScanArgs a) {
         c_anom += __shfl_xor_sync(0xffffffffu, c_anom, o);
     }
     if (lane == 0) {
-        atomicAdd(&a.counters[0], c_words);
+        if (a.count_words) atomicAdd(&a.counters[0], c_words);
         atomicAdd(&a.counters[1], c_hits);
         atomicAdd(&a.counters[2], c_pass);
         if (c_anom) atomicAdd(&a.counters[3], c_anom);

@@ -95,7 +95,7 @@ typedef struct imsame_stats {
     uint32_t k2_launches, k3_launches, total_launches;
     uint32_t k3_packed_launches; /* of k3_launches: packed-word kernel (imsame_gpu_set_nw_mode) */
     float ms_comm;               /* NCCL reductions of a sharded run (imsame_gpu_run_sharded) */
-    uint32_t reserved;
+    uint32_t scan_passes;        /* 1, or 2: early words first (imsame_gpu_set_passes) */
 } imsame_stats;
 
 typedef struct imsame_ctx imsame_ctx;
@@ -202,8 +202,19 @@ int imsame_gpu_nw_batch(imsame_ctx *ctx, uint32_t n_pairs, const unsigned char *
                         const uint32_t *xlen, const unsigned char *const *Y, const uint32_t *ylen,
                         int igap, int egap, int32_t *out5, float *ms_kernel);
 
+/* How the database is scanned.  The reference walks the words of a query read left to right and stops at the
+ * read's first accepted hit (src/alignmentFunctions.c:172,189); a read that is in the database is usually
+ * accepted on one of its first words.  2 = "early words first": scan with the words that end inside the first
+ * 6 of the 32 k-mer-end bands of their read, align those bands, then scan again with the later words of the
+ * reads that are still without an accepted hit only (a third less scan work on config 2; identical records).
+ * 1 = one scan with every word.  0 (default) = 2 when the expected number of seed hits per GPU (query bases x
+ * database bases / 4^k) is at least 4e9, else 1.  Resident samples (imsame_gpu_align_samples) and callers that
+ * step through a run themselves (imsame_gpu_run_begin ...) always get one pass.  In a sharded run the keys are
+ * reduced between the passes; every rank must use the same setting (checked: IMSAME_ESTATE otherwise). */
+int imsame_gpu_set_passes(imsame_ctx *ctx, int mode);
+
 /* Which K3 kernel evaluates the pairs: 0 (default) = the packed-word kernel for every pair that fits it
- * (<= 257 query / 512 database bases, non-positive gap scores; nwp_core.cuh: pw_eligible) and the generic
+ * (<= 321 query / 512 database bases, non-positive gap scores; nwp_core.cuh: pw_eligible) and the generic
  * kernel for the others, pair by pair; 1 = always the generic kernel.  Both give identical results; the
  * switch exists so tests and benchmarks can compare them. */
 int imsame_gpu_set_nw_mode(imsame_ctx *ctx, int mode);

@@ -36,6 +36,7 @@ def _worker(rank, world, port, tmpdir):
     b0, b1 = int(ds[lo]), int(ds[hi])
     ctx = api.Imsame(rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.set_passes(int(os.environ.get("IMSAME_TEST_PASSES", "0")))
     p = api.make_params(n_threads=4, db_total_len_global=len(db), db_pos_base=b0, db_seq_base=lo)
     mode = os.environ.get("IMSAME_TEST_STEPPED", "1")
     keys = torch.empty(nq, dtype=torch.int64, device="cuda")
@@ -50,6 +51,7 @@ def _worker(rank, world, port, tmpdir):
         ctx.comm_init(box[0], world, rank)
         st = ctx.align_shard((db[b0:b1], ds[lo:hi + 1] - ds[lo]), (q, qs), p, keys.data_ptr(), payload.data_ptr())
         assert st["ms_comm"] > 0 and st["h2d_bytes"] >= (b1 - b0) + len(q)
+        assert st["scan_passes"] == max(1, int(os.environ.get("IMSAME_TEST_PASSES", "0")))
     elif mode == "nccl_in_library":
         # the product path: the library's own communicator (ncclCommInitRank from 128 bytes handed around by
         # torch.distributed) and its band-stepped run with ncclMin / ncclMax reductions inside
@@ -58,6 +60,7 @@ def _worker(rank, world, port, tmpdir):
         ctx.comm_init(box[0], world, rank)
         st = ctx.run_sharded(p, keys.data_ptr(), payload.data_ptr())
         assert st["ms_comm"] > 0
+        assert st["scan_passes"] == max(1, int(os.environ.get("IMSAME_TEST_PASSES", "0")))
     elif mode == "1":
         # keys exchanged between bands (what bench.py does), payload of the owner at the end
         ctx.run_stepped(p, keys.data_ptr(), payload.data_ptr(),
@@ -78,13 +81,20 @@ def _worker(rank, world, port, tmpdir):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("stepped", ["nccl_in_library", "align_shard", "1", "0"])
-def test_nccl_sharded_equals_single_gpu(gpu, tmp_path, stepped):
+@pytest.mark.parametrize("stepped,passes", [("nccl_in_library", 0), ("align_shard", 0), ("1", 0), ("0", 0),
+                                            ("nccl_in_library", 2), ("align_shard", 2), ("0", 2)])
+def test_nccl_sharded_equals_single_gpu(gpu, tmp_path, stepped, passes):
+    """passes = 2: early words first (imsame_gpu_set_passes) -- in the library's sharded run the keys are reduced
+    between the two scans, so a read accepted in one shard drops out of the second scan of both"""
     import torch.multiprocessing as mp
     from imsame_b200 import api
     os.environ["IMSAME_TEST_STEPPED"] = stepped
-    port = 29700 + (os.getpid() % 1000) + len(stepped)
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    os.environ["IMSAME_TEST_PASSES"] = str(passes)
+    port = 29700 + (os.getpid() % 1000) + len(stepped) + 7 * passes
+    try:
+        mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    finally:
+        os.environ.pop("IMSAME_TEST_PASSES", None)
     rec = np.load(tmp_path / "rec.npy")
     db, ds, q, qs = sc.fixed_case(31, 4, 80000, 150, 16000, 1500, 0.03)
     whole, _ = gpu.align((db, ds), (q, qs), api.make_params(n_threads=4))
@@ -107,8 +117,11 @@ def test_align_sharded_in_one_process_equals_oracle(gpu):
     n = min(_n_gpus(), 4)
     ctxs = [gpu] + [api.Imsame(d) for d in range(1, n)]
     try:
-        for _ in range(2):  # the second call reuses the communicator kept in the contexts
+        for it in range(3):  # the later calls reuse the communicator kept in the contexts; the last: early words first
+            for c in ctxs:
+                c.set_passes(2 if it == 2 else 0)
             out, stats = api.align_sharded(ctxs, (db, ds), (q, qs), api.make_params(n_threads=4), db_breaks=brk)
+            assert all(s["scan_passes"] == (2 if it == 2 else 1) for s in stats)
             got = {int(r): (int(o["db_seq"]), int(o["qpos_end"]), int(o["db_pos"]), int(o["length"]), int(o["identities"]))
                    for r, o in enumerate(out) if o["accepted"]}
             assert got == want and len(want) > 150
@@ -116,6 +129,7 @@ def test_align_sharded_in_one_process_equals_oracle(gpu):
             assert sum(s["n_db_kmers"] for s in stats) == gpu.align((db, ds), (q, qs), api.make_params(n_threads=4),
                                                                      db_breaks=brk)[1]["n_db_kmers"]
     finally:
+        gpu.set_passes(0)
         for c in ctxs[1:]:
             c.close()
         gpu.comm_free()

@@ -259,6 +259,56 @@ def test_read_size_error_exactly_when_the_reference_stops(gpu):
     assert gpu_records(out) == want
 
 
+def test_early_words_first_gives_the_same_records(gpu):
+    """two-pass runs (imsame_gpu_set_passes: scan with the words that end in the first bands of their read, align,
+    then scan again with the later words of the still unaccepted reads only): the records equal the oracle's and the
+    one-pass run's, fewer seed hits are extended; fixed-length reads with both chunkings of the phantom word, ragged
+    reads with word breaks and other thresholds, 300-base reads, a seed length other than 12"""
+    from imsame_b200 import api
+    rng = np.random.default_rng(5)
+    cases = []
+    db, ds, q, qs = sc.fixed_case(1001, 4, 100000, 150, 20000, 2000, 0.03)
+    cases += [("fixed/1", db, ds, q, qs, None, dict(n_threads=1), {}), ("fixed/4", db, ds, q, qs, None, dict(n_threads=4), {})]
+    db, ds, q, qs = sc.ragged_case(11, 3, 60000, 6000, 900, 0.05)
+    brk = np.unique(rng.integers(1, len(db), size=300)).astype(np.uint64)
+    brk = np.array([b for b in brk if b not in set(ds.tolist())], dtype=np.uint64)
+    cases += [("ragged+breaks", db, ds, q, qs, brk, dict(n_threads=3), {}),
+              ("ragged/thresholds", db, ds, q, qs, None, dict(n_threads=3, min_coverage=0.8, min_identity=0.9),
+               dict(coverage=0.8, identity=0.9))]
+    db, ds, q, qs = sc.fixed_case(3001, 3, 60000, 300, 5000, 800, 0.03)
+    cases += [("wide", db, ds, q, qs, None, dict(n_threads=4), {})]
+    try:
+        for name, db, ds, q, qs, brk, gk, ok in cases:
+            want, _ = oracle_records(db, ds, q, qs, gk["n_threads"], breaks=brk, **ok)
+            p = api.make_params(**gk)
+            gpu.set_passes(2)
+            out2, st2 = gpu.align((db, ds), (q, qs), p, db_breaks=brk)
+            gpu.set_passes(1)
+            out1, st1 = gpu.align((db, ds), (q, qs), p, db_breaks=brk)
+            assert st2["scan_passes"] == 2 and st1["scan_passes"] == 1, name
+            assert gpu_records(out2) == want and gpu_records(out1) == want and len(want) > 100, name
+            assert st2["n_hits"] < st1["n_hits"] and st2["n_db_kmers"] == st1["n_db_kmers"], name
+            assert st2["k2_launches"] == 2 * st1["k2_launches"], name
+        # the same context, device-resident inputs, a run of each kind after the other (tables of both kinds are kept)
+        name, db, ds, q, qs, brk, gk, ok = cases[0]
+        want, _ = oracle_records(db, ds, q, qs, gk["n_threads"])
+        p = api.make_params(**gk)
+        gpu.set_query((q, qs), p)
+        gpu.set_db((db, ds))
+        for mode in (2, 1, 2, 2):
+            gpu.set_passes(mode)
+            st = gpu.run(p)
+            assert st["scan_passes"] == mode
+            assert gpu_records(gpu.fetch()) == want
+        gpu.set_kmer(9)
+        gpu.set_passes(2)
+        out, st = gpu.align((db, ds), (q, qs), p)
+        assert st["scan_passes"] == 2 and gpu_records(out) == oracle_records(db, ds, q, qs, gk["n_threads"], k=9)[0]
+    finally:
+        gpu.set_kmer(12)
+        gpu.set_passes(0)
+
+
 def test_packed_and_generic_kernels_give_the_same_records(gpu):
     from imsame_b200 import api
     db, ds, q, qs = sc.fixed_case(41, 4, 100000, 250, 30000, 1500, 0.08)
