@@ -420,8 +420,11 @@ int ensure_pairs(imsame_ctx *ctx, uint64_t need) {
     int rc;
     if ((rc = dev_alloc(ctx, &np, cap))) return rc;
     if ((rc = dev_alloc(ctx, &nr, cap))) { cudaFree(np); return rc; }
-    if (ctx->pairs && ctx->pairs_cap)
+    if (ctx->pairs && ctx->pairs_cap) {
         CK(cudaMemcpyAsync(np, ctx->pairs, ctx->pairs_cap * sizeof(PairRec), cudaMemcpyDeviceToDevice, ctx->stream));
+        // (a two-pass run grows the list during its second scan, when the NW results of the first pass are in place)
+        CK(cudaMemcpyAsync(nr, ctx->res, ctx->pairs_cap * sizeof(PairRes), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));  // (segment-major experiment: NW launches may run there)
     dev_free(ctx->pairs); dev_free(ctx->res);
