@@ -106,8 +106,45 @@ static Res dispatch(int s, const unsigned char *X, int xlen, const unsigned char
     fprintf(stderr, "bad S\n"); exit(2);
 }
 
+// A run whose longest reads are eligible launches no other NW kernel (capi.cu: use_packed), and a mixed run gives the
+// packed-word kernel every pair that is eligible under the RUN's score offset: check that eligibility with a run's
+// offset really holds for every pair inside the run's box of lengths, and that the class of a query read gives its
+// packed-word kernel enough columns (nw.cuh is not included here: 16 lanes x 2 * class columns, classes as below).
+static int check_eligibility_boxes() {
+    int bad = 0;
+    const int gaps[][2] = {{-5, -2}, {0, 0}, {-8, -1}, {-7, -3}, {-1, 0}, {-12, -4}, {-40, -3}, {-3, -1}};
+    for (auto &g : gaps) {
+        for (int trial = 0; trial < 40; trial++) {
+            uint32_t xmax = 2 + rnd() % 560, ymax = 2 + rnd() % 340;
+            if (trial == 0) { xmax = 512; ymax = 321; }
+            if (trial == 1) { xmax = 250; ymax = 250; }
+            if (trial == 2) { xmax = 3000; ymax = 3000; }
+            if (trial == 3) { xmax = 300; ymax = 300; }
+            const int bias = pw_bias(xmax, ymax, g[0], g[1]);
+            if (xmax == 250 && ymax == 250 && g[0] == -5 && bias != 0) { printf("cfg2 must not need a score offset\n"); bad++; }
+            if (pw_eligible(xmax, ymax, g[0], g[1], bias)) {  // "packed" run: every pair of the box must be eligible
+                for (uint32_t x = 2; x <= xmax; x++)
+                    for (uint32_t y = 2; y <= ymax; y++)
+                        if (!pw_pair_eligible(x, y, g[0], g[1], bias)) { if (bad++ < 5) printf("box %u x %u gaps %d,%d: pair %u x %u not eligible\n", xmax, ymax, g[0], g[1], x, y); }
+            }
+            // whatever the run: an eligible pair keeps every field inside its bits (the bounds pw_eligible states)
+            for (int k = 0; k < 2000; k++) {
+                const uint32_t x = 2 + rnd() % (xmax < 600 ? xmax : 600), y = 2 + rnd() % (ymax < 340 ? ymax : 340);
+                if (!pw_pair_eligible(x, y, g[0], g[1], bias)) continue;
+                const int X1 = (int)x - 1, Y1 = (int)y - 1, mn = X1 < Y1 ? X1 : Y1;
+                const long depth = pw_depth(x, y, g[0], g[1]);
+                const bool ok = y <= (uint32_t)PW_MAX_Y && x <= (uint32_t)PW_MAX_X && depth - bias <= 1890 && 4L * (mn + 1) + bias <= 2040 &&
+                                X1 + Y1 + 3 <= 1023 && (Y1 > PW_NARROW_Y1 || mn <= 255) && mn <= 511;
+                if (!ok && bad++ < 5) printf("pair %u x %u gaps %d,%d bias %d: field bounds violated\n", x, y, g[0], g[1], bias);
+            }
+        }
+    }
+    return bad;
+}
+
 int main(int argc, char **argv) {
     int n = argc > 1 ? atoi(argv[1]) : 200; rng_state = argc > 2 ? strtoull(argv[2], 0, 10) : 1;
+    if (check_eligibility_boxes()) { printf("eligibility self-check failed\n"); return 1; }
     const char B[4] = {'A', 'C', 'G', 'T'};
     int bad = 0, skipped = 0;
     for (int it = 0; it < n; it++) {
