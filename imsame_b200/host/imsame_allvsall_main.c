@@ -22,6 +22,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 
 #include "imsame_host.h"
 #include "imsame_job.h"
@@ -196,6 +197,14 @@ int main(int argc, char **av) {
                 fflush(stdout);
             }
     fprintf(stdout, "[INFO] %" PRIu64 " comparisons of %zu samples in %.3f s\n", jobs, n, now_s() - t_all);
+    fflush(stdout);
+    /* every output file is closed: as in IMSAME (imsame_main.c) the release of the device and host memory is left
+       to the operating system unless IMSAME_FAST_EXIT=0 asks for the orderly one */
+    const char *fast = getenv("IMSAME_FAST_EXIT");
+    if (!(fast && fast[0] == '0')) {
+        fflush(stderr);
+        _exit(0);
+    }
     for (size_t i = 0; i < n; i++) {
         imsame_gpu_sample_free(ctx, sm[i].dfwd);
         imsame_gpu_sample_free(ctx, sm[i].drev);
