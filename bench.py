@@ -20,7 +20,8 @@ NW, D2H of the records.
 
 After the timed region (never inside it):
   sampled_parity  1024 seeded random query reads re-derived by the index-free CPU oracle (oracle/imsame_sampled.c)
-                  against this run's full-size database (per shard + min-key merge at N > 1), all record fields equal
+                  against this run's full-size database (per shard + min-key merge at N > 1), all record fields equal;
+                  its `cpu_port_same_database` is the port's reads/s on that sample (the one CPU figure at full database size)
   sharded_check   N > 1: the library's band-stepped NCCL run == independent shard runs reduced through torch.distributed
   same_config     N = 1: configs[0] at full size through the unmodified reference binary (whole process and alignment
                   phase, all host threads) and through imsame_gpu_align, record sets compared
@@ -378,6 +379,7 @@ def sampled_parity(n_sample, rec, db, ds, q, qs, db_total_global, rank, world, n
     p = hp.default_params(n_threads=4, db_total_len_global=db_total_global)
     got, st = hp.oracle_align_sampled(hp.OracleSeqs(seq=db, start=ds), hp.OracleSeqs(seq=q, start=qs), p, reads,
                                       db_pos_base=rank * nd * L, db_seq_base=rank * nd)
+    t_oracle = time.perf_counter() - t0
     # oracle winners of this shard -> the same (key, payload) words the product reduces
     from imsame_b200 import sharding
     ok = np.full(n_sample, sharding.KEY_NONE, dtype=np.int64)
@@ -412,7 +414,13 @@ def sampled_parity(n_sample, rec, db, ds, q, qs, db_total_global, rank, world, n
            "fields": "accepted, db_seq, qpos_end, db_pos, length, identities",
            "oracle": "oracle/imsame_sampled.c (index-free scan-order replay), per shard + min-key merge",
            "oracle_hits_this_rank": int(st.hits), "oracle_nw_calls_this_rank": int(st.nw_calls),
-           "seconds": round(time.perf_counter() - t0, 1)}
+           "seconds": round(time.perf_counter() - t0, 1),
+           # the only CPU execution of the reference's algorithm against the FULL database of the workload (the reference's
+           # own index cannot hold it): per-read cost of the port on this rank's shard.  It extends every seed hit of the
+           # sampled reads (the reference skips the later words of an accepted read) and runs exactly the reference's NW calls.
+           "cpu_port_same_database": {"reads_per_s": round(n_sample / max(t_oracle, 1e-9), 1), "seconds": round(t_oracle, 2),
+                                      "threads": max(1, (os.cpu_count() or 1) // max(1, world)), "kind": "port",
+                                      "what": "oracle/imsame_sampled.c, %d sampled query reads vs this rank's %d-read shard" % (n_sample, nd)}}
     if first_bad:
         out["first_mismatch"] = first_bad
     return out
