@@ -135,12 +135,14 @@ int main(int argc, char **av) {
     if (!d) terror("Could not open the metagenomes directory");
     size_t n = 0, cap = 16, el = strlen(ext);
     sample *sm = (sample *)calloc(cap, sizeof(sample));
+    if (!sm) terror("Could not allocate memory for the sample list");
     for (struct dirent *e; (e = readdir(d)) != NULL;) {
         const size_t l = strlen(e->d_name);
         if (e->d_name[0] == '.' || l < el + 2 || e->d_name[l - el - 1] != '.' || strcmp(e->d_name + l - el, ext) != 0) continue;
         if (n == cap) {
             cap *= 2;
             sm = (sample *)realloc(sm, cap * sizeof(sample));
+            if (!sm) terror("Could not allocate memory for the sample list");
             memset(sm + n, 0, (cap - n) * sizeof(sample));
         }
         sm[n].name = strndup(e->d_name, l - el - 1);

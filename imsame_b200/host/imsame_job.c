@@ -73,6 +73,10 @@ int imsame_run_job(const imsame_fasta *qf, const imsame_fasta *dbf, const imsame
         ctx_job *jobs = (ctx_job *)calloc((size_t)ng, sizeof(ctx_job));
         pthread_t *th = (pthread_t *)calloc((size_t)ng, sizeof(pthread_t));
         imsame_ctx **ctxs = (imsame_ctx **)calloc((size_t)ng, sizeof(imsame_ctx *));
+        if (!jobs || !th || !ctxs) {
+            free(jobs); free(th); free(ctxs); free(best);
+            return IMSAME_ENOMEM;
+        }
         for (int g = 0; g < ng; g++) {
             jobs[g].device = o->device + g;
             jobs[g].kmer = kmer;
@@ -107,7 +111,7 @@ int imsame_run_job(const imsame_fasta *qf, const imsame_fasta *dbf, const imsame
         if (!ctx && (rc = imsame_gpu_create(&ctx, o->device))) { free(best); return rc; }
         uint64_t *ops_off = (uint64_t *)malloc((q.n_seqs + 1) * sizeof(uint64_t));
         uint32_t *cell = (uint32_t *)malloc(4 * q.n_seqs * sizeof(uint32_t)), *ops = NULL;
-        rc = imsame_gpu_traceback(ctx, &dv, &qv, &p, best, ops_off, &ops, cell);
+        rc = (ops_off && cell) ? imsame_gpu_traceback(ctx, &dv, &qv, &p, best, ops_off, &ops, cell) : IMSAME_ENOMEM;
         if (rc) {
             if (err && errlen) snprintf(err, errlen, "%s", imsame_gpu_last_cuda_error(ctx));
         } else {
