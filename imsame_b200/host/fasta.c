@@ -245,18 +245,32 @@ int imsame_revcomp_mem(const unsigned char *buf, size_t n, unsigned char **out, 
     comp['a'] = 't'; comp['c'] = 'g'; comp['g'] = 'c'; comp['t'] = 'a'; comp['u'] = 'a';
     size_t cap = 1024, nrec = 0;
     size_t *off = (size_t *)malloc(cap * sizeof(size_t));
-    unsigned char *dst = (unsigned char *)malloc(2 * n + 16); /* every record gains at most one '\n' */
-    if (!off || !dst) { free(off); free(dst); return IMSAME_ENOMEM; }
+    if (!off) return IMSAME_ENOMEM;
     for (size_t i = 0; i < n; i++)
         if (buf[i] == '>') {
             if (nrec == cap) {
                 cap *= 2;
                 size_t *o2 = (size_t *)realloc(off, cap * sizeof(size_t));
-                if (!o2) { free(off); free(dst); return IMSAME_ENOMEM; }
+                if (!o2) { free(off); return IMSAME_ENOMEM; }
                 off = o2;
             }
             off[nrec++] = i;
         }
+    /* Size of the output: a record is its header line + its letters + '\n'.  A header line that holds further
+       '>' bytes is copied once per '>' (every '>' starts a record, :47-52, and the header runs to the end of the
+       line, :59), so the output can be far longer than the input: count first.  Header end and body end of
+       record r are the same two scans in both passes. */
+    size_t total = 0;
+    for (size_t r = 0; r < nrec; r++) {
+        size_t h = off[r];
+        while (h < n && buf[h] != '\n') h++;
+        if (h < n) h++;
+        size_t end = h;
+        while (end < n && buf[end] != '>') end++;
+        total += (h - off[r]) + (end - h) + 1;
+    }
+    unsigned char *dst = (unsigned char *)malloc(total + 16);
+    if (!dst) { free(off); return IMSAME_ENOMEM; }
     size_t w = 0;
     for (size_t r = nrec; r-- > 0;) {
         /* header = up to the first newline (fgets, :59), even if it holds another '>';

@@ -96,7 +96,12 @@ static void need_forward_dev(sample *s, imsame_ctx *ctx) {
 static void need_reverse_dev(sample *s, imsame_ctx *ctx) {
     if (s->drev) return;
     int rc;
-    if (s->has_u || !s->have_fwd) {
+    /* The device reverse complement works on the parsed reads.  revComp works on the text, where EVERY '>' byte
+       starts a record (src/reverseComplement.c:47-52): a header line that holds further '>' bytes comes out once
+       per '>' and the loader then sees that read several times.  Such a sample (its reverse complement parses into
+       a different number of reads or bases than the sample itself) is uploaded from the text form, like one with 'U'. */
+    const int same_shape = s->have_fwd && s->have_rev && s->rev.n_seqs == s->fwd.n_seqs && s->rev.total_len == s->fwd.total_len;
+    if (s->has_u || !s->have_fwd || !same_shape) {
         imsame_seqinfo v;
         imsame_fasta_view(&s->rev, &v);
         rc = imsame_gpu_sample_create(ctx, &v, &s->drev);

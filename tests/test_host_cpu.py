@@ -123,6 +123,53 @@ def test_revcomp_matches_reference_semantics(built, tmp_path):
         assert ref2.read_bytes() == out2.read_bytes()
 
 
+def test_revcomp_header_lines_with_many_record_starts(built, tmp_path):
+    """every '>' byte starts a record (src/reverseComplement.c:47-52) and a record's header runs to the end of its
+    line (:59), so a line holding m '>' bytes comes out m times: the output is longer than twice the input (the
+    first implementation sized its buffer 2 n + 16 and overflowed; found by fuzzing against the reference tool)"""
+    src = tmp_path / "in.fa"
+    line = b">" * 40 + b"tail of the line" * 4 + b"\n"
+    src.write_bytes(b">first rec\nACGT\n" + line + b"ACGTTGCA\n" + line)
+    out = tmp_path / "out.fa"
+    subprocess.check_call([os.path.join(hp.ROOT, "bin", "revComp"), str(src), str(out)])
+    got = out.read_bytes()
+    assert len(got) > 2 * len(src.read_bytes()) + 16
+    want = b""
+    for body in (b"", b"TGCAACGT"):  # records in reverse file order; all 40 of a line share the body after it
+        for k in range(40):  # the last '>' of the line first
+            want += b">" * (k + 1) + b"tail of the line" * 4 + b"\n" + body + b"\n"
+    want += b">first rec\nACGT\n"
+    assert got == want
+    if os.path.exists(hp.REF_REVCOMP):
+        ref = tmp_path / "ref.fa"
+        subprocess.check_call([hp.REF_REVCOMP, str(src), str(ref)])
+        assert ref.read_bytes() == got
+
+
+@pytest.mark.skipif(not os.path.exists(hp.REF_REVCOMP), reason="oracle/_ref not built")
+def test_revcomp_fuzz_against_the_reference_tool(built, tmp_path):
+    """seeded random byte soup (record starts anywhere, CRLF, tabs, U/u, IUPAC letters, empty files): same output
+    file, same stdout, same exit status as the compiled reference tool"""
+    rng = np.random.default_rng(5)
+    tokens = [b"A", b"C", b"G", b"T", b"a", b"c", b"g", b"t", b"N", b"n", b"\n", b"\r\n", b">", b">h\n", b" ", b"-", b"U", b"u",
+              b"R", b"\t", b"ACGTACGTACGTACGTACGTTTGGCCAA", b"\n>x y\n", b"\n\n", b">\n"]
+    src, o1, o2 = (str(tmp_path / n) for n in ("in.fa", "o1", "o2"))
+    compared = 0
+    for it in range(400):
+        body = b"".join(tokens[i] for i in rng.integers(0, len(tokens), size=int(rng.integers(0, 120))))
+        if it % 2 == 0:
+            body = b">first rec\n" + body
+        open(src, "wb").write(body)
+        r2 = subprocess.run([hp.REF_REVCOMP, src, o2], capture_output=True)
+        if r2.returncode < 0:
+            continue  # the reference itself died on a signal: nothing to compare with
+        r1 = subprocess.run([os.path.join(hp.ROOT, "bin", "revComp"), src, o1], capture_output=True)
+        assert (r1.returncode, r1.stdout) == (r2.returncode, r2.stdout), (it, body)
+        assert open(o1, "rb").read() == open(o2, "rb").read(), (it, body)
+        compared += 1
+    assert compared > 300
+
+
 def test_c_abi_exports_every_declared_symbol(built):
     from imsame_b200 import api
     hdr = open(os.path.join(hp.ROOT, "include", "imsame_gpu.h")).read()
