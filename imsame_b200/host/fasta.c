@@ -132,7 +132,10 @@ int imsame_fasta_parse_mem(const unsigned char *buf, size_t flen, int is_db, ims
     np = omp_get_max_threads();
 #endif
     if (np > 256) np = 256;
-    if ((size_t)np > flen / (1 << 20) + 1) np = (int)(flen / (1 << 20) + 1); /* >= 1 MB per piece */
+    size_t piece = 1 << 20; /* >= 1 MB per piece */
+    const char *tp = getenv("IMSAME_TEST_FASTA_PIECE"); /* test hook (tools/host_fuzz.c): many pieces on small inputs */
+    if (tp && atol(tp) > 0) { piece = (size_t)atol(tp); np = 256; }
+    if ((size_t)np > flen / piece + 1) np = (int)(flen / piece + 1);
     size_t cut[257];
     cut[0] = 0;
     for (int k = 1; k < np; k++) {

@@ -170,6 +170,28 @@ def test_revcomp_fuzz_against_the_reference_tool(built, tmp_path):
     assert compared > 300
 
 
+def test_host_fuzz_under_sanitizers(tmp_path):
+    """tools/host_fuzz.c built with AddressSanitizer + UBSan: the threaded FASTA parser cut into pieces of a few
+    bytes against a char-at-a-time model of the reference loader (src/IMSAME.c:193-285, :323-347), revComp and the
+    parse of its output, the renderer on random paths with the buffer imsame_host.h promises"""
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    probe = tmp_path / "p.c"
+    probe.write_text("int main(void){return 0;}")
+    san = ["-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-fno-omit-frame-pointer"]
+    if subprocess.run([cc, *san, str(probe), "-o", str(tmp_path / "p")], capture_output=True).returncode != 0:
+        pytest.skip("no sanitizer runtime for this gcc")
+    omp = ["-fopenmp"] if subprocess.run([cc, "-fopenmp", str(probe), "-o", str(tmp_path / "p")], capture_output=True).returncode == 0 else []
+    exe = str(tmp_path / "host_fuzz")
+    host = os.path.join(hp.ROOT, "imsame_b200", "host")
+    subprocess.check_call([cc, "-O1", "-g", "-Wall", *omp, *san, "-D_FILE_OFFSET_BITS=64", os.path.join(hp.ROOT, "tools", "host_fuzz.c"),
+                           os.path.join(host, "fasta.c"), os.path.join(host, "render.c"), "-lm", "-o", exe])
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", OMP_NUM_THREADS="4")
+    env.pop("LD_PRELOAD", None)
+    r = subprocess.run([exe, "500", "7"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout and "2000 parses" in r.stdout
+
+
 def test_c_abi_exports_every_declared_symbol(built):
     from imsame_b200 import api
     hdr = open(os.path.join(hp.ROOT, "include", "imsame_gpu.h")).read()
