@@ -297,6 +297,29 @@ int imsame_revcomp_mem(const unsigned char *buf, size_t n, unsigned char **out, 
     return IMSAME_OK;
 }
 
+/* Is `rev` (the parse of revComp's output for a sample) exactly the mirror image of `fwd` (the parse of the sample):
+ * the concatenated bases reversed and complemented, read offsets and word breaks mirrored?  Then -- and only then --
+ * the device may derive the reverse-complemented read set from the packed forward one (csrc/capi_samples.inc).
+ * It is not whenever revComp's text filter and the loader's disagree: revComp keeps letters only
+ * (src/reverseComplement.c:65-70), so a '\r', '-', '*' or digit inside a record restarts the database's seed word in
+ * the sample (src/IMSAME.c:229-231) but not in its reverse complement; 'U' comes back as an 'A' the loader keeps;
+ * a header line with several '>' bytes comes out once per '>'. */
+int imsame_revcomp_is_mirror(const imsame_fasta *fwd, const imsame_fasta *rev) {
+    if (fwd->n_seqs != rev->n_seqs || fwd->total_len != rev->total_len || fwd->n_breaks != rev->n_breaks) return 0;
+    const uint64_t n = fwd->n_seqs, total = fwd->total_len, nb = fwd->n_breaks;
+    for (uint64_t i = 0; i <= n; i++)
+        if (rev->start_pos[i] != total - fwd->start_pos[n - i]) return 0;
+    for (uint64_t i = 0; i < nb; i++)
+        if (rev->break_pos[i] != total - fwd->break_pos[nb - 1 - i]) return 0;
+    unsigned char comp[256];
+    memset(comp, 0, sizeof comp);
+    comp['A'] = 'T'; comp['C'] = 'G'; comp['G'] = 'C'; comp['T'] = 'A';
+    int differ = 0;
+#pragma omp parallel for reduction(| : differ) schedule(static)
+    for (int64_t i = 0; i < (int64_t)total; i++) differ |= rev->sequences[i] != comp[fwd->sequences[total - 1 - (uint64_t)i]];
+    return !differ;
+}
+
 void imsame_fasta_free(imsame_fasta *f) {
     free(f->sequences);
     free(f->start_pos);

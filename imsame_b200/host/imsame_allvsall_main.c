@@ -96,11 +96,11 @@ static void need_forward_dev(sample *s, imsame_ctx *ctx) {
 static void need_reverse_dev(sample *s, imsame_ctx *ctx) {
     if (s->drev) return;
     int rc;
-    /* The device reverse complement works on the parsed reads.  revComp works on the text, where EVERY '>' byte
-       starts a record (src/reverseComplement.c:47-52): a header line that holds further '>' bytes comes out once
-       per '>' and the loader then sees that read several times.  Such a sample (its reverse complement parses into
-       a different number of reads or bases than the sample itself) is uploaded from the text form, like one with 'U'. */
-    const int same_shape = s->have_fwd && s->have_rev && s->rev.n_seqs == s->fwd.n_seqs && s->rev.total_len == s->fwd.total_len;
+    /* The device reverse complement works on the packed forward reads; revComp works on the text, and its filter is
+       not the loader's (imsame_revcomp_is_mirror, host/fasta.c: '\r' / '-' / digits inside a record, 'U', header lines
+       with several '>').  Both parses are in memory for the renderer anyway: the device path is taken only when
+       the parse of revComp's text IS the mirror image of the sample, otherwise that parse is uploaded. */
+    const int same_shape = s->have_fwd && s->have_rev && imsame_revcomp_is_mirror(&s->fwd, &s->rev);
     if (s->has_u || !s->have_fwd || !same_shape) {
         imsame_seqinfo v;
         imsame_fasta_view(&s->rev, &v);

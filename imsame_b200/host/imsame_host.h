@@ -37,6 +37,8 @@ int imsame_file_map(const char *path, imsame_file_image *img);
 void imsame_file_unmap(imsame_file_image *img);
 /* src/reverseComplement.c on a memory image; *out is malloc'ed */
 int imsame_revcomp_mem(const unsigned char *buf, size_t n, unsigned char **out, size_t *out_len);
+/* 1 when `rev` (parse of revComp's output) is exactly the mirror image of `fwd`: bases, read offsets, word breaks */
+int imsame_revcomp_is_mirror(const imsame_fasta *fwd, const imsame_fasta *rev);
 void imsame_fasta_free(imsame_fasta *f);
 void imsame_fasta_view(const imsame_fasta *f, imsame_seqinfo *v);
 

@@ -114,6 +114,28 @@ def load_fasta(path, is_db):
     return seq, start, brk
 
 
+def revcomp_is_mirror(text):
+    """does the parse of revComp(text) mirror the parse of `text` (bases, read offsets, word breaks)?  The test
+    bin/IMSAME_allvsall makes before it derives a reverse-complemented read set on the device."""
+    l = lib()
+    l.imsame_fasta_parse_mem.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(Fasta)]
+    l.imsame_revcomp_mem.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    l.imsame_revcomp_is_mirror.argtypes = [C.POINTER(Fasta), C.POINTER(Fasta)]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    fwd, rev, out, n = Fasta(), Fasta(), C.c_void_p(), C.c_size_t()
+    if l.imsame_fasta_parse_mem(text, len(text), 1, C.byref(fwd)) or l.imsame_revcomp_mem(text, len(text), C.byref(out), C.byref(n)):
+        raise MemoryError("parse / revcomp")
+    rc_text = C.string_at(out, n.value)
+    libc.free(out)
+    if l.imsame_fasta_parse_mem(rc_text, len(rc_text), 1, C.byref(rev)):
+        raise MemoryError("parse")
+    r = bool(l.imsame_revcomp_is_mirror(C.byref(fwd), C.byref(rev)))
+    l.imsame_fasta_free(C.byref(fwd))
+    l.imsame_fasta_free(C.byref(rev))
+    return r
+
+
 def threshold_tables(min_e_value, min_coverage, min_identity, db_total_len, max_read=3000):
     nmin = np.zeros(max_read + 1, dtype=np.uint16)
     lmin = np.zeros(max_read + 1, dtype=np.uint16)

@@ -70,3 +70,41 @@ def random_pairs(seed, n, max_len=300, long_every=0):
         xs.append(np.ascontiguousarray(x))
         ys.append(np.ascontiguousarray(y))
     return xs, ys
+
+
+def _revcomp(b):
+    return b.translate(bytes.maketrans(b"ACGT", b"TGCA"))[::-1]
+
+
+def write_allvsall_filter_samples(d):
+    """four samples for the all-vs-all tests about revComp's text filter vs the loader's (tests/test_gpu_zz_allvsall_text_filters.py,
+    tests/test_host_cpu.py): s0 forward strand and clean; s1-s3 reverse strand (so that the .r.align files hold records)"""
+    from imsame_b200 import hostlib as H
+    pool = H.SynthPool(4107, 3, 30000)
+    L, n = 150, 400
+    sets = [pool.db_reads(i * 1000, n, L) for i in range(4)]
+    pool.close()
+    reads = [[bytes(s[r * L:(r + 1) * L]) for r in range(n)] for s in sets]
+    with open(d / "s0.fasta", "wb") as f:  # forward strand, clean
+        for r, b in enumerate(reads[0]):
+            f.write(b">a%d\n" % r + b + b"\n")
+    with open(d / "s1.fasta", "wb") as f:  # reverse strand, multi-line CRLF: '\r' inside every record
+        for r, b in enumerate(reads[1]):
+            b = _revcomp(b)
+            f.write(b">b%d\r\n" % r + b[:70] + b"\r\n" + b[70:] + b"\r\n")
+    with open(d / "s2.fasta", "wb") as f:  # reverse strand, gap characters / 'U' / digits inside some records
+        for r, b in enumerate(reads[2]):
+            b = _revcomp(b)
+            if r % 3 == 0:
+                b = b[:60] + b"-" + b[60:]
+            elif r % 3 == 1:
+                b = b[:90] + b"U" + b[90:]
+            elif r % 7 == 2:
+                b = b[:30] + b"12 " + b[30:]
+            f.write(b">c%d\n" % r + b + b"\n")
+    with open(d / "s3.fasta", "wb") as f:  # reverse strand, clean apart from 'N' (a letter: kept by revComp): device path
+        for r, b in enumerate(reads[3]):
+            b = _revcomp(b)
+            if r % 5 == 0:
+                b = b[:100] + b"N" + b[100:]
+            f.write(b">d%d\n" % r + b + b"\n")

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import helpers as hp
+import synth_cases as sc
 
 G = os.path.join(hp.ROOT, "tests", "golden")
 
@@ -168,6 +169,76 @@ def test_revcomp_fuzz_against_the_reference_tool(built, tmp_path):
         assert open(o1, "rb").read() == open(o2, "rb").read(), (it, body)
         compared += 1
     assert compared > 300
+
+
+def test_device_revcomp_only_for_samples_whose_revcomp_is_their_mirror(built):
+    """bin/IMSAME_allvsall derives the reverse-complemented read set on the device from the packed forward one only
+    when revComp's text parses into exactly its mirror image (imsame_revcomp_is_mirror).  revComp keeps letters only
+    (src/reverseComplement.c:65-70) while the database loader restarts the seed word at every dropped character but
+    the newline (src/IMSAME.c:229-231): a CRLF file, gap characters, 'U' and repeated '>' all break the symmetry."""
+    from imsame_b200 import hostlib as H
+    body = b"ACGTTGCAGGCATTACGGATCCATGCAAGT"
+    assert H.revcomp_is_mirror(b">a\n" + body + b"\n>b\n" + body[::-1] + b"\n" + body[:11] + b"\n>c x\nacgtacgtTTGA\n")
+    assert H.revcomp_is_mirror(b">a\n" + body + b"N" + body + b"\n>b\nNN" + body + b"NN\n")  # letters break words both ways
+    assert H.revcomp_is_mirror(b">only header\n")
+    assert H.revcomp_is_mirror(b"")
+    # multi-line records with CRLF: '\r' restarts the word in the sample, revComp drops it and writes one line
+    assert not H.revcomp_is_mirror(b">a\r\n" + body + b"\r\n" + body + b"\r\n>b\r\n" + body + b"\r\n")
+    assert H.revcomp_is_mirror(b">a\r\n" + body + b"\r\n>b\r\n" + body + b"\r\n")  # a trailing '\r' is no word break
+    assert not H.revcomp_is_mirror(b">a\n" + body + b"-" + body + b"\n")      # gap character
+    assert not H.revcomp_is_mirror(b">a\n" + body + b"*7 " + body + b"\n")
+    assert not H.revcomp_is_mirror(b">a\n" + body + b"U" + body + b"\n")      # U -> A, which the loader keeps
+    assert not H.revcomp_is_mirror(b">a>b\n" + body + b"\n")                  # one record per '>' byte
+    rng = np.random.default_rng(3)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    clean = b"".join(b">r%d\n" % i + alphabet[rng.choice(9, size=int(rng.integers(1, 300)), p=[.12] * 8 + [.04])].tobytes() + b"\n"
+                     for i in range(500))
+    assert H.revcomp_is_mirror(clean)
+    assert not H.revcomp_is_mirror(clean + b">z\nAC-GT\n")
+
+
+@pytest.mark.skipif(not hp.have_reference(), reason="oracle/_ref not built (no /root/reference here)")
+def test_allvsall_text_filter_samples_reference_workflow_vs_oracle(built, tmp_path):
+    """The CPU half of tests/test_gpu_zz_allvsall_text_filters.py: on its four samples (multi-line CRLF, gap characters,
+    'U', 'N') the UNMODIFIED reference workflow (oracle/_ref script + binaries) and the oracle fed with bin/revComp's
+    text give the same records -- and aligning against the MIRROR of the forward parse (what a device-side reverse
+    complement of the packed sample would be) does not, exactly for the samples imsame_revcomp_is_mirror rejects."""
+    from imsame_b200 import hostlib as H
+    d, o3 = tmp_path / "samples", tmp_path / "out_reference"
+    d.mkdir(); o3.mkdir()
+    sc.write_allvsall_filter_samples(d)
+    args = [str(d), "0.5", "0.5", "2", "fasta"]
+    subprocess.run(["bash", os.path.join(hp.ROOT, "oracle", "_ref", "all_vs_all_metagenomes_IMSAME.sh")] + args + [str(o3)],
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    assert len(os.listdir(o3)) == 12
+    p = hp.default_params(n_threads=2, coverage=0.5, identity=0.5)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    for y, mirror_ok in (("s1", False), ("s2", False), ("s3", True)):
+        text = (d / f"{y}.fasta").read_bytes()
+        assert H.revcomp_is_mirror(text) == mirror_ok
+        q = hp.OracleSeqs(str(d / "s0.fasta"), False)
+        nq = int(q.s.n_seqs)
+        for rev in (0, 1):
+            dbf = str(d / f"{y}.fasta")
+            if rev:
+                dbf = str(tmp_path / f"{y}.r.fasta")
+                subprocess.check_call([os.path.join(hp.ROOT, "bin", "revComp"), str(d / f"{y}.fasta"), dbf], stdout=subprocess.DEVNULL)
+            oo, name = str(tmp_path / "orc.align"), f"s0-{y}{'.r' if rev else ''}.align"
+            best, _ = hp.oracle_align(hp.OracleSeqs(dbf, True), q, p, out_path=oo)
+            ref_hdr = hp.parse_align_headers(str(o3 / name))
+            assert ref_hdr == hp.parse_align_headers(oo), name
+            assert sorted(open(o3 / name, "rb").read().split(b"\n")) == sorted(open(oo, "rb").read().split(b"\n")), name
+            if rev:
+                assert len(ref_hdr) > 100 and os.path.getsize(o3 / name) > 5000  # reverse-strand samples: records in the .r files
+                fwd = hp.OracleSeqs(str(d / f"{y}.fasta"), True)  # owns the arrays numpy() views
+                seq, start, brk = fwd.numpy()
+                total = len(seq)
+                mirror = hp.OracleSeqs(seq=comp[seq[::-1]].copy(), start=(total - start.astype(np.int64)[::-1]).astype(np.uint64),
+                                       brk=np.sort(total - brk.astype(np.int64)).astype(np.uint64))
+                b2, _ = hp.oracle_align(mirror, q, p)
+                assert (hp.best_to_records(best, nq) == hp.best_to_records(b2, nq)) == mirror_ok, name
 
 
 def test_host_fuzz_under_sanitizers(tmp_path):
