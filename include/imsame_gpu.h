@@ -235,9 +235,13 @@ int imsame_gpu_set_kmer(imsame_ctx *ctx, int k);
  * of any number of comparisons, and keeps the word table built for it as a query.  Its reverse
  * complement is made on the device from the packed form: revComp writes the records in reverse order
  * (src/reverseComplement.c:56) and reverses each one, which together is the whole concatenated array
- * reversed and complemented; start offsets and word breaks are mirrored.  (Letters other than
- * A/C/G/T/U are dropped by the loader either way; a sample containing U must be reverse-complemented
- * as text instead, because revComp turns U into A, which the loader keeps.)
+ * reversed and complemented; start offsets and word breaks are mirrored.  That equals revComp + the
+ * loader exactly when the sample's records hold letters only, no U and one '>' per header line:
+ * revComp keeps letters only (src/reverseComplement.c:65-70) whereas the database loader restarts its
+ * seed word at every dropped character but '\n' (src/IMSAME.c:229-231), so a '\r', '-' or digit inside
+ * a record is a word break of the sample but not of its reverse complement, and revComp turns U into
+ * an A the loader keeps.  imsame_revcomp_is_mirror (imsame_b200/host/imsame_host.h) decides it on the
+ * two parses; otherwise upload the parse of revComp's text with imsame_gpu_sample_create.
  * A sample used as a database must fit one segment (2^29 bases, IMSAME_ELIMIT otherwise). */
 typedef struct imsame_sample imsame_sample;
 int imsame_gpu_sample_create(imsame_ctx *ctx, const imsame_seqinfo *reads, imsame_sample **out);
