@@ -241,59 +241,94 @@ int imsame_fasta_load(const char *path, int is_db, imsame_fasta *out) {
  * copied verbatim (:59-62); only letters are kept from the body (:65-70) and written
  * reverse-complemented on ONE line (:71-112) with A<->T, C<->G, U->A (case preserved), every other
  * letter unchanged.  *out is malloc'ed (free it). */
+/* Threaded like the parser: the '>' bytes are located piece by piece (count, prefix sum, fill), every record's
+ * output length is counted (header line + letters + '\n'), a suffix sum over the records gives each its place in
+ * the output (records come out in reverse order), and a last pass writes them.  A header line that holds further
+ * '>' bytes is copied once per '>' (every '>' starts a record, :47-52, and the header runs to the end of the
+ * line, :59), so the output can be far longer than the input: hence the counting pass. */
+static inline int is_letter(unsigned char c) { return (unsigned)((c | 0x20) - 'a') < 26u; }
+
+/* header end (one past its '\n') and body end (the next '>' at or after the header end) of record r */
+static inline void record_bounds(const unsigned char *buf, size_t n, const size_t *off, size_t nrec, size_t r, size_t *h, size_t *end) {
+    const unsigned char *nl = (const unsigned char *)memchr(buf + off[r], '\n', n - off[r]);
+    *h = nl ? (size_t)(nl - buf) + 1 : n;
+    size_t k = r + 1;
+    while (k < nrec && off[k] < *h) k++; /* '>' bytes inside the header line */
+    *end = k < nrec ? off[k] : n;
+}
+
 int imsame_revcomp_mem(const unsigned char *buf, size_t n, unsigned char **out, size_t *out_len) {
     unsigned char comp[256];
     for (int c = 0; c < 256; c++) comp[c] = (unsigned char)c;
     comp['A'] = 'T'; comp['C'] = 'G'; comp['G'] = 'C'; comp['T'] = 'A'; comp['U'] = 'A';
     comp['a'] = 't'; comp['c'] = 'g'; comp['g'] = 'c'; comp['t'] = 'a'; comp['u'] = 'a';
-    size_t cap = 1024, nrec = 0;
-    size_t *off = (size_t *)malloc(cap * sizeof(size_t));
-    if (!off) return IMSAME_ENOMEM;
-    for (size_t i = 0; i < n; i++)
-        if (buf[i] == '>') {
-            if (nrec == cap) {
-                cap *= 2;
-                size_t *o2 = (size_t *)realloc(off, cap * sizeof(size_t));
-                if (!o2) { free(off); return IMSAME_ENOMEM; }
-                off = o2;
-            }
-            off[nrec++] = i;
-        }
-    /* Size of the output: a record is its header line + its letters + '\n'.  A header line that holds further
-       '>' bytes is copied once per '>' (every '>' starts a record, :47-52, and the header runs to the end of the
-       line, :59), so the output can be far longer than the input: count first.  Header end and body end of
-       record r are the same two scans in both passes. */
+    int np = 1;
+#ifdef _OPENMP
+    np = omp_get_max_threads();
+#endif
+    if (np > 256) np = 256;
+    size_t piece = 1 << 20;
+    const char *tp = getenv("IMSAME_TEST_FASTA_PIECE"); /* test hook, as in imsame_fasta_parse_mem */
+    if (tp && atol(tp) > 0) { piece = (size_t)atol(tp); np = 256; }
+    if ((size_t)np > n / piece + 1) np = (int)(n / piece + 1);
+    /* 1. where the records start */
+    size_t first[257];
+    first[0] = 0;
+#pragma omp parallel for schedule(static, 1) if (np > 1)
+    for (int k = 0; k < np; k++) {
+        const size_t a = n / (size_t)np * (size_t)k, b = k + 1 == np ? n : n / (size_t)np * (size_t)(k + 1);
+        size_t c = 0;
+        for (const unsigned char *g = buf + a; g < buf + b && (g = (const unsigned char *)memchr(g, '>', (size_t)(buf + b - g))) != NULL; g++) c++;
+        first[k + 1] = c;
+    }
+    for (int k = 0; k < np; k++) first[k + 1] += first[k];
+    const size_t nrec = first[np];
+    size_t *off = (size_t *)malloc((nrec + 1) * sizeof(size_t));
+    size_t *place = (size_t *)malloc((nrec + 1) * sizeof(size_t)); /* output length, then output offset, of record r */
+    if (!off || !place) { free(off); free(place); return IMSAME_ENOMEM; }
+#pragma omp parallel for schedule(static, 1) if (np > 1)
+    for (int k = 0; k < np; k++) {
+        const size_t a = n / (size_t)np * (size_t)k, b = k + 1 == np ? n : n / (size_t)np * (size_t)(k + 1);
+        size_t w = first[k];
+        for (const unsigned char *g = buf + a; g < buf + b && (g = (const unsigned char *)memchr(g, '>', (size_t)(buf + b - g))) != NULL; g++)
+            off[w++] = (size_t)(g - buf);
+    }
+    /* 2. output length of every record */
+#pragma omp parallel for schedule(static) if (np > 1)
+    for (int64_t r = 0; r < (int64_t)nrec; r++) {
+        size_t h, end, letters = 0;
+        record_bounds(buf, n, off, nrec, (size_t)r, &h, &end);
+        for (size_t k = h; k < end; k++) letters += (size_t)is_letter(buf[k]);
+        place[r] = (h - off[r]) + letters + 1;
+    }
+    /* 3. records in REVERSE file order (:56): record r starts where the records after it end */
     size_t total = 0;
-    for (size_t r = 0; r < nrec; r++) {
-        size_t h = off[r];
-        while (h < n && buf[h] != '\n') h++;
-        if (h < n) h++;
-        size_t end = h;
-        while (end < n && buf[end] != '>') end++;
-        total += (h - off[r]) + (end - h) + 1;
+    for (size_t r = nrec; r-- > 0;) {
+        const size_t len = place[r];
+        place[r] = total;
+        total += len;
     }
     unsigned char *dst = (unsigned char *)malloc(total + 16);
-    if (!dst) { free(off); return IMSAME_ENOMEM; }
-    size_t w = 0;
-    for (size_t r = nrec; r-- > 0;) {
+    if (!dst) { free(off); free(place); return IMSAME_ENOMEM; }
+#pragma omp parallel for schedule(static) if (np > 1)
+    for (int64_t r = 0; r < (int64_t)nrec; r++) {
         /* header = up to the first newline (fgets, :59), even if it holds another '>';
-           body = up to the next '>' after the header (:65) */
-        size_t i = off[r], h = i;
-        while (h < n && buf[h] != '\n') h++;
-        if (h < n) h++;
-        size_t end = h;
-        while (end < n && buf[end] != '>') end++;
-        memcpy(dst + w, buf + i, h - i);
-        w += h - i;
+           body = up to the next '>' after the header (:65), letters only, reverse-complemented on one line */
+        size_t h, end, w = place[r];
+        record_bounds(buf, n, off, nrec, (size_t)r, &h, &end);
+        memcpy(dst + w, buf + off[r], h - off[r]);
+        w += h - off[r];
         for (size_t k = end; k-- > h;) {
             const unsigned char c = buf[k];
-            if ((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z')) dst[w++] = comp[c];
+            dst[w] = comp[c];
+            w += (size_t)is_letter(c);
         }
-        dst[w++] = '\n';
+        dst[w] = '\n';
     }
     free(off);
+    free(place);
     *out = dst;
-    *out_len = w;
+    *out_len = total;
     return IMSAME_OK;
 }
 

@@ -8,8 +8,9 @@
  *      different threads, against a char-at-a-time model of the reference loader written here
  *      (src/IMSAME.c:193-285 database, :323-347 query: a record starts at '>', its header runs to '\n', only
  *      A/C/G/T are stored upper-cased, a dropped character other than '\n' restarts the seed word);
- *   2. imsame_revcomp_mem on the same soups (sanitizer-checked; its text is pinned to the reference tool by
- *      tests/test_host_cpu.py::test_revcomp_fuzz_against_the_reference_tool), and the parse of its output;
+ *   2. imsame_revcomp_mem (threaded, cut into the same tiny pieces) on the same soups against a serial
+ *      record-by-record model (the form tests/test_host_cpu.py::test_revcomp_fuzz_against_the_reference_tool pinned
+ *      to the reference tool), and the parse of its output;
  *   3. imsame_render_alignment on random paths with the buffer the header promises (6 (xlen + ylen) + 256).
  *
  * usage: host_fuzz [iterations] [seed]          prints one summary line, exit status 1 on a mismatch
@@ -62,6 +63,43 @@ static void model_parse(const unsigned char *b, size_t n, int is_db, model *m) {
 }
 
 static void model_free(model *m) { free(m->seq); free(m->start); free(m->brk); }
+
+/* revComp, one record after the other (src/reverseComplement.c:47-112; this serial form is what
+ * tests/test_host_cpu.py::test_revcomp_fuzz_against_the_reference_tool pinned to the reference tool) */
+static size_t model_revcomp(const unsigned char *b, size_t n, unsigned char **out) {
+    size_t nrec = 0, cap = 0;
+    for (size_t i = 0; i < n; i++) nrec += b[i] == '>';
+    size_t *off = (size_t *)malloc((nrec + 1) * sizeof(size_t));
+    nrec = 0;
+    for (size_t i = 0; i < n; i++)
+        if (b[i] == '>') off[nrec++] = i;
+    for (size_t r = 0; r < nrec; r++) cap += n - off[r] + 2;
+    unsigned char *dst = (unsigned char *)malloc(cap + 1);
+    size_t w = 0;
+    for (size_t r = nrec; r-- > 0;) {
+        size_t i = off[r], h = i;
+        while (h < n && b[h] != '\n') h++;
+        if (h < n) h++;
+        size_t end = h;
+        while (end < n && b[end] != '>') end++;
+        memcpy(dst + w, b + i, h - i);
+        w += h - i;
+        for (size_t k = end; k-- > h;) {
+            unsigned char c = b[k];
+            if (!((c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z'))) continue;
+            switch (c) {
+                case 'A': c = 'T'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; case 'T': c = 'A'; break; case 'U': c = 'A'; break;
+                case 'a': c = 't'; break; case 'c': c = 'g'; break; case 'g': c = 'c'; break; case 't': c = 'a'; break; case 'u': c = 'a'; break;
+                default: break;
+            }
+            dst[w++] = c;
+        }
+        dst[w++] = '\n';
+    }
+    free(off);
+    *out = dst;
+    return w;
+}
 
 static size_t soup(unsigned char *dst, size_t cap) {
     static const char *tok[] = {"A", "C", "G", "T", "a", "c", "g", "t", "N", "n", "\n", "\r\n", ">", ">h\n", " ", "-", "U", "u",
@@ -170,6 +208,15 @@ int main(int argc, char **av) {
         unsigned char *rc = NULL;
         size_t rl = 0;
         if (imsame_revcomp_mem(img, n, &rc, &rl)) { fprintf(stderr, "revcomp failed\n"); return 1; }
+        {
+            unsigned char *want = NULL;
+            const size_t wl = model_revcomp(img, n, &want);
+            if (wl != rl || (rl && memcmp(want, rc, rl))) {
+                fprintf(stderr, "host_fuzz: revcomp mismatch at iteration %llu (%zu bytes in, %zu / %zu bytes out)\n", (unsigned long long)it, n, rl, wl);
+                return 1;
+            }
+            free(want);
+        }
         unsigned char *rimg = (unsigned char *)malloc(rl ? rl : 1);
         memcpy(rimg, rc, rl);
         free(rc);
@@ -181,7 +228,7 @@ int main(int argc, char **av) {
         rendered++;
     }
     free(b);
-    printf("host_fuzz: %llu parses (many pieces each) equal to the char-at-a-time model, %llu rendered paths, 0 mismatches\n",
-           (unsigned long long)parsed, (unsigned long long)rendered);
+    printf("host_fuzz: %llu parses (many pieces each) and %llu reverse complements equal to the serial models, %llu rendered paths, 0 mismatches\n",
+           (unsigned long long)parsed, (unsigned long long)rendered, (unsigned long long)rendered);
     return 0;
 }
