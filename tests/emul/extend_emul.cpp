@@ -1,6 +1,7 @@
 // CPU check of the packed-sequence helpers and the ungapped extension used by the
 // scan kernel (common.cuh / extend.cuh) against the oracle's byte-wise extension.
-//   usage: extend_emul <seed> [k]     (k = seed length, default 12 = the reference's FIXED_K)
+//   usage: extend_emul <seed> [k] [max_len]   (k = seed length, default 12 = the reference's FIXED_K; max_len = longest
+//          read beyond the seed, default 200 -- thousands of bases exercise walks of many windows and the 15-bit step field)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,20 +25,21 @@ int main(int argc, char **argv) {
     rng_state = argc > 1 ? strtoull(argv[1], 0, 10) : 1;
     const int k = argc > 2 ? atoi(argv[2]) : K;
     const uint32_t kmask = kmask_of(k);
+    const int max_len = argc > 3 ? atoi(argv[3]) : 200;
     const char B[4] = {'A', 'C', 'G', 'T'};
     // database: reads of varying length cut from a small genome (so that many words repeat)
-    std::vector<unsigned char> genome(3000);
+    std::vector<unsigned char> genome(max_len > 600 ? (size_t)max_len * 5 : 3000);
     for (auto &c : genome) c = B[rnd() & 3];
     std::vector<unsigned char> D, Q;
     std::vector<uint64_t> ds, qs;
     for (int r = 0; r < 120; r++) {
         ds.push_back(D.size());
-        int len = k + rnd() % 200, at = rnd() % (genome.size() - len);
+        int len = k + rnd() % max_len, at = rnd() % (genome.size() - len);
         for (int i = 0; i < len; i++) D.push_back((rnd() % 100 < 2) ? B[rnd() & 3] : genome[at + i]);
     }
     for (int r = 0; r < 60; r++) {
         qs.push_back(Q.size());
-        int len = k - 1 + rnd() % 200, at = rnd() % (genome.size() - len);
+        int len = k - 1 + rnd() % max_len, at = rnd() % (genome.size() - len);
         for (int i = 0; i < len; i++) Q.push_back((rnd() % 100 < 5) ? B[rnd() & 3] : genome[at + i]);
     }
     ds.push_back(D.size()); qs.push_back(Q.size());
