@@ -1,7 +1,7 @@
 // CPU emulation of the winners-only traceback path: wavefront with back-pointer
 // codes (nw_core.cuh, TB = true) -> tb_walk (traceback.cuh) -> host renderer
 // (host/render.c), compared with the oracle's table-based traceback + text.
-//   usage: tb_emul <n_cases> <seed>
+//   usage: tb_emul <n_cases> <seed> [long_len]   (long_len: every 7th / 5th case draws its X / Y length below it, default 700 / 900)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,11 +58,12 @@ static NwBest run_pair_tb(const unsigned char *X, int xlen, const unsigned char 
 
 int main(int argc, char **argv) {
     int n = argc > 1 ? atoi(argv[1]) : 200; rng_state = argc > 2 ? strtoull(argv[2], 0, 10) : 1;
+    const int long_x = argc > 3 ? atoi(argv[3]) : 700, long_y = argc > 3 ? atoi(argv[3]) : 900;
     const char B[4] = {'A', 'C', 'G', 'T'};
     int bad = 0;
     std::vector<char> want(200000), got(200000);
     for (int it = 0; it < n; it++) {
-        int xlen = 12 + rnd() % (it % 7 == 0 ? 700 : 300), ylen = 11 + rnd() % (it % 5 == 0 ? 900 : 300);
+        int xlen = 12 + rnd() % (it % 7 == 0 ? long_x : 300), ylen = 11 + rnd() % (it % 5 == 0 ? long_y : 300);
         if (it % 11 == 0) { xlen = 250; ylen = 250; }
         if (it % 13 == 0) xlen = 2 + rnd() % 6;
         if (it % 17 == 0) ylen = 2 + rnd() % 6;

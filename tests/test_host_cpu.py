@@ -90,7 +90,7 @@ def test_threshold_tables_are_exact(built):
 @pytest.mark.parametrize("prog,args", [("nw_emul", ["400", "3"]), ("nwp_emul", ["3000", "5"]), ("extend_emul", ["5"]),
                                        ("extend_emul", ["6", "8"]), ("extend_emul", ["7", "15"]),
                                        ("extend_emul", ["5", "12", "3000"]),  # reads of up to 3000 bases: walks of ~100 windows
-                                       ("tb_emul", ["300", "4"])])
+                                       ("tb_emul", ["300", "4"]), ("tb_emul", ["400", "9", "2989"])])  # reads of up to 3000 bases
 def test_device_functions_on_cpu(built, prog, args, tmp_path):
     """the HD functions the kernels are made of (nw_core.cuh, nwp_core.cuh, extend.cuh, traceback.cuh) + render.c,
     compiled for the host and stepped as a 32-lane warp, against the oracle"""
