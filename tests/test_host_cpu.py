@@ -289,6 +289,26 @@ def test_no_gpu_means_error_not_fallback(built):
     assert e.value.code == -1
 
 
+def test_command_lines_fail_loudly_without_a_gpu(built, tmp_path):
+    """no CPU fallback behind the command lines either: without an sm_100 device bin/IMSAME and bin/IMSAME_allvsall
+    end with the reference's error form (terror: message on stdout, exit status 255) and write no record"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    d, o = tmp_path / "s", tmp_path / "o"
+    d.mkdir(); o.mkdir()
+    (d / "a.fasta").write_bytes(open(os.path.join(G, "dirty.q.fa"), "rb").read())
+    (d / "b.fasta").write_bytes(open(os.path.join(G, "dirty.db.fa"), "rb").read())
+    r = subprocess.run([os.path.join(hp.ROOT, "bin", "IMSAME"), "-query", str(d / "a.fasta"), "-db", str(d / "b.fasta"), "-out",
+                        str(o / "x.align")], capture_output=True, text=True)
+    assert r.returncode == 255 and "ERR**** GPU hot path failed: no usable sm_100 CUDA device" in r.stdout
+    assert "from the query were found" not in r.stdout and os.path.getsize(o / "x.align") == 0
+    r = subprocess.run([os.path.join(hp.ROOT, "bin", "IMSAME_allvsall"), str(d), "0.5", "0.5", "2", "fasta", str(o)],
+                       capture_output=True, text=True)
+    assert r.returncode == 255 and "ERR**** no usable GPU" in r.stdout
+    assert not [n for n in os.listdir(o) if n != "x.align"]
+
+
 def test_cli_flags_and_errors(built, tmp_path):
     exe = os.path.join(hp.ROOT, "bin", "IMSAME")
     r = subprocess.run([exe, "--help"], capture_output=True, text=True)
